@@ -1,0 +1,118 @@
+#!/usr/bin/env python3
+"""Build the reference's own kernel sources into CPU libraries under oracle/_ref/.
+
+TEST INFRASTRUCTURE ONLY.  The reference host program cannot be built in this image (no
+Boost/GDAL/OpenCL headers), but its kernel sources are plain OpenCL C
+and compile with g++ through oracle/ref_shim/cl_shim.h.  This script
+
+  1. reads the .clh/.clc files WHERE THEY LIE under /root/reference (never copied into the
+     repository), in the order the reference's prepareCode() concatenates them
+     (src/Schemes/CSchemeGodunov.cpp:483-504, CSchemeMUSCLHancock.cpp:324-345,
+     CSchemeInertial.cpp:204-220), after the universal header the program wrapper always
+     prepends (src/OpenCL/Executors/COCLProgram.cpp);
+  2. applies two mechanical rewrites (vector-constructor syntax, work-group attributes);
+  3. writes the translation unit to a temp directory and compiles it with
+     g++ -O2 -ffp-contract=off -fopenmp into oracle/_ref/ref_<variant>.so.
+
+Variants: scheme in {godunov, mh, inertial} x precision {f64, f32} x timestep {dyn, fix}
+x friction {fric, nofric}.  `python oracle/build_ref.py` builds the set the tests use.
+"""
+import os
+import re
+import subprocess
+import sys
+import tempfile
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_SRC = os.environ.get("HIPIMS_REFERENCE", "/root/reference") + "/src"
+OUT = os.path.join(HERE, "_ref")
+
+_COMMON_H = ["Domain/Cartesian/CLDomainCartesian.clh", "Schemes/CLFriction.clh"]
+_COMMON_C = ["Domain/Cartesian/CLDomainCartesian.clc", "Schemes/CLFriction.clc"]
+PROGRAMS = {
+    "godunov": (_COMMON_H + ["Solvers/CLSolverHLLC.clh", "Schemes/CLDynamicTimestep.clh", "Schemes/CLSchemeGodunov.clh",
+                             "Boundaries/CLBoundaries.clh"],
+                _COMMON_C + ["Solvers/CLSolverHLLC.clc", "Schemes/CLDynamicTimestep.clc", "Schemes/CLSchemeGodunov.clc",
+                             "Boundaries/CLBoundaries.clc"], "SHIM_SCHEME_GODUNOV"),
+    "mh": (_COMMON_H + ["Schemes/Limiters/CLSlopeLimiterMINMOD.clh", "Solvers/CLSolverHLLC.clh",
+                        "Schemes/CLDynamicTimestep.clh", "Schemes/CLSchemeMUSCLHancock.clh",
+                        "Boundaries/CLBoundaries.clh"],
+           _COMMON_C + ["Schemes/Limiters/CLSlopeLimiterMINMOD.clc", "Solvers/CLSolverHLLC.clc",
+                        "Schemes/CLDynamicTimestep.clc", "Schemes/CLSchemeMUSCLHancock.clc",
+                        "Boundaries/CLBoundaries.clc"], "SHIM_SCHEME_MUSCL_HANCOCK"),
+    "inertial": (_COMMON_H + ["Schemes/CLDynamicTimestep.clh", "Schemes/CLSchemeInertial.clh",
+                              "Boundaries/CLBoundaries.clh"],
+                 _COMMON_C + ["Schemes/CLDynamicTimestep.clc", "Schemes/CLSchemeInertial.clc",
+                              "Boundaries/CLBoundaries.clc"], "SHIM_SCHEME_INERTIAL"),
+}
+
+DEFAULT_VARIANTS = [
+    "godunov_f64_dyn_fric", "godunov_f64_dyn_nofric", "godunov_f64_fix_fric", "godunov_f32_dyn_fric",
+    "mh_f64_dyn_fric", "mh_f32_dyn_fric", "inertial_f64_dyn_fric", "inertial_f32_dyn_fric",
+]
+
+_VEC_CTOR = re.compile(r"\(\s*(cl_double[248]|uint2|cl_uint2)\s*\)\s*\(")
+_WG_ATTR = re.compile(r"__attribute__\s*\(\(\s*reqd_work_group_size\s*\([^)]*\)\s*\)\)")
+
+
+def reference_available():
+    return os.path.isdir(REF_SRC)
+
+
+def _translation_unit(scheme):
+    headers, sources, macro = PROGRAMS[scheme]
+    parts = ['#include "cl_shim.h"\n']
+    for rel in ["OpenCL/Executors/CLUniversalHeader.clh"] + headers + sources:
+        with open(os.path.join(REF_SRC, rel), "r", encoding="latin-1") as f:
+            text = f.read()
+        text = _VEC_CTOR.sub(lambda mt: "shim_make<%s>(" % mt.group(1), text)
+        text = _WG_ATTR.sub("", text)
+        parts.append('#line 1 "%s"\n%s\n' % (rel, text))
+    parts.append('#include "ref_unit.inc"\n')
+    return "".join(parts), macro
+
+
+def build_variant(name, force=False):
+    scheme, prec, ts, fric = name.split("_")
+    out = os.path.join(OUT, "ref_%s.so" % name)
+    if os.path.exists(out) and not force:
+        deps = [os.path.join(HERE, "ref_shim", "cl_shim.h"), os.path.join(HERE, "ref_shim", "ref_unit.inc"),
+                os.path.join(HERE, "sim_driver.h"), os.path.join(HERE, "hpo_api.h"), os.path.abspath(__file__)]
+        if all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
+            return out
+    os.makedirs(OUT, exist_ok=True)
+    tu, macro = _translation_unit(scheme)
+    flags = ["-D" + macro]
+    if prec == "f32":
+        flags += ["-DSHIM_REAL=float", "-fsingle-precision-constant"]
+    if ts == "fix":
+        flags.append("-DSHIM_TIMESTEP_FIXED")
+    if fric == "fric":
+        flags.append("-DSHIM_FRICTION")
+    with tempfile.TemporaryDirectory(prefix="hpo_ref_") as tmp:
+        src = os.path.join(tmp, "unit_%s.cpp" % name)
+        with open(src, "w") as f:
+            f.write(tu)
+        cmd = ["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fopenmp", "-fpermissive", "-w", "-shared", "-fPIC",
+               "-I", os.path.join(HERE, "ref_shim"), "-I", HERE] + flags + [src, "-o", out]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("reference shim build failed for %s:\n%s" % (name, res.stderr[-4000:]))
+    return out
+
+
+def build_all(variants=None, force=False):
+    if not reference_available():
+        return []
+    variants = variants or DEFAULT_VARIANTS
+    with ThreadPoolExecutor(max_workers=min(8, len(variants))) as ex:
+        return list(ex.map(lambda v: build_variant(v, force), variants))
+
+
+if __name__ == "__main__":
+    if not reference_available():
+        print("reference tree not present at %s; nothing built" % REF_SRC)
+        sys.exit(0)
+    for path in build_all(sys.argv[1:] or None, force=True):
+        print("built", os.path.relpath(path, os.path.dirname(HERE)))

@@ -1,0 +1,140 @@
+"""The oracle (oracle/hipims_oracle.cpp) must be BIT-IDENTICAL to the reference's own kernel
+sources compiled through oracle/ref_shim (both -ffp-contract=off).  CPU only; skipped when
+neither /root/reference nor a prebuilt oracle/_ref library is available."""
+import numpy as np
+import pytest
+
+from hipims_ocl_b200 import config as hc
+from oracle import cpu_sim
+from tests.helpers import add_standard_boundaries, dtype_of, make_cfg, scenario
+
+
+def _pair(cfg):
+    if not cpu_sim.ref_available(cfg):
+        pytest.skip("reference tree / prebuilt reference library not available")
+    return cpu_sim.CpuSim("oracle", cfg), cpu_sim.CpuSim("ref", cfg)
+
+
+def _same(a, b):
+    # bit-identical apart from the sign of zero
+    np.testing.assert_array_equal(a, b)
+
+
+@pytest.mark.parametrize("precision", ["double", "single"])
+@pytest.mark.parametrize("scheme", ["godunov", "inertial"])
+def test_single_step_kernel(scheme, precision):
+    rows, cols = 61, 83
+    cfg = make_cfg(scheme, precision, rows, cols)
+    orc, ref = _pair(cfg)
+    dt = dtype_of(precision)
+    for seed in (1, 2, 3):
+        bed, st, man = scenario("wetdry", rows, cols, dt, seed)
+        for step_dt in (0.05, 0.0, -0.01):
+            d_o = np.full_like(st, -123.0)
+            d_r = np.full_like(st, -123.0)
+            orc.k_step(step_dt, bed, st, d_o, man)
+            ref.k_step(step_dt, bed, st, d_r, man)
+            _same(d_o, d_r)
+            if step_dt > 0:
+                assert (d_o != -123.0).any() and (d_o == -123.0).any()  # ring (and dry stencils) untouched
+    assert abs(orc.k_reduce(st, bed) - ref.k_reduce(st, bed)) == 0.0
+
+
+def test_godunov_without_friction():
+    rows, cols = 40, 52
+    cfg = make_cfg("godunov", "double", rows, cols, friction=False)
+    orc, ref = _pair(cfg)
+    bed, st, man = scenario("wetdry", rows, cols, np.float64, 5)
+    d_o, d_r = np.full_like(st, -7.0), np.full_like(st, -7.0)
+    orc.k_step(0.04, bed, st, d_o, man)
+    ref.k_step(0.04, bed, st, d_r, man)
+    _same(d_o, d_r)
+
+
+@pytest.mark.parametrize("precision", ["double", "single"])
+def test_muscl_hancock_kernels(precision):
+    rows, cols = 57, 66
+    cfg = make_cfg("muscl-hancock", precision, rows, cols)
+    orc, ref = _pair(cfg)
+    dt = dtype_of(precision)
+    for seed in (4, 5):
+        bed, st, man = scenario("wetdry", rows, cols, dt, seed)
+        f_o = [np.full_like(st, -5.0) for _ in range(4)]
+        f_r = [np.full_like(st, -5.0) for _ in range(4)]
+        orc.k_mch_1st(0.03, bed, st, f_o)
+        ref.k_mch_1st(0.03, bed, st, f_r)
+        for a, b in zip(f_o, f_r):
+            _same(a, b)
+        s_o, s_r = st.copy(), st.copy()
+        orc.k_mch_2nd(0.03, s_o, bed, man, f_o)
+        ref.k_mch_2nd(0.03, s_r, bed, man, f_r)
+        _same(s_o, s_r)
+        assert (s_o != st).any()
+
+
+CASES = [
+    # scheme, precision, scenario, boundaries, n, iterations, extra config
+    ("godunov", "double", "dambreak", "none", 64, 60, {}),
+    ("godunov", "double", "dambreak-dry", "none", 64, 60, {}),
+    ("godunov", "single", "dambreak", "none", 64, 60, {}),
+    ("godunov", "double", "pluvial", "rain+loss", 50, 400, {"delta": 2.0}),
+    ("godunov", "double", "pluvial-wet", "gridded", 48, 150, {}),
+    ("godunov", "double", "valley", "cells", 48, 150, {}),
+    ("godunov", "double", "dambreak", "none", 48, 40, {"dynamic": False, "fixed_dt": 0.01}),
+    ("godunov", "double", "wetdry", "rain", 45, 80, {"quirks": 0}),
+    ("inertial", "double", "pluvial-wet", "rain", 48, 200, {}),
+    ("inertial", "single", "valley", "cells", 48, 150, {}),
+    ("muscl-hancock", "double", "dambreak", "none", 64, 50, {}),
+    ("muscl-hancock", "double", "dambreak-dry", "none", 64, 50, {}),
+    ("muscl-hancock", "single", "dambreak", "none", 48, 50, {}),
+    ("muscl-hancock", "double", "valley", "cells", 48, 120, {}),
+    ("muscl-hancock", "double", "pluvial-wet", "rain", 48, 200, {"quirks": hc.QUIRKS_REFERENCE | hc.QUIRK_MH_NO_BOUNDARIES}),
+]
+
+
+@pytest.mark.parametrize("scheme,precision,scen,bdy,n,iters,extra", CASES)
+def test_multi_step_runs(scheme, precision, scen, bdy, n, iters, extra):
+    cfg = make_cfg(scheme, precision, n, n, **extra)
+    orc, ref = _pair(cfg)
+    bed, st, man = scenario(scen, n, n, dtype_of(precision))
+    for sim in (orc, ref):
+        sim.upload(st, bed, man)
+        add_standard_boundaries(sim, cfg, bdy)
+        sim.set_target(1.0e6)
+    done = 0
+    for chunk in (1, 2, 7, iters - 10):
+        orc.iterate(chunk)
+        ref.iterate(chunk)
+        done += chunk
+        assert orc.stats() == ref.stats(), "clock diverged after %d iterations" % done
+        a_o, b_o = orc.download_both()
+        a_r, b_r = ref.download_both()
+        _same(a_o, a_r)
+        _same(b_o, b_r)
+    s = orc.stats()
+    assert s["batch_successful"] == iters and s["time"] > 0.0
+    assert np.isfinite(orc.download()).all()
+
+
+def test_sync_point_suspension_and_update():
+    """dt goes negative at the sync time (CLDynamicTimestep.clc:118-124), iterations are then
+    skipped; a new target plus tst_UpdateTimestep resumes (CSchemeGodunov.cpp:1164-1210)."""
+    n = 40
+    cfg = make_cfg("godunov", "double", n, n)
+    orc, ref = _pair(cfg)
+    bed, st, man = scenario("dambreak", n, n, np.float64)
+    for sim in (orc, ref):
+        sim.upload(st, bed, man)
+        sim.set_target(0.25)
+        sim.iterate(30)
+    so, sr = orc.stats(), ref.stats()
+    assert so == sr
+    assert so["time"] == 0.25 and so["timestep"] < 0.0 and so["batch_skipped"] > 0
+    for sim in (orc, ref):
+        sim.set_target(0.5)
+        sim.update_timestep()
+        sim.reset_counters()
+        sim.iterate(10)
+    assert orc.stats() == ref.stats()
+    _same(orc.download(), ref.download())
+    assert orc.stats()["time"] > 0.25

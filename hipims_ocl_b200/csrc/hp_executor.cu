@@ -1,0 +1,613 @@
+// hp_executor.cu -- implementation of the C ABI declared in include/hipims_cuda.h.
+//
+// Owns what the reference's scheme classes own through the OpenCL wrappers: the device buffers
+// (src/Schemes/CSchemeGodunov.cpp:789-893), the kernel launch sequence of one iteration
+// (:1617-1666; MUSCL-Hancock src/Schemes/CSchemeMUSCLHancock.cpp:646-680) and the data movement of
+// prepareSimulation / readDomainAll / CDomainLink.  One CUDA stream per executor; batches of
+// iterations are replayed as CUDA graphs so that small domains are not launch-bound (the
+// reference blocks the host once per batch, CSchemeGodunov.cpp:1337-1341 -- so do we).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/hipims_cuda.h"
+#include "hp_comm.h"
+#include "hp_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define HP_CUDA(expr)                                                                                              \
+    do {                                                                                                           \
+        cudaError_t e__ = (expr);                                                                                  \
+        if (e__ != cudaSuccess)                                                                                    \
+            return fail(e__ == cudaErrorMemoryAllocation ? HP_ERR_OOM : HP_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, \
+                        cudaGetErrorString(e__), __FILE__, __LINE__);                                              \
+    } while (0)
+
+template <class R> hp::Clock<R> make_clock(double t, double dt, double th, double target) {
+    hp::Clock<R> c;
+    c.time = static_cast<R>(t); c.timestep = static_cast<R>(dt); c.time_hydro = static_cast<R>(th);
+    c.time_target = static_cast<R>(target); c.batch_timesteps = R(0); c.batch_successful = 0; c.batch_skipped = 0;
+    return c;
+}
+
+struct Boundary {
+    int kind = 0;  // 0 uniform, 1 gridded, 2 cell
+    hp_bdy_uniform uniform{}; hp_bdy_gridded gridded{}; hp_bdy_cell cell{};
+    void* series = nullptr; long long* relations = nullptr; unsigned long long count = 0;
+};
+
+}  // namespace
+
+struct hp_executor {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaDeviceProp prop{};
+};
+
+struct hp_scheme {
+    hp_executor* ex = nullptr;
+    hp_scheme_config cfg{};
+    hp::Grid grid{};
+    hp::ParamsD params{};
+    const hp::KernelTable* K = nullptr;
+    size_t rb = 8, plane_bytes = 0;
+    hp::Planes A{}, B{};
+    void *bed = nullptr, *manning = nullptr, *clock = nullptr;
+    unsigned long long* max_bits = nullptr;
+    unsigned int* ticket = nullptr;
+    void* staging = nullptr; size_t staging_bytes = 0; int staging_rows = 0;
+    std::vector<Boundary> bdys;
+    bool use_alt = false;
+    uint64_t iterations = 0, launches = 0;
+    // graphs: [0] one pair of iterations (A->B, B->A), [1] kGraphPairs pairs
+    cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};
+    int graph_launches[2] = {0, 0};
+    hp::Comm* comm = nullptr;
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t ev_edges = nullptr, ev_halo = nullptr;
+};
+
+namespace {
+
+constexpr int kGraphPairs = 8;
+
+void drop_graphs(hp_scheme* s) {
+    for (auto& g : s->graph_exec) { if (g) cudaGraphExecDestroy(g); g = nullptr; }
+}
+
+hp::Planes& src_planes(hp_scheme* s, bool alt) { return alt ? s->B : s->A; }
+hp::Planes& dst_planes(hp_scheme* s, bool alt) { return alt ? s->A : s->B; }
+
+hp::StepArgs base_args(hp_scheme* s, bool alt) {
+    hp::StepArgs a{};
+    a.src = src_planes(s, alt); a.dst = dst_planes(s, alt);
+    a.bed = s->bed; a.manning = s->manning; a.clock = s->clock; a.max_bits = s->max_bits; a.ticket = s->ticket;
+    a.grid = s->grid; a.params = s->params; a.y0 = s->grid.own_y0; a.y1 = s->grid.own_y1;
+    a.reduce_mode = hp::kReduceNone; a.finalize = 1; a.total_ctas = 0;
+    return a;
+}
+
+int apply_boundaries(hp_scheme* s, const hp::Planes& state) {
+    int n = 0;
+    const auto& g = s->grid;
+    const bool q6 = (s->cfg.quirks & HP_QUIRK_BDY_COVERAGE) != 0;
+    const int cover_x = q6 ? (g.cols / 8) * 8 : g.cols, cover_y = q6 ? (g.grows / 8) * 8 : g.grows;
+    for (const auto& b : s->bdys) {
+        if (b.kind == 0) {
+            hp::BdyUniformArgs a{state, s->bed, s->clock, b.series, g, b.uniform.entries, b.uniform.definition,
+                                 b.uniform.interval, b.uniform.length, cover_x, cover_y};
+            n += s->K->bdy_uniform(static_cast<int>(s->rb), a, s->ex->stream);
+        } else if (b.kind == 1) {
+            hp::BdyGriddedArgs a{state, s->clock, b.series, g, b.gridded.interval, b.gridded.resolution, b.gridded.offset_x,
+                                 b.gridded.offset_y, s->cfg.delta, b.gridded.entries, b.gridded.definition, b.gridded.rows,
+                                 b.gridded.cols, cover_x, cover_y};
+            n += s->K->bdy_gridded(static_cast<int>(s->rb), a, s->ex->stream);
+        } else {
+            hp::BdyCellArgs a{state, s->bed, s->clock, b.series, b.relations, g, s->params, b.cell.entries, b.count,
+                              b.cell.interval, b.cell.length, b.cell.def_depth, b.cell.def_discharge};
+            n += s->K->bdy_cell(static_cast<int>(s->rb), a, s->ex->stream);
+        }
+    }
+    return n;
+}
+
+// One iteration = CSchemeGodunov::scheduleIteration / CSchemeMUSCLHancock::scheduleIteration.
+int enqueue_iteration(hp_scheme* s, bool alt, int* launched) {
+    const int rb = static_cast<int>(s->rb);
+    cudaStream_t st = s->ex->stream;
+    hp::StepArgs a = base_args(s, alt);
+    int n = 0;
+    const bool mh = s->cfg.scheme == HP_SCHEME_MUSCL_HANCOCK;
+    if (!(mh && (s->cfg.quirks & HP_QUIRK_MH_NO_BOUNDARIES))) n += apply_boundaries(s, a.src);
+    if (s->cfg.dynamic_timestep) {
+        if (mh || !(s->cfg.quirks & HP_QUIRK_REDUCE_BUFFER_A)) a.reduce_mode = hp::kReduceDst;
+        else a.reduce_mode = alt ? hp::kReduceDst : hp::kReduceSrc;   // Q1: always buffer A
+    }
+    if (s->comm == nullptr) {
+        a.finalize = 1;
+        n += s->K->step(static_cast<int>(s->cfg.scheme), rb, a, st);
+    } else {
+        // Row strips: edge rows first, their halo exchange overlaps the interior rows, then the
+        // wave-speed maximum is all-reduced on the device and one thread runs the time controller.
+        a.finalize = 0;
+        const int halo = mh ? 2 : 1;
+        const int y0 = s->grid.own_y0, y1 = s->grid.own_y1;
+        const int e0 = y0 + halo < y1 ? y0 + halo : y1, e1 = y1 - halo > e0 ? y1 - halo : e0;
+        hp::StepArgs lo = a, hi = a, mid = a;
+        lo.y1 = e0; hi.y0 = e1; mid.y0 = e0; mid.y1 = e1;
+        n += s->K->step(static_cast<int>(s->cfg.scheme), rb, lo, st);
+        n += s->K->step(static_cast<int>(s->cfg.scheme), rb, hi, st);
+        if (cudaEventRecord(s->ev_edges, st) != cudaSuccess) return fail(HP_ERR_CUDA, "cudaEventRecord failed");
+        if (cudaStreamWaitEvent(s->comm_stream, s->ev_edges, 0) != cudaSuccess) return fail(HP_ERR_CUDA, "cudaStreamWaitEvent failed");
+        const char* err = hp::comm_exchange_halos(s->comm, a.dst, s->grid, halo, s->rb, s->comm_stream);
+        if (err) return fail(HP_ERR_NCCL, "halo exchange: %s", err);
+        if (cudaEventRecord(s->ev_halo, s->comm_stream) != cudaSuccess) return fail(HP_ERR_CUDA, "cudaEventRecord failed");
+        n += s->K->step(static_cast<int>(s->cfg.scheme), rb, mid, st);
+        if (cudaStreamWaitEvent(st, s->ev_halo, 0) != cudaSuccess) return fail(HP_ERR_CUDA, "cudaStreamWaitEvent failed");
+        err = hp::comm_allreduce_max(s->comm, s->max_bits, st);
+        if (err) return fail(HP_ERR_NCCL, "allreduce: %s", err);
+        n += s->K->advance(rb, a, st);
+    }
+    if (launched) *launched += n;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(HP_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+    return HP_OK;
+}
+
+int build_graph(hp_scheme* s, int slot, int pairs) {
+    cudaStream_t st = s->ex->stream;
+    cudaGraph_t graph = nullptr;
+    HP_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    int launched = 0, rc = HP_OK;
+    for (int p = 0; p < pairs && rc == HP_OK; ++p) {
+        rc = enqueue_iteration(s, false, &launched);
+        if (rc == HP_OK) rc = enqueue_iteration(s, true, &launched);
+    }
+    cudaError_t e = cudaStreamEndCapture(st, &graph);
+    if (rc != HP_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess) return fail(HP_ERR_CUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&s->graph_exec[slot], graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return fail(HP_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+    s->graph_launches[slot] = launched;
+    return HP_OK;
+}
+
+template <class T> int dev_alloc(T** p, size_t bytes) {
+    HP_CUDA(cudaMalloc(reinterpret_cast<void**>(p), bytes));
+    HP_CUDA(cudaMemset(*p, 0, bytes));
+    return HP_OK;
+}
+
+int alloc_planes(hp_scheme* s, hp::Planes& p) {
+    int rc;
+    if ((rc = dev_alloc(reinterpret_cast<char**>(&p.eta), s->plane_bytes))) return rc;
+    if ((rc = dev_alloc(reinterpret_cast<char**>(&p.emax), s->plane_bytes))) return rc;
+    if ((rc = dev_alloc(reinterpret_cast<char**>(&p.qx), s->plane_bytes))) return rc;
+    if ((rc = dev_alloc(reinterpret_cast<char**>(&p.qy), s->plane_bytes))) return rc;
+    return HP_OK;
+}
+void free_planes(hp::Planes& p) { cudaFree(p.eta); cudaFree(p.emax); cudaFree(p.qx); cudaFree(p.qy); p = hp::Planes{}; }
+
+int write_clock(hp_scheme* s, double t, double dt, double th, double target) {
+    if (s->rb == 8) { auto c = make_clock<double>(t, dt, th, target); HP_CUDA(cudaMemcpyAsync(s->clock, &c, sizeof(c), cudaMemcpyHostToDevice, s->ex->stream)); }
+    else { auto c = make_clock<float>(t, dt, th, target); HP_CUDA(cudaMemcpyAsync(s->clock, &c, sizeof(c), cudaMemcpyHostToDevice, s->ex->stream)); }
+    HP_CUDA(cudaStreamSynchronize(s->ex->stream));
+    return HP_OK;
+}
+
+// writes one real-typed field of the device clock
+int write_clock_field(hp_scheme* s, int index, double value) {
+    double d = value; float f = static_cast<float>(value);
+    char* base = static_cast<char*>(s->clock) + static_cast<size_t>(index) * s->rb;
+    HP_CUDA(cudaMemcpyAsync(base, s->rb == 8 ? static_cast<void*>(&d) : static_cast<void*>(&f), s->rb, cudaMemcpyHostToDevice,
+                            s->ex->stream));
+    HP_CUDA(cudaStreamSynchronize(s->ex->stream));
+    return HP_OK;
+}
+
+int rows_to_device(hp_scheme* s, const void* host_aos, int row0, int nrows, bool both) {
+    const size_t row_bytes = static_cast<size_t>(s->grid.cols) * 4 * s->rb;
+    const char* h = static_cast<const char*>(host_aos);
+    for (int r = 0; r < nrows; r += s->staging_rows) {
+        const int n = nrows - r < s->staging_rows ? nrows - r : s->staging_rows;
+        HP_CUDA(cudaMemcpyAsync(s->staging, h + static_cast<size_t>(r) * row_bytes, static_cast<size_t>(n) * row_bytes,
+                                cudaMemcpyHostToDevice, s->ex->stream));
+        if (both) {
+            s->launches += s->K->aos_to_soa(static_cast<int>(s->rb), s->staging, s->A, s->grid, row0 + r, n, s->ex->stream);
+            s->launches += s->K->aos_to_soa(static_cast<int>(s->rb), s->staging, s->B, s->grid, row0 + r, n, s->ex->stream);
+        } else {
+            s->launches += s->K->aos_to_soa(static_cast<int>(s->rb), s->staging, src_planes(s, s->use_alt), s->grid, row0 + r, n,
+                                            s->ex->stream);
+        }
+    }
+    HP_CUDA(cudaGetLastError());
+    return HP_OK;
+}
+
+int rows_to_host(hp_scheme* s, const hp::Planes& p, void* host_aos, int row0, int nrows) {
+    const size_t row_bytes = static_cast<size_t>(s->grid.cols) * 4 * s->rb;
+    char* h = static_cast<char*>(host_aos);
+    for (int r = 0; r < nrows; r += s->staging_rows) {
+        const int n = nrows - r < s->staging_rows ? nrows - r : s->staging_rows;
+        s->launches += s->K->soa_to_aos(static_cast<int>(s->rb), p, s->staging, s->grid, row0 + r, n, s->ex->stream);
+        HP_CUDA(cudaMemcpyAsync(h + static_cast<size_t>(r) * row_bytes, s->staging, static_cast<size_t>(n) * row_bytes,
+                                cudaMemcpyDeviceToHost, s->ex->stream));
+    }
+    HP_CUDA(cudaStreamSynchronize(s->ex->stream));
+    return HP_OK;
+}
+
+int upload_series(hp_scheme* s, const double* host, size_t count, size_t padded, void** out) {
+    // converted to the working precision like the reference's host does before upload
+    std::vector<char> tmp(padded * s->rb, 0);
+    if (s->rb == 8) { double* d = reinterpret_cast<double*>(tmp.data()); for (size_t i = 0; i < count; ++i) d[i] = host[i]; }
+    else { float* f = reinterpret_cast<float*>(tmp.data()); for (size_t i = 0; i < count; ++i) f[i] = static_cast<float>(host[i]); }
+    HP_CUDA(cudaMalloc(out, tmp.size()));
+    HP_CUDA(cudaMemcpy(*out, tmp.data(), tmp.size(), cudaMemcpyHostToDevice));
+    return HP_OK;
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+int hp_abi_version(void) { return HP_ABI_VERSION; }
+const char* hp_last_error(void) { return g_last_error.c_str(); }
+
+int hp_device_count(int* count) {
+    if (!count) return fail(HP_ERR_INVALID, "count is null");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        *count = 0;
+        cudaGetLastError();
+        return fail(HP_ERR_NO_DEVICE, "no CUDA device available (%s); this library has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    *count = n;
+    return HP_OK;
+}
+
+int hp_executor_create(int device_ordinal, void* external_stream, hp_executor** out) {
+    if (!out) return fail(HP_ERR_INVALID, "out is null");
+    int n = 0, rc = hp_device_count(&n);
+    if (rc != HP_OK) return rc;
+    if (device_ordinal < 0 || device_ordinal >= n) return fail(HP_ERR_INVALID, "device ordinal %d out of range [0,%d)", device_ordinal, n);
+    HP_CUDA(cudaSetDevice(device_ordinal));
+    hp_executor* ex = new hp_executor();
+    ex->device = device_ordinal;
+    HP_CUDA(cudaGetDeviceProperties(&ex->prop, device_ordinal));
+    if (ex->prop.major < 10) {
+        const int major = ex->prop.major, minor = ex->prop.minor;
+        delete ex;
+        return fail(HP_ERR_NO_DEVICE, "device is sm_%d%d; this library is built for sm_100a (B200) only", major, minor);
+    }
+    if (external_stream) { ex->stream = static_cast<cudaStream_t>(external_stream); ex->own_stream = false; }
+    else { HP_CUDA(cudaStreamCreateWithFlags(&ex->stream, cudaStreamNonBlocking)); ex->own_stream = true; }
+    HP_CUDA(cudaEventCreate(&ex->ev0));
+    HP_CUDA(cudaEventCreate(&ex->ev1));
+    *out = ex;
+    return HP_OK;
+}
+
+void hp_executor_destroy(hp_executor* ex) {
+    if (!ex) return;
+    cudaSetDevice(ex->device);
+    if (ex->ev0) cudaEventDestroy(ex->ev0);
+    if (ex->ev1) cudaEventDestroy(ex->ev1);
+    if (ex->own_stream && ex->stream) cudaStreamDestroy(ex->stream);
+    delete ex;
+}
+
+int hp_executor_describe(hp_executor* ex, char* name, size_t name_len, int* sm_count, size_t* total_mem) {
+    if (!ex) return fail(HP_ERR_INVALID, "executor is null");
+    if (name && name_len) { strncpy(name, ex->prop.name, name_len - 1); name[name_len - 1] = 0; }
+    if (sm_count) *sm_count = ex->prop.multiProcessorCount;
+    if (total_mem) *total_mem = ex->prop.totalGlobalMem;
+    return HP_OK;
+}
+
+int hp_executor_finish(hp_executor* ex) {
+    if (!ex) return fail(HP_ERR_INVALID, "executor is null");
+    HP_CUDA(cudaStreamSynchronize(ex->stream));
+    return HP_OK;
+}
+int hp_executor_timer_start(hp_executor* ex) {
+    if (!ex) return fail(HP_ERR_INVALID, "executor is null");
+    HP_CUDA(cudaEventRecord(ex->ev0, ex->stream));
+    return HP_OK;
+}
+int hp_executor_timer_stop(hp_executor* ex, float* ms) {
+    if (!ex || !ms) return fail(HP_ERR_INVALID, "null argument");
+    HP_CUDA(cudaEventRecord(ex->ev1, ex->stream));
+    HP_CUDA(cudaEventSynchronize(ex->ev1));
+    HP_CUDA(cudaEventElapsedTime(ms, ex->ev0, ex->ev1));
+    return HP_OK;
+}
+
+int hp_scheme_create(hp_executor* ex, const hp_scheme_config* cfg, hp_scheme** out) {
+    if (!ex || !cfg || !out) return fail(HP_ERR_INVALID, "null argument");
+    if (cfg->struct_size != sizeof(hp_scheme_config)) return fail(HP_ERR_INVALID, "hp_scheme_config size mismatch (ABI %d)", HP_ABI_VERSION);
+    if (cfg->scheme > HP_SCHEME_INERTIAL) return fail(HP_ERR_INVALID, "unknown scheme %u", cfg->scheme);
+    if (cfg->real_bytes != 4 && cfg->real_bytes != 8) return fail(HP_ERR_INVALID, "real_bytes must be 4 or 8");
+    if (cfg->cols < 3 || cfg->rows < 3 || cfg->cols > 0x3fffffff || cfg->rows > 0x3fffffff) return fail(HP_ERR_INVALID, "bad domain size");
+    if (!(cfg->delta > 0.0)) return fail(HP_ERR_INVALID, "delta must be positive");
+    const uint64_t own = cfg->rows - cfg->halo_south - cfg->halo_north;
+    if (cfg->halo_south + cfg->halo_north >= cfg->rows || cfg->row_offset < cfg->halo_south ||
+        cfg->row_offset + own + cfg->halo_north > cfg->global_rows)
+        return fail(HP_ERR_INVALID, "strip geometry inconsistent (rows=%llu offset=%llu global=%llu)", (unsigned long long)cfg->rows,
+                    (unsigned long long)cfg->row_offset, (unsigned long long)cfg->global_rows);
+    HP_CUDA(cudaSetDevice(ex->device));
+    hp_scheme* s = new hp_scheme();
+    s->ex = ex; s->cfg = *cfg; s->rb = cfg->real_bytes;
+    s->K = (cfg->options & HP_OPT_STRICT_FP) ? &hp::strict_kernels() : &hp::fast_kernels();
+    hp::Grid& g = s->grid;
+    g.cols = static_cast<int>(cfg->cols); g.rows = static_cast<int>(cfg->rows);
+    g.pitch = (g.cols + 31) / 32 * 32;
+    g.grows = static_cast<int>(cfg->global_rows);
+    g.gy0 = static_cast<int>(cfg->row_offset) - static_cast<int>(cfg->halo_south);
+    g.own_y0 = static_cast<int>(cfg->halo_south); g.own_y1 = g.rows - static_cast<int>(cfg->halo_north);
+    s->params = hp::ParamsD{cfg->dry_threshold, cfg->dry_threshold * 10, cfg->delta, cfg->courant, cfg->end_time,
+                            cfg->fixed_timestep, static_cast<int>(cfg->dynamic_timestep), static_cast<int>(cfg->friction),
+                            cfg->scheme == HP_SCHEME_INERTIAL ? 1 : 0};
+    s->plane_bytes = static_cast<size_t>(g.rows) * g.pitch * s->rb;
+    int rc = HP_OK;
+    do {
+        if ((rc = alloc_planes(s, s->A))) break;
+        if ((rc = alloc_planes(s, s->B))) break;
+        if ((rc = dev_alloc(reinterpret_cast<char**>(&s->bed), s->plane_bytes))) break;
+        if ((rc = dev_alloc(reinterpret_cast<char**>(&s->manning), s->plane_bytes))) break;
+        if ((rc = dev_alloc(reinterpret_cast<char**>(&s->clock), 64))) break;
+        if ((rc = dev_alloc(&s->max_bits, sizeof(unsigned long long)))) break;
+        if ((rc = dev_alloc(&s->ticket, sizeof(unsigned int)))) break;
+        const size_t row_bytes = static_cast<size_t>(g.cols) * 4 * s->rb;
+        size_t rows_fit = (static_cast<size_t>(256) << 20) / row_bytes;
+        if (rows_fit < 1) rows_fit = 1;
+        if (rows_fit > static_cast<size_t>(g.rows)) rows_fit = g.rows;
+        s->staging_rows = static_cast<int>(rows_fit);
+        s->staging_bytes = rows_fit * row_bytes;
+        if ((rc = dev_alloc(reinterpret_cast<char**>(&s->staging), s->staging_bytes))) break;
+        if ((rc = write_clock(s, 0.0, cfg->initial_timestep, 0.0, 0.0))) break;
+    } while (0);
+    if (rc != HP_OK) { hp_scheme_destroy(s); return rc; }
+    *out = s;
+    return HP_OK;
+}
+
+void hp_scheme_destroy(hp_scheme* s) {
+    if (!s) return;
+    cudaSetDevice(s->ex->device);
+    cudaStreamSynchronize(s->ex->stream);
+    drop_graphs(s);
+    if (s->comm) hp::comm_destroy(s->comm);
+    if (s->comm_stream) cudaStreamDestroy(s->comm_stream);
+    if (s->ev_edges) cudaEventDestroy(s->ev_edges);
+    if (s->ev_halo) cudaEventDestroy(s->ev_halo);
+    free_planes(s->A); free_planes(s->B);
+    cudaFree(s->bed); cudaFree(s->manning); cudaFree(s->clock); cudaFree(s->max_bits); cudaFree(s->ticket); cudaFree(s->staging);
+    for (auto& b : s->bdys) { cudaFree(b.series); cudaFree(b.relations); }
+    delete s;
+}
+
+int hp_boundary_add_uniform(hp_scheme* s, const hp_bdy_uniform* conf, const double* series) {
+    if (!s || !conf || !series) return fail(HP_ERR_INVALID, "null argument");
+    if (conf->entries < 2 || !(conf->interval > 0.0)) return fail(HP_ERR_INVALID, "a boundary timeseries is too short");
+    Boundary b; b.kind = 0; b.uniform = *conf;
+    int rc = upload_series(s, series, 2 * static_cast<size_t>(conf->entries), 2 * static_cast<size_t>(conf->entries) + 2, &b.series);
+    if (rc) return rc;
+    s->bdys.push_back(b);
+    drop_graphs(s);
+    return static_cast<int>(s->bdys.size()) - 1;
+}
+
+int hp_boundary_add_gridded(hp_scheme* s, const hp_bdy_gridded* conf, const double* series) {
+    if (!s || !conf || !series) return fail(HP_ERR_INVALID, "null argument");
+    if (conf->entries < 1 || conf->rows < 1 || conf->cols < 1 || !(conf->interval > 0.0) || !(conf->resolution > 0.0))
+        return fail(HP_ERR_INVALID, "bad gridded boundary configuration");
+    Boundary b; b.kind = 1; b.gridded = *conf;
+    const size_t frame = static_cast<size_t>(conf->rows * conf->cols);
+    // the kernel may index frame `entries` (CLBoundaries.clc:229): keep one zero frame of padding
+    int rc = upload_series(s, series, frame * conf->entries, frame * (conf->entries + 1), &b.series);
+    if (rc) return rc;
+    s->bdys.push_back(b);
+    drop_graphs(s);
+    return static_cast<int>(s->bdys.size()) - 1;
+}
+
+int hp_boundary_add_cell(hp_scheme* s, const hp_bdy_cell* conf, const uint64_t* relations, const double* series) {
+    if (!s || !conf || !relations || !series) return fail(HP_ERR_INVALID, "null argument");
+    if (conf->entries < 2 || !(conf->interval > 0.0)) return fail(HP_ERR_INVALID, "a boundary timeseries is too short");
+    Boundary b; b.kind = 2; b.cell = *conf; b.count = conf->relations;
+    // the kernel reads entry base+1 (CLBoundaries.clc:44,49): one padding entry
+    int rc = upload_series(s, series, 4 * static_cast<size_t>(conf->entries), 4 * (static_cast<size_t>(conf->entries) + 1), &b.series);
+    if (rc) return rc;
+    std::vector<long long> local(conf->relations > 0 ? conf->relations : 1, -1);
+    const hp::Grid& g = s->grid;
+    for (uint64_t i = 0; i < conf->relations; ++i) {
+        const uint64_t gx = relations[i] % static_cast<uint64_t>(g.cols), gy = relations[i] / static_cast<uint64_t>(g.cols);
+        if (gy >= static_cast<uint64_t>(g.grows)) { cudaFree(b.series); return fail(HP_ERR_INVALID, "boundary cell %llu outside the domain", (unsigned long long)relations[i]); }
+        const long long y = static_cast<long long>(gy) - g.gy0;
+        local[i] = (y >= 0 && y < g.rows) ? y * g.pitch + static_cast<long long>(gx) : -1;
+    }
+    HP_CUDA(cudaMalloc(reinterpret_cast<void**>(&b.relations), local.size() * sizeof(long long)));
+    HP_CUDA(cudaMemcpy(b.relations, local.data(), local.size() * sizeof(long long), cudaMemcpyHostToDevice));
+    s->bdys.push_back(b);
+    drop_graphs(s);
+    return static_cast<int>(s->bdys.size()) - 1;
+}
+
+int hp_scheme_upload_cells(hp_scheme* s, const void* states, const void* bed, const void* manning) {
+    if (!s || !states || !bed || !manning) return fail(HP_ERR_INVALID, "null argument");
+    HP_CUDA(cudaSetDevice(s->ex->device));
+    const hp::Grid& g = s->grid;
+    const size_t w = static_cast<size_t>(g.cols) * s->rb, dp = static_cast<size_t>(g.pitch) * s->rb;
+    HP_CUDA(cudaMemcpy2DAsync(s->bed, dp, bed, w, w, g.rows, cudaMemcpyHostToDevice, s->ex->stream));
+    HP_CUDA(cudaMemcpy2DAsync(s->manning, dp, manning, w, w, g.rows, cudaMemcpyHostToDevice, s->ex->stream));
+    s->use_alt = false;
+    return rows_to_device(s, states, 0, g.rows, true);
+}
+
+int hp_scheme_download_cells(hp_scheme* s, void* states) {
+    if (!s || !states) return fail(HP_ERR_INVALID, "null argument");
+    HP_CUDA(cudaSetDevice(s->ex->device));
+    return rows_to_host(s, src_planes(s, s->use_alt), states, 0, s->grid.rows);
+}
+
+int hp_scheme_download_both(hp_scheme* s, void* a, void* b) {
+    if (!s || !a || !b) return fail(HP_ERR_INVALID, "null argument");
+    HP_CUDA(cudaSetDevice(s->ex->device));
+    int rc = rows_to_host(s, s->A, a, 0, s->grid.rows);
+    if (rc) return rc;
+    return rows_to_host(s, s->B, b, 0, s->grid.rows);
+}
+
+int hp_scheme_read_rows(hp_scheme* s, uint64_t first_row, uint64_t row_count, void* states) {
+    if (!s || !states) return fail(HP_ERR_INVALID, "null argument");
+    if (first_row + row_count > static_cast<uint64_t>(s->grid.rows)) return fail(HP_ERR_INVALID, "row range outside the scheme");
+    HP_CUDA(cudaSetDevice(s->ex->device));
+    return rows_to_host(s, src_planes(s, s->use_alt), states, static_cast<int>(first_row), static_cast<int>(row_count));
+}
+
+int hp_scheme_write_rows(hp_scheme* s, uint64_t first_row, uint64_t row_count, const void* states) {
+    if (!s || !states) return fail(HP_ERR_INVALID, "null argument");
+    if (first_row + row_count > static_cast<uint64_t>(s->grid.rows)) return fail(HP_ERR_INVALID, "row range outside the scheme");
+    HP_CUDA(cudaSetDevice(s->ex->device));
+    return rows_to_device(s, states, static_cast<int>(first_row), static_cast<int>(row_count), false);
+}
+
+int hp_scheme_set_target_time(hp_scheme* s, double target) {
+    if (!s) return fail(HP_ERR_INVALID, "scheme is null");
+    return write_clock_field(s, 3, target);
+}
+int hp_scheme_force_timestep(hp_scheme* s, double timestep) {
+    if (!s) return fail(HP_ERR_INVALID, "scheme is null");
+    return write_clock_field(s, 1, timestep);
+}
+int hp_scheme_set_clock(hp_scheme* s, double time, double timestep, double th) {
+    if (!s) return fail(HP_ERR_INVALID, "scheme is null");
+    int rc = write_clock_field(s, 0, time);
+    if (!rc) rc = write_clock_field(s, 1, timestep);
+    if (!rc) rc = write_clock_field(s, 2, th);
+    return rc;
+}
+
+int hp_scheme_update_timestep(hp_scheme* s) {
+    if (!s) return fail(HP_ERR_INVALID, "scheme is null");
+    HP_CUDA(cudaSetDevice(s->ex->device));
+    // the reference's reduction kernel stays bound to "Cell states" (Q1); for MUSCL-Hancock that
+    // buffer is the only one.  Here MUSCL-Hancock ping-pongs, so read the current buffer.
+    hp::StepArgs a = base_args(s, false);
+    if (s->cfg.scheme == HP_SCHEME_MUSCL_HANCOCK || !(s->cfg.quirks & HP_QUIRK_REDUCE_BUFFER_A)) a.src = src_planes(s, s->use_alt);
+    else a.src = s->A;
+    s->launches += s->K->reduce_only(static_cast<int>(s->rb), a, s->ex->stream);
+    if (s->comm) { const char* err = hp::comm_allreduce_max(s->comm, s->max_bits, s->ex->stream); if (err) return fail(HP_ERR_NCCL, "allreduce: %s", err); }
+    s->launches += s->K->update_timestep(static_cast<int>(s->rb), a, s->ex->stream);
+    HP_CUDA(cudaGetLastError());
+    return HP_OK;
+}
+
+int hp_scheme_reset_counters(hp_scheme* s) {
+    if (!s) return fail(HP_ERR_INVALID, "scheme is null");
+    int rc = write_clock_field(s, 4, 0.0);
+    if (rc) return rc;
+    HP_CUDA(cudaMemsetAsync(static_cast<char*>(s->clock) + 5 * s->rb, 0, 2 * sizeof(unsigned int), s->ex->stream));
+    return HP_OK;
+}
+
+int hp_scheme_iterate(hp_scheme* s, uint32_t iterations) {
+    if (!s) return fail(HP_ERR_INVALID, "scheme is null");
+    HP_CUDA(cudaSetDevice(s->ex->device));
+    uint32_t left = iterations;
+    const bool use_graph = !(s->cfg.options & HP_OPT_NO_GRAPH) && s->comm == nullptr;
+    int rc = HP_OK;
+    auto direct = [&]() {
+        int launched = 0;
+        rc = enqueue_iteration(s, s->use_alt, &launched);
+        s->launches += launched; s->use_alt = !s->use_alt; ++s->iterations; --left;
+        return rc;
+    };
+    if (use_graph && left >= 2) {
+        if (s->use_alt && direct() != HP_OK) return rc;
+        for (int slot = 1; slot >= 0; --slot) {
+            const uint32_t per = 2u * (slot == 1 ? kGraphPairs : 1);
+            if (left < per) continue;
+            if (!s->graph_exec[slot] && (rc = build_graph(s, slot, static_cast<int>(per / 2))) != HP_OK) return rc;
+            while (left >= per) {
+                HP_CUDA(cudaGraphLaunch(s->graph_exec[slot], s->ex->stream));
+                s->launches += s->graph_launches[slot]; s->iterations += per; left -= per;
+            }
+        }
+    }
+    while (left > 0) if (direct() != HP_OK) return rc;
+    return HP_OK;
+}
+
+int hp_scheme_sync(hp_scheme* s) {
+    if (!s) return fail(HP_ERR_INVALID, "scheme is null");
+    HP_CUDA(cudaStreamSynchronize(s->ex->stream));
+    HP_CUDA(cudaGetLastError());
+    return HP_OK;
+}
+
+int hp_scheme_read_stats(hp_scheme* s, hp_scheme_stats* out) {
+    if (!s || !out) return fail(HP_ERR_INVALID, "null argument");
+    HP_CUDA(cudaSetDevice(s->ex->device));
+    char buf[64];
+    HP_CUDA(cudaMemcpyAsync(buf, s->clock, 64, cudaMemcpyDeviceToHost, s->ex->stream));
+    HP_CUDA(cudaStreamSynchronize(s->ex->stream));
+    if (s->rb == 8) {
+        hp::Clock<double> c; memcpy(&c, buf, sizeof(c));
+        out->time = c.time; out->timestep = c.timestep; out->time_hydrological = c.time_hydro; out->time_target = c.time_target;
+        out->batch_timesteps = c.batch_timesteps; out->batch_successful = c.batch_successful; out->batch_skipped = c.batch_skipped;
+    } else {
+        hp::Clock<float> c; memcpy(&c, buf, sizeof(c));
+        out->time = c.time; out->timestep = c.timestep; out->time_hydrological = c.time_hydro; out->time_target = c.time_target;
+        out->batch_timesteps = c.batch_timesteps; out->batch_successful = c.batch_successful; out->batch_skipped = c.batch_skipped;
+    }
+    out->iterations = s->iterations; out->kernel_launches = s->launches; out->use_alternate = s->use_alt ? 1u : 0u; out->reserved0 = 0;
+    return HP_OK;
+}
+
+int hp_comm_unique_id(void* id_out) {
+    if (!id_out) return fail(HP_ERR_INVALID, "id_out is null");
+    const char* err = hp::comm_unique_id(id_out);
+    if (err) return fail(HP_ERR_NCCL, "%s", err);
+    return HP_OK;
+}
+
+int hp_scheme_attach_comm(hp_scheme* s, const void* id, int rank, int world_size) {
+    if (!s || !id) return fail(HP_ERR_INVALID, "null argument");
+    if (world_size < 1 || rank < 0 || rank >= world_size) return fail(HP_ERR_INVALID, "bad rank/world size");
+    HP_CUDA(cudaSetDevice(s->ex->device));
+    if (world_size == 1) return HP_OK;
+    const char* err = hp::comm_create(&s->comm, id, rank, world_size);
+    if (err) return fail(HP_ERR_NCCL, "%s", err);
+    HP_CUDA(cudaStreamCreateWithFlags(&s->comm_stream, cudaStreamNonBlocking));
+    HP_CUDA(cudaEventCreateWithFlags(&s->ev_edges, cudaEventDisableTiming));
+    HP_CUDA(cudaEventCreateWithFlags(&s->ev_halo, cudaEventDisableTiming));
+    drop_graphs(s);
+    return HP_OK;
+}
+
+}  // extern "C"

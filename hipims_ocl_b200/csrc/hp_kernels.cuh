@@ -1,0 +1,91 @@
+// hp_kernels.cuh -- kernel-side shared declarations (device structs + the launch interface the
+// executor calls).  hp_kernels.cu is compiled twice, with HP_NS=hp_strict (-fmad=false) and
+// HP_NS=hp_fast (FMA contraction on); this header is what hp_executor.cu sees of both.
+#pragma once
+
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace hp {
+
+// Device-resident clock: the reference's "Time", "Timestep", "Time (hydrological)", "Target time
+// (sync)" and batch counter buffers (src/Schemes/CSchemeGodunov.cpp:803-873) in one record, kept
+// in the working precision like the reference's buffers.
+template <class R> struct Clock {
+    R time, timestep, time_hydro, time_target, batch_timesteps;
+    unsigned int batch_successful, batch_skipped;
+};
+
+// Structure-of-arrays planes of one state buffer ("Cell states" / "Cell states (alternate)").
+struct Planes { void *eta, *emax, *qx, *qy; };
+
+// Geometry of the rows one scheme holds (a whole domain or a row strip with halo rows).
+struct Grid {
+    int cols;        // DOMAIN_COLS
+    int rows;        // local rows (owned + halo)
+    int pitch;       // elements between consecutive rows of a plane
+    int grows;       // DOMAIN_ROWS of the whole domain
+    int gy0;         // global row index of local row 0
+    int own_y0;      // first owned local row
+    int own_y1;      // one past the last owned local row
+};
+
+// Scalars every kernel needs, in double; converted to the working precision on the device side.
+struct ParamsD {
+    double eps, eps10, delta, courant, end_time, fixed_dt;
+    int dynamic, friction, simplified_speed;
+};
+
+enum ReduceMode { kReduceNone = 0, kReduceSrc = 1, kReduceDst = 2 };
+
+// One row range [y0, y1) of local rows to update in a launch (edge rows first, interior after).
+struct StepArgs {
+    Planes src, dst;
+    const void *bed, *manning;
+    void* clock;              // Clock<R>*
+    unsigned long long* max_bits;  // running maximum of the wave speed, as ordered bits
+    unsigned int* ticket;     // CTA arrival counter for the in-kernel finaliser
+    Grid grid;
+    ParamsD params;
+    int y0, y1;
+    int reduce_mode;          // ReduceMode
+    int finalize;             // 1: last CTA runs the time controller (single device)
+    unsigned int total_ctas;  // CTAs that will arrive on `ticket` before the finaliser runs
+};
+
+struct BdyUniformArgs {
+    Planes state; const void* bed; const void* clock; const void* series;  // series: entries x {t, value}
+    Grid grid; unsigned int entries, definition; double interval, length; int cover_x, cover_y;
+};
+struct BdyGriddedArgs {
+    Planes state; const void* clock; const void* series;
+    Grid grid; double interval, resolution, offset_x, offset_y, delta;
+    unsigned long long entries, definition, grows, gcols; int cover_x, cover_y;
+};
+struct BdyCellArgs {
+    Planes state; const void* bed; const void* clock; const void* series; const long long* relations;  // LOCAL ids
+    Grid grid; ParamsD params; unsigned long long entries, count; double interval, length;
+    unsigned int def_depth, def_discharge;
+};
+
+// The launch interface of one compiled flavour (strict / fast).
+struct KernelTable {
+    // returns the number of kernels launched
+    int (*step)(int scheme, int real_bytes, const StepArgs& a, cudaStream_t st);
+    int (*reduce_only)(int real_bytes, const StepArgs& a, cudaStream_t st);       // tst_Reduce
+    int (*advance)(int real_bytes, const StepArgs& a, cudaStream_t st);           // tst_Advance_Normal
+    int (*update_timestep)(int real_bytes, const StepArgs& a, cudaStream_t st);   // tst_UpdateTimestep
+    int (*bdy_uniform)(int real_bytes, const BdyUniformArgs& a, cudaStream_t st);
+    int (*bdy_gridded)(int real_bytes, const BdyGriddedArgs& a, cudaStream_t st);
+    int (*bdy_cell)(int real_bytes, const BdyCellArgs& a, cudaStream_t st);
+    // AoS (host layout, staged on the device) <-> SoA planes, whole rows
+    int (*aos_to_soa)(int real_bytes, const void* aos, Planes dst, Grid g, int row0, int nrows, cudaStream_t st);
+    int (*soa_to_aos)(int real_bytes, Planes src, void* aos, Grid g, int row0, int nrows, cudaStream_t st);
+    int (*copy_plane_rows)(int real_bytes, const void* dense, void* plane, Grid g, int row0, int nrows, cudaStream_t st);
+};
+
+const KernelTable& strict_kernels();
+const KernelTable& fast_kernels();
+
+}  // namespace hp

@@ -1,0 +1,240 @@
+/*
+ * hipims_cuda.h -- C ABI of the B200 executor for the HiPIMS explicit cell-update path.
+ *
+ * This library replaces the reference's OpenCL executor layer (src/OpenCL/Executors/*:
+ * CExecutorControlOpenCL, COCLDevice, COCLProgram, COCLKernel, COCLBuffer and the
+ * runtime-compiled .clc sources) underneath the scheme / domain / boundary classes.  The entry
+ * points are what CSchemeGodunov / CSchemeMUSCLHancock / CSchemeInertial, CBoundaryCell /
+ * CBoundaryUniform / CBoundaryGridded and CDomainLink call the OpenCL wrappers for today; each
+ * declaration cites the reference call site it replaces (paths relative to the reference root).
+ * INTEGRATION.md shows the binding a maintainer would add to the reference's C++ host.
+ *
+ * Conventions
+ *   - plain C: opaque handles, POD structs, pointers and sizes; no C++ or torch types.
+ *   - every function returns HP_OK (0) or a negative hp_status; hp_last_error() returns the
+ *     message for the calling thread.  The reference forwards such failures to
+ *     model::doError (src/main.cpp:631-652).
+ *   - host arrays keep the reference's host layout (src/Domain/CDomain.h:28-33,
+ *     src/Schemes/CSchemeGodunov.cpp:832-845): cell states are `cells` 4-vectors
+ *     {eta (free-surface level), eta_max, qx, qy} of `real`, bed elevations and Manning
+ *     coefficients are `cells` reals; row-major, row 0 is the SOUTHERN edge
+ *     (src/Domain/Cartesian/CLDomainCartesian.clc:26-30).  `real` is double or float according
+ *     to hp_scheme_config.real_bytes (the reference's floatingPointPrecision switch,
+ *     src/OpenCL/Executors/COCLProgram.cpp:381-399).  On the device the library keeps
+ *     structure-of-arrays planes; the conversion happens inside upload/download.
+ *   - all work of one scheme is issued on one CUDA stream; calls are asynchronous unless stated.
+ *     A handle must not be used from two threads at once.
+ *   - there is NO CPU fallback: without a CUDA device every call fails with HP_ERR_NO_DEVICE.
+ */
+#ifndef HIPIMS_CUDA_H
+#define HIPIMS_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HP_ABI_VERSION 1
+
+typedef enum hp_status {
+    HP_OK = 0,
+    HP_ERR_NO_DEVICE = -1,
+    HP_ERR_INVALID = -2,
+    HP_ERR_CUDA = -3,
+    HP_ERR_NCCL = -4,
+    HP_ERR_OOM = -5
+} hp_status;
+
+typedef struct hp_executor hp_executor; /* one CUDA device + stream: CExecutorControlOpenCL + COCLDevice */
+typedef struct hp_scheme hp_scheme;     /* program + kernels + buffers one CScheme* owns                */
+
+/* <scheme name="..."> (src/Schemes/CScheme.cpp:148-165) */
+enum { HP_SCHEME_GODUNOV = 0, HP_SCHEME_MUSCL_HANCOCK = 1, HP_SCHEME_INERTIAL = 2 };
+
+/* Reference behaviours that change results; set to reproduce them. */
+enum {
+    HP_QUIRK_REDUCE_BUFFER_A  = 1u << 0, /* tst_Reduce always reads buffer "Cell states"
+                                            (src/Schemes/CSchemeGodunov.cpp:1629,1634)              */
+    HP_QUIRK_BDY_COVERAGE     = 1u << 1, /* bdy_Uniform / bdy_Gridded cover floor(n/8)*8 cells per
+                                            axis (src/Boundaries/CBoundaryUniform.cpp:294-295)      */
+    HP_QUIRK_MH_NO_BOUNDARIES = 1u << 2  /* MUSCL-Hancock iteration applies no boundaries
+                                            (src/Schemes/CSchemeMUSCLHancock.cpp:646-680)           */
+};
+
+/* Execution options (not part of the numerical contract). */
+enum {
+    HP_OPT_STRICT_FP   = 1u << 0, /* kernels built without FMA contraction: bit-comparable with the
+                                     reference arithmetic evaluated in IEEE order                   */
+    HP_OPT_NO_GRAPH    = 1u << 1, /* launch kernels directly instead of replaying CUDA graphs      */
+    HP_OPT_NO_TMA      = 1u << 2  /* use the plain-load kernels instead of the TMA-staged ones     */
+};
+
+/*
+ * Everything the reference bakes into the OpenCL program as "#define"s
+ * (src/Schemes/CSchemeGodunov.cpp:667-783) plus the domain geometry.
+ */
+typedef struct hp_scheme_config {
+    uint32_t struct_size;     /* sizeof(hp_scheme_config)                                           */
+    uint32_t scheme;          /* HP_SCHEME_*                                                        */
+    uint32_t real_bytes;      /* 8 = double, 4 = float                                              */
+    uint32_t quirks;          /* HP_QUIRK_*                                                         */
+    uint32_t options;         /* HP_OPT_*                                                           */
+    uint32_t dynamic_timestep;/* TIMESTEP_DYNAMIC (1) or TIMESTEP_FIXED (0)                         */
+    uint32_t friction;        /* FRICTION_ENABLED && FRICTION_IN_FLUX_KERNEL                        */
+    uint32_t reserved0;
+    uint64_t cols;            /* DOMAIN_COLS                                                        */
+    uint64_t rows;            /* rows held by THIS scheme (strip rows incl. halo rows)              */
+    double   delta;           /* DOMAIN_DELTAX == DOMAIN_DELTAY                                     */
+    double   courant;         /* COURANT_NUMBER                                                     */
+    double   dry_threshold;   /* VERY_SMALL; QUITE_SMALL is 10x                                     */
+    double   end_time;        /* SCHEME_ENDTIME                                                     */
+    double   fixed_timestep;  /* TIMESTEP_FIXED                                                     */
+    double   initial_timestep;/* first timestep (src/Schemes/CScheme.cpp:49)                        */
+    /* Row-strip decomposition (replaces the overlap zones of src/Domain/Links/CDomainLink.cpp):
+     * this scheme holds global rows [row_offset - halo_south, row_offset + own_rows + halo_north).
+     * A single-device run has global_rows == rows, row_offset == 0 and no halos.                  */
+    uint64_t global_rows;     /* DOMAIN_ROWS of the whole domain                                    */
+    uint64_t row_offset;      /* global index of the first OWNED row                                */
+    uint32_t halo_south;      /* halo rows below the owned rows (0 on the southern strip)           */
+    uint32_t halo_north;      /* halo rows above the owned rows (0 on the northern strip)           */
+} hp_scheme_config;
+
+/* What CSchemeGodunov::readKeyStatistics pulls back (src/Schemes/CSchemeGodunov.cpp:1817-1850). */
+typedef struct hp_scheme_stats {
+    double   time;              /* "Time"                                                           */
+    double   timestep;          /* "Timestep" (negative = suspended at the sync time)               */
+    double   time_hydrological; /* "Time (hydrological)"                                            */
+    double   time_target;       /* "Target time (sync)"                                             */
+    double   batch_timesteps;   /* "Batch timesteps cumulative"                                     */
+    uint32_t batch_successful;  /* "Batch successful iterations"                                    */
+    uint32_t batch_skipped;     /* "Batch skipped iterations"                                       */
+    uint64_t iterations;        /* iterations scheduled since creation                              */
+    uint64_t kernel_launches;   /* CUDA kernels launched (directly or inside graphs) since creation */
+    uint32_t use_alternate;     /* next source buffer is "Cell states (alternate)"                  */
+    uint32_t reserved0;
+} hp_scheme_stats;
+
+/* Boundary configuration records, as src/Boundaries/CLBoundaries.clh:54-82 with doubles. */
+typedef struct hp_bdy_uniform {
+    uint32_t entries;           /* TimeseriesEntries                                                */
+    uint32_t definition;        /* 0 rain-intensity [mm/h], 1 loss-rate [mm/h]                      */
+    double   interval;          /* TimeseriesInterval                                               */
+    double   length;            /* TimeseriesLength                                                 */
+} hp_bdy_uniform;
+
+typedef struct hp_bdy_gridded {
+    double   interval, resolution, offset_x, offset_y;
+    uint64_t entries;           /* frames                                                           */
+    uint64_t definition;        /* 0 rain-intensity [mm/h], 2 mass-flux [m3/s per cell]             */
+    uint64_t rows, cols;        /* coarse grid shape                                                */
+} hp_bdy_gridded;
+
+typedef struct hp_bdy_cell {
+    uint64_t entries;
+    double   interval, length;
+    uint64_t relations;         /* RelationCount                                                    */
+    uint32_t def_depth;         /* 0 ignore, 1 fsl, 2 depth                                         */
+    uint32_t def_discharge;     /* 0 ignore, 1 discharge, 2 velocity, 3 volume                      */
+} hp_bdy_cell;
+
+/* ---- library ------------------------------------------------------------------------------ */
+int         hp_abi_version(void);
+const char* hp_last_error(void);
+/* CExecutorControlOpenCL::getDeviceCount (src/OpenCL/Executors/CExecutorControlOpenCL.h:55-63) */
+int         hp_device_count(int* count);
+
+/* ---- executor: device + queue --------------------------------------------------------------
+ * replaces CExecutorControlOpenCL::createDevices / COCLDevice (context + command queue,
+ * src/OpenCL/Executors/COCLDevice.cpp:250-300).  `external_stream` is a cudaStream_t to issue
+ * work on (0 = create a private non-blocking stream). */
+int  hp_executor_create(int device_ordinal, void* external_stream, hp_executor** out);
+void hp_executor_destroy(hp_executor* ex);
+/* COCLDevice::getDeviceShortName / capability fields (src/OpenCL/Executors/COCLDevice.h:87-111) */
+int  hp_executor_describe(hp_executor* ex, char* name, size_t name_len, int* sm_count, size_t* total_mem);
+/* COCLDevice::blockUntilFinished (src/OpenCL/Executors/COCLDevice.cpp:374-401) */
+int  hp_executor_finish(hp_executor* ex);
+/* device-side timing on the executor's stream (the reference only has wall clock,
+ * src/General/CBenchmark.cpp:77-79): records events around whatever is enqueued between. */
+int  hp_executor_timer_start(hp_executor* ex);
+int  hp_executor_timer_stop(hp_executor* ex, float* milliseconds);
+
+/* ---- scheme: prepareAll ----------------------------------------------------------------------
+ * replaces CSchemeGodunov::prepareAll -> prepareCode/compileProgram, prepare1OMemory,
+ * prepareGeneralKernels, prepare1OKernels (src/Schemes/CSchemeGodunov.cpp:386-478, 789-988) and
+ * the MUSCL-Hancock / inertial equivalents (src/Schemes/CSchemeMUSCLHancock.cpp:230-320,
+ * src/Schemes/CSchemeInertial.cpp:120-300). */
+int  hp_scheme_create(hp_executor* ex, const hp_scheme_config* cfg, hp_scheme** out);
+void hp_scheme_destroy(hp_scheme* s);
+
+/* ---- boundaries: CBoundary*::prepareBoundary -----------------------------------------------
+ * Boundaries are applied in the order they are added (the reference's order is hash order on an
+ * out-of-order queue).  `series` layouts as the reference uploads them:
+ *   uniform: entries x {t, value}             (src/Boundaries/CBoundaryUniform.cpp:255-262)
+ *   gridded: entries x rows x cols values     (src/Boundaries/CBoundaryGridded.cpp:254-271)
+ *   cell:    entries x {t, depth|fsl, Qx, Qy} (src/Boundaries/CBoundaryCell.cpp:383-400), already
+ *            divided by the relation count for dischargeValue=total, and `relations` cell IDs
+ *            y * cols + x in GLOBAL coordinates (src/Boundaries/CBoundaryCell.cpp:417-421).
+ * All series are doubles on the host and converted to `real`. */
+int  hp_boundary_add_uniform(hp_scheme* s, const hp_bdy_uniform* conf, const double* series);
+int  hp_boundary_add_gridded(hp_scheme* s, const hp_bdy_gridded* conf, const double* series);
+int  hp_boundary_add_cell(hp_scheme* s, const hp_bdy_cell* conf, const uint64_t* relations, const double* series);
+
+/* ---- data movement ---------------------------------------------------------------------------
+ * hp_scheme_upload_cells: CSchemeGodunov::prepareSimulation's queueWriteAll of "Cell states",
+ * "Cell states (alternate)", "Bed elevations", "Manning coefficients" and the clock buffers
+ * (src/Schemes/CSchemeGodunov.cpp:1053-1071).  Pointers are HOST memory (pinned or pageable)
+ * covering this scheme's `rows` x `cols` cells. */
+int  hp_scheme_upload_cells(hp_scheme* s, const void* states, const void* bed, const void* manning);
+/* CSchemeGodunov::readDomainAll / saveCurrentState: reads the next source buffer
+ * (src/Schemes/CSchemeGodunov.cpp:1671-1679, 1720-1736).  Synchronous. */
+int  hp_scheme_download_cells(hp_scheme* s, void* states);
+/* both ping-pong buffers, for parity checks of the "leave dst untouched" rule */
+int  hp_scheme_download_both(hp_scheme* s, void* states_a, void* states_b);
+/* COCLBuffer::queueReadPartial / queueWritePartial on whole rows of the next source buffer, as
+ * CDomainLink::pullFromBuffer / pushToBuffer use them (src/Domain/Links/CDomainLink.cpp:168-197,
+ * 252-270).  `first_row` is local to this scheme. */
+int  hp_scheme_read_rows(hp_scheme* s, uint64_t first_row, uint64_t row_count, void* states);
+int  hp_scheme_write_rows(hp_scheme* s, uint64_t first_row, uint64_t row_count, const void* states);
+
+/* ---- clock -----------------------------------------------------------------------------------
+ * write of "Target time (sync)" (src/Schemes/CSchemeGodunov.cpp:1164-1180) */
+int  hp_scheme_set_target_time(hp_scheme* s, double target);
+/* timestep override at the start of a batch (src/Schemes/CSchemeGodunov.cpp:1213-1232) */
+int  hp_scheme_force_timestep(hp_scheme* s, double timestep);
+/* sets time, timestep and hydrological accumulator (prepareSimulation / tests) */
+int  hp_scheme_set_clock(hp_scheme* s, double time, double timestep, double time_hydrological);
+/* tst_Reduce + tst_UpdateTimestep after a sync point (src/Schemes/CSchemeGodunov.cpp:1191-1196) */
+int  hp_scheme_update_timestep(hp_scheme* s);
+/* tst_ResetCounters (src/Schemes/CLDynamicTimestep.clc:151-161) */
+int  hp_scheme_reset_counters(hp_scheme* s);
+
+/* ---- the hot loop ---------------------------------------------------------------------------
+ * hp_scheme_iterate(n) enqueues n iterations of
+ *   boundaries -> cell update -> CFL reduction -> time advance
+ * i.e. n x CSchemeGodunov::scheduleIteration (src/Schemes/CSchemeGodunov.cpp:1617-1666) or
+ * CSchemeMUSCLHancock::scheduleIteration (src/Schemes/CSchemeMUSCLHancock.cpp:646-680), including
+ * the ping-pong toggle of Threaded_runBatch (src/Schemes/CSchemeGodunov.cpp:1287-1301).
+ * Asynchronous; the timestep never leaves the device. */
+int  hp_scheme_iterate(hp_scheme* s, uint32_t iterations);
+/* clFlush + clFinish of the batch (src/Schemes/CSchemeGodunov.cpp:1337-1341) */
+int  hp_scheme_sync(hp_scheme* s);
+/* CSchemeGodunov::readKeyStatistics (src/Schemes/CSchemeGodunov.cpp:1817-1850). Synchronous. */
+int  hp_scheme_read_stats(hp_scheme* s, hp_scheme_stats* out);
+
+/* ---- row-strip multi-GPU (replaces src/MPI/CMPIManager.cpp:555-717, 837-889) -------------------
+ * One process per GPU.  Rank r owns a contiguous strip of rows; after each cell update the
+ * edge rows are sent to the neighbouring strips' halo rows (ncclSend/ncclRecv) while the
+ * interior rows are still being computed, and the CFL wave-speed maximum is all-reduced on the
+ * device (ncclAllReduce, ncclMax) before the time controller runs.
+ * hp_comm_unique_id fills a 128-byte NCCL id on rank 0; the caller broadcasts it (e.g. with
+ * torch.distributed) and every rank passes it to hp_scheme_attach_comm. */
+#define HP_COMM_ID_BYTES 128
+int  hp_comm_unique_id(void* id_out);
+int  hp_scheme_attach_comm(hp_scheme* s, const void* id, int rank, int world_size);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HIPIMS_CUDA_H */

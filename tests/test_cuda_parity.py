@@ -1,0 +1,203 @@
+"""Parity of the CUDA executor (through the C ABI) with the CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north star): max |d eta| <= 1e-9 m in fp64, <= 1e-4 m in fp32, after a
+fixed number of iterations, with identical wet-cell counts and identical timestep counts.
+With HP_OPT_STRICT_FP (no FMA contraction) friction-free Godunov / MUSCL-Hancock runs are
+bit-identical to the oracle; with friction the only difference is pow().
+"""
+import numpy as np
+import pytest
+
+from hipims_ocl_b200 import config as hc
+from hipims_ocl_b200 import executor as hx
+from oracle import cpu_sim
+from tests.helpers import add_standard_boundaries, dtype_of, make_cfg, scenario
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"double": 1e-9, "single": 1e-4}
+
+
+@pytest.fixture(scope="module")
+def ex():
+    e = hx.Executor(0)
+    yield e
+    e.close()
+
+
+def wet_count(states, bed, eps=1e-10):
+    return int(((states[..., 0] - bed) > eps).sum())
+
+
+def run_pair(ex, cfg, scen, bdy, iters, options, chunks=None):
+    dt = dtype_of(cfg.precision)
+    bed, st, man = scenario(scen, cfg.rows, cfg.cols, dt)
+    orc = cpu_sim.CpuSim("oracle", cfg)
+    gpu = hx.CudaScheme(ex, cfg, options=options)
+    for sim in (orc, gpu):
+        sim.upload(st, bed, man)
+        add_standard_boundaries(sim, cfg, bdy)
+        sim.set_target(1.0e6)
+    for n in (chunks or [iters]):
+        orc.iterate(n)
+        gpu.iterate(n)
+    return orc, gpu, bed
+
+
+def compare(orc, gpu, bed, cfg, exact=False):
+    so, sg = orc.stats(), gpu.stats()
+    assert sg["batch_successful"] == so["batch_successful"]
+    assert sg["batch_skipped"] == so["batch_skipped"]
+    assert sg["use_alternate"] == so["use_alternate"]
+    a_o, b_o = orc.download_both()
+    a_g, b_g = gpu.download_both()
+    if exact:
+        assert sg == so
+        np.testing.assert_array_equal(a_g, a_o)
+        np.testing.assert_array_equal(b_g, b_o)
+        return
+    tol = TOL[cfg.precision]
+    rel = 1e-9 if cfg.precision == "double" else 1e-4
+    assert abs(sg["time"] - so["time"]) <= rel * max(1.0, abs(so["time"]))
+    assert abs(sg["timestep"] - so["timestep"]) <= rel * max(1.0, abs(so["timestep"]))
+    cur_o, cur_g = orc.download(), gpu.download()
+    assert np.isfinite(cur_g).all()
+    assert np.abs(cur_g[..., 0] - cur_o[..., 0]).max() <= tol            # eta
+    assert np.abs(cur_g[..., 1] - cur_o[..., 1]).max() <= tol            # eta_max
+    assert np.abs(cur_g[..., 2:] - cur_o[..., 2:]).max() <= 100 * tol    # discharges
+    assert wet_count(cur_g, bed) == wet_count(cur_o, bed)
+    vol_o = (cur_o[..., 0].astype(np.float64) - bed).sum()
+    vol_g = (cur_g[..., 0].astype(np.float64) - bed).sum()
+    assert abs(vol_g - vol_o) <= (1e-10 if cfg.precision == "double" else 1e-5) * max(1.0, abs(vol_o))
+    if cfg.scheme != hc.SCHEME_MUSCL_HANCOCK:  # the other ping-pong buffer too (stale-dst rule, Q2)
+        other_o, other_g = (a_o, a_g) if so["use_alternate"] else (b_o, b_g)
+        assert np.abs(other_g[..., 0] - other_o[..., 0]).max() <= tol
+
+
+STRICT_EXACT = [
+    ("godunov", "double", "dambreak", "none", 64, 60, {"friction": False}),
+    ("godunov", "double", "dambreak-dry", "none", 64, 60, {"friction": False}),
+    ("godunov", "single", "dambreak", "none", 64, 60, {"friction": False}),
+    ("godunov", "double", "wetdry", "rain", 45, 80, {"friction": False}),
+    ("godunov", "double", "wetdry", "rain", 45, 80, {"friction": False, "quirks": 0}),
+    ("godunov", "double", "pluvial-wet", "gridded", 48, 150, {"friction": False}),
+    ("godunov", "double", "dambreak", "none", 48, 40, {"friction": False, "dynamic": False, "fixed_dt": 0.01}),
+    ("muscl-hancock", "double", "dambreak", "none", 64, 50, {"friction": False}),
+    ("muscl-hancock", "double", "dambreak-dry", "none", 64, 50, {"friction": False}),
+    ("muscl-hancock", "single", "wetdry", "rain", 50, 60, {"friction": False}),
+]
+
+
+@pytest.mark.parametrize("scheme,precision,scen,bdy,n,iters,extra", STRICT_EXACT)
+def test_strict_mode_is_bit_identical(ex, scheme, precision, scen, bdy, n, iters, extra):
+    cfg = make_cfg(scheme, precision, n, n, **extra)
+    orc, gpu, bed = run_pair(ex, cfg, scen, bdy, iters, hx.OPT_STRICT_FP, chunks=[1, 2, 5, iters - 8])
+    compare(orc, gpu, bed, cfg, exact=True)
+
+
+TOLERANCE_CASES = [
+    ("godunov", "double", "dambreak", "none", 96, 200, {}),
+    ("godunov", "double", "dambreak-dry", "none", 96, 200, {}),
+    ("godunov", "single", "dambreak", "none", 96, 200, {}),
+    ("godunov", "double", "pluvial", "rain+loss", 50, 400, {"delta": 2.0}),
+    ("godunov", "double", "valley", "cells", 64, 200, {}),
+    ("godunov", "double", "pluvial-wet", "gridded", 64, 200, {}),
+    ("godunov", "double", "lake", "none", 64, 100, {}),
+    ("inertial", "double", "pluvial-wet", "rain", 64, 200, {}),
+    ("inertial", "single", "valley", "cells", 64, 200, {}),
+    ("muscl-hancock", "double", "dambreak", "none", 96, 200, {}),
+    ("muscl-hancock", "double", "dambreak-dry", "none", 96, 200, {}),
+    ("muscl-hancock", "single", "dambreak", "none", 96, 200, {}),
+    ("muscl-hancock", "double", "valley", "cells", 64, 200, {}),
+    ("muscl-hancock", "double", "pluvial-wet", "rain", 64, 200, {}),
+]
+
+
+@pytest.mark.parametrize("options", [hx.OPT_STRICT_FP, 0, hx.OPT_NO_GRAPH], ids=["strict", "fast", "fast-nograph"])
+@pytest.mark.parametrize("scheme,precision,scen,bdy,n,iters,extra", TOLERANCE_CASES)
+def test_parity_within_tolerance(ex, options, scheme, precision, scen, bdy, n, iters, extra):
+    cfg = make_cfg(scheme, precision, n, n, **extra)
+    orc, gpu, bed = run_pair(ex, cfg, scen, bdy, iters, options)
+    compare(orc, gpu, bed, cfg)
+
+
+def test_ragged_sizes_and_ring(ex):
+    """Sizes that are not multiples of the tile, and the frozen outer ring."""
+    for rows, cols in ((3, 3), (5, 67), (37, 4), (33, 65)):
+        cfg = make_cfg("godunov", "double", rows, cols, friction=False)
+        bed, st, man = scenario("wetdry", rows, cols, np.float64, seed=rows * 100 + cols)
+        orc = cpu_sim.CpuSim("oracle", cfg)
+        gpu = hx.CudaScheme(ex, cfg, options=hx.OPT_STRICT_FP)
+        for sim in (orc, gpu):
+            sim.upload(st, bed, man)
+            sim.set_target(1e6)
+            sim.iterate(7)
+        np.testing.assert_array_equal(gpu.download(), orc.download())
+        out = gpu.download()
+        np.testing.assert_array_equal(out[0], st[0])
+        np.testing.assert_array_equal(out[:, 0], st[:, 0])
+
+
+def test_sync_point_suspension_and_update(ex):
+    n = 48
+    cfg = make_cfg("godunov", "double", n, n, friction=False)
+    bed, st, man = scenario("dambreak", n, n, np.float64)
+    orc = cpu_sim.CpuSim("oracle", cfg)
+    gpu = hx.CudaScheme(ex, cfg, options=hx.OPT_STRICT_FP)
+    for sim in (orc, gpu):
+        sim.upload(st, bed, man)
+        sim.set_target(0.25)
+        sim.iterate(30)
+    assert gpu.stats() == orc.stats()
+    assert gpu.stats()["timestep"] < 0 and gpu.stats()["batch_skipped"] > 0
+    for sim in (orc, gpu):
+        sim.set_target(0.5)
+        sim.update_timestep()
+        sim.reset_counters()
+        sim.iterate(10)
+    assert gpu.stats() == orc.stats()
+    np.testing.assert_array_equal(gpu.download(), orc.download())
+
+
+def test_link_rows_roundtrip(ex):
+    """hp_scheme_read_rows / write_rows (CDomainLink pull/push)."""
+    cfg = make_cfg("godunov", "double", 20, 31)
+    bed, st, man = scenario("wetdry", 20, 31, np.float64, seed=3)
+    gpu = hx.CudaScheme(ex, cfg)
+    gpu.upload(st, bed, man)
+    np.testing.assert_array_equal(gpu.read_rows(5, 4), st[5:9])
+    patch = st[5:9] + 1.0
+    gpu.write_rows(5, patch)
+    out = gpu.download()
+    np.testing.assert_array_equal(out[5:9], patch)
+    np.testing.assert_array_equal(out[:5], st[:5])
+
+
+def test_size_independent_properties_at_scale(ex):
+    """At a size the oracle would take minutes for: lake at rest stays at rest, and the dam break
+    conserves volume and keeps its 4-fold symmetry."""
+    n = 2048
+    cfg = make_cfg("godunov", "double", n, n)
+    bed, st, man = scenario("lake", n, n, np.float64)
+    gpu = hx.CudaScheme(ex, cfg)
+    gpu.upload(st, bed, man)
+    gpu.set_target(1e6)
+    gpu.iterate(50)
+    out = gpu.download()
+    wet = (st[..., 0] - bed) > 1e-10
+    assert np.abs(out[..., 0][wet] - st[..., 0][wet]).max() < 1e-9
+    assert np.abs(out[..., 2:]).max() < 1e-7
+    gpu.close()
+
+    bed, st, man = scenario("dambreak", n, n, np.float64)
+    gpu = hx.CudaScheme(ex, cfg.with_(friction=False))
+    gpu.upload(st, bed, man)
+    gpu.set_target(1e6)
+    gpu.iterate(100)
+    out = gpu.download()
+    v0, v1 = (st[..., 0] - bed).sum(), (out[..., 0] - bed).sum()
+    assert abs(v1 - v0) / v0 < 1e-12
+    eta = out[..., 0]
+    assert np.abs(eta - eta[::-1, :]).max() < 1e-9 and np.abs(eta - eta[:, ::-1]).max() < 1e-9
+    assert np.abs(eta - eta.T).max() < 1e-9
+    assert gpu.stats()["batch_successful"] == 100

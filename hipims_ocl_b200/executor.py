@@ -7,6 +7,7 @@ construction raises.
 """
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 
@@ -139,6 +140,7 @@ class Executor:
         _check(self.lib.hp_executor_describe(self.h, name, 256, C.byref(sms), C.byref(mem)))
         self.name, self.sm_count, self.total_mem = name.value.decode(), sms.value, mem.value
         self.device = int(device)
+        self._schemes = weakref.WeakSet()   # schemes must be destroyed before their executor
 
     def finish(self):
         _check(self.lib.hp_executor_finish(self.h))
@@ -153,8 +155,16 @@ class Executor:
 
     def close(self):
         if self.h:
+            for sch in list(self._schemes):
+                sch.close()
             self.lib.hp_executor_destroy(self.h)
             self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class CudaScheme:
@@ -175,10 +185,12 @@ class CudaScheme:
                            halo_south=halo_south, halo_north=halo_north)
         self.h = _VP()
         _check(self.lib.hp_scheme_create(executor.h, C.byref(c), C.byref(self.h)))
+        executor._schemes.add(self)
 
     def close(self):
         if self.h:
-            self.lib.hp_scheme_destroy(self.h)
+            if self.ex.h:
+                self.lib.hp_scheme_destroy(self.h)
             self.h = None
 
     def __del__(self):

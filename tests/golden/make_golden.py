@@ -1,0 +1,61 @@
+#!/usr/bin/env python3
+"""Generates tests/golden/*.npz from the REFERENCE's own kernels (oracle/_ref, built from
+/root/reference by oracle/build_ref.py).  Run in the build container:
+
+    python tests/golden/make_golden.py
+
+Each file holds the seeded inputs, the boundary set name, and the reference outputs (both
+ping-pong buffers and the clock) after a fixed number of iterations.  The fixtures travel to the
+GPU box, where /root/reference does not exist.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from oracle import cpu_sim  # noqa: E402
+from tests.helpers import add_standard_boundaries, dtype_of, make_cfg, scenario  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+CASES = {
+    # name: (scheme, precision, scenario, boundaries, rows, cols, iterations, extra config)
+    # adversarial inputs (random rough bed, patchy water, shocks everywhere): friction off so that
+    # no pow() is involved and a strict-IEEE implementation must reproduce them bit for bit
+    "godunov_f64_wetdry_rain": ("godunov", "double", "wetdry", "rain", 40, 36, 30, {"friction": False}),
+    "godunov_f32_wetdry_rain": ("godunov", "single", "wetdry", "rain", 40, 36, 30, {"friction": False}),
+    "godunov_f64_dambreak_nofric": ("godunov", "double", "dambreak-dry", "none", 40, 40, 40, {"friction": False}),
+    "godunov_f64_valley_cells": ("godunov", "double", "valley", "cells", 36, 40, 60, {}),
+    "godunov_f64_pluvial_gridded": ("godunov", "double", "pluvial-wet", "gridded", 36, 40, 60, {}),
+    "mh_f64_dambreak_dry": ("muscl-hancock", "double", "dambreak-dry", "none", 40, 40, 30, {}),
+    "mh_f32_wetdry": ("muscl-hancock", "single", "wetdry", "none", 38, 42, 30, {"friction": False}),
+    "mh_f64_valley_cells": ("muscl-hancock", "double", "valley", "cells", 36, 40, 60, {}),
+    "godunov_f64_dambreak_fric": ("godunov", "double", "dambreak", "none", 40, 40, 60, {}),
+    "inertial_f64_valley_cells": ("inertial", "double", "valley", "cells", 36, 40, 60, {}),
+    "inertial_f32_pluvial_rain": ("inertial", "single", "pluvial-wet", "rain", 36, 40, 60, {}),
+}
+
+
+def main():
+    for name, (scheme, precision, scen, bdy, rows, cols, iters, extra) in CASES.items():
+        cfg = make_cfg(scheme, precision, rows, cols, **extra)
+        bed, st, man = scenario(scen, rows, cols, dtype_of(precision))
+        sim = cpu_sim.CpuSim("ref", cfg)
+        sim.upload(st, bed, man)
+        add_standard_boundaries(sim, cfg, bdy)
+        sim.set_target(1.0e6)
+        sim.iterate(iters)
+        a, b = sim.download_both()
+        stats = sim.stats()
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), bed=bed, states=st, manning=man, out_a=a, out_b=b,
+                            out_current=sim.download(), stats_keys=np.array(sorted(stats)),
+                            stats_vals=np.array([stats[k] for k in sorted(stats)], dtype=np.float64),
+                            meta=np.array([scheme, precision, scen, bdy, str(iters), repr(extra)]))
+        print("wrote %s.npz (t = %.4f s)" % (name, stats["time"]))
+
+
+if __name__ == "__main__":
+    main()

@@ -192,18 +192,20 @@ int build_graph(hp_scheme* s, int slot, int pairs) {
     return HP_OK;
 }
 
-template <class T> int dev_alloc(T** p, size_t bytes) {
+// zero-filled device allocation; the fill is ordered on the scheme's own stream (a legacy
+// default-stream cudaMemset is NOT ordered against a non-blocking stream)
+template <class T> int dev_alloc(hp_scheme* s, T** p, size_t bytes) {
     HP_CUDA(cudaMalloc(reinterpret_cast<void**>(p), bytes));
-    HP_CUDA(cudaMemset(*p, 0, bytes));
+    HP_CUDA(cudaMemsetAsync(*p, 0, bytes, s->ex->stream));
     return HP_OK;
 }
 
 int alloc_planes(hp_scheme* s, hp::Planes& p) {
     int rc;
-    if ((rc = dev_alloc(reinterpret_cast<char**>(&p.eta), s->plane_bytes))) return rc;
-    if ((rc = dev_alloc(reinterpret_cast<char**>(&p.emax), s->plane_bytes))) return rc;
-    if ((rc = dev_alloc(reinterpret_cast<char**>(&p.qx), s->plane_bytes))) return rc;
-    if ((rc = dev_alloc(reinterpret_cast<char**>(&p.qy), s->plane_bytes))) return rc;
+    if ((rc = dev_alloc(s, reinterpret_cast<char**>(&p.eta), s->plane_bytes))) return rc;
+    if ((rc = dev_alloc(s, reinterpret_cast<char**>(&p.emax), s->plane_bytes))) return rc;
+    if ((rc = dev_alloc(s, reinterpret_cast<char**>(&p.qx), s->plane_bytes))) return rc;
+    if ((rc = dev_alloc(s, reinterpret_cast<char**>(&p.qy), s->plane_bytes))) return rc;
     return HP_OK;
 }
 void free_planes(hp::Planes& p) { cudaFree(p.eta); cudaFree(p.emax); cudaFree(p.qx); cudaFree(p.qy); p = hp::Planes{}; }
@@ -263,7 +265,8 @@ int upload_series(hp_scheme* s, const double* host, size_t count, size_t padded,
     if (s->rb == 8) { double* d = reinterpret_cast<double*>(tmp.data()); for (size_t i = 0; i < count; ++i) d[i] = host[i]; }
     else { float* f = reinterpret_cast<float*>(tmp.data()); for (size_t i = 0; i < count; ++i) f[i] = static_cast<float>(host[i]); }
     HP_CUDA(cudaMalloc(out, tmp.size()));
-    HP_CUDA(cudaMemcpy(*out, tmp.data(), tmp.size(), cudaMemcpyHostToDevice));
+    HP_CUDA(cudaMemcpyAsync(*out, tmp.data(), tmp.size(), cudaMemcpyHostToDevice, s->ex->stream));
+    HP_CUDA(cudaStreamSynchronize(s->ex->stream));
     return HP_OK;
 }
 
@@ -376,18 +379,18 @@ int hp_scheme_create(hp_executor* ex, const hp_scheme_config* cfg, hp_scheme** o
     do {
         if ((rc = alloc_planes(s, s->A))) break;
         if ((rc = alloc_planes(s, s->B))) break;
-        if ((rc = dev_alloc(reinterpret_cast<char**>(&s->bed), s->plane_bytes))) break;
-        if ((rc = dev_alloc(reinterpret_cast<char**>(&s->manning), s->plane_bytes))) break;
-        if ((rc = dev_alloc(reinterpret_cast<char**>(&s->clock), 64))) break;
-        if ((rc = dev_alloc(&s->max_bits, sizeof(unsigned long long)))) break;
-        if ((rc = dev_alloc(&s->ticket, sizeof(unsigned int)))) break;
+        if ((rc = dev_alloc(s, reinterpret_cast<char**>(&s->bed), s->plane_bytes))) break;
+        if ((rc = dev_alloc(s, reinterpret_cast<char**>(&s->manning), s->plane_bytes))) break;
+        if ((rc = dev_alloc(s, reinterpret_cast<char**>(&s->clock), 64))) break;
+        if ((rc = dev_alloc(s, &s->max_bits, sizeof(unsigned long long)))) break;
+        if ((rc = dev_alloc(s, &s->ticket, sizeof(unsigned int)))) break;
         const size_t row_bytes = static_cast<size_t>(g.cols) * 4 * s->rb;
         size_t rows_fit = (static_cast<size_t>(256) << 20) / row_bytes;
         if (rows_fit < 1) rows_fit = 1;
         if (rows_fit > static_cast<size_t>(g.rows)) rows_fit = g.rows;
         s->staging_rows = static_cast<int>(rows_fit);
         s->staging_bytes = rows_fit * row_bytes;
-        if ((rc = dev_alloc(reinterpret_cast<char**>(&s->staging), s->staging_bytes))) break;
+        if ((rc = dev_alloc(s, reinterpret_cast<char**>(&s->staging), s->staging_bytes))) break;
         if ((rc = write_clock(s, 0.0, cfg->initial_timestep, 0.0, 0.0))) break;
     } while (0);
     if (rc != HP_OK) { hp_scheme_destroy(s); return rc; }
@@ -451,7 +454,8 @@ int hp_boundary_add_cell(hp_scheme* s, const hp_bdy_cell* conf, const uint64_t* 
         local[i] = (y >= 0 && y < g.rows) ? y * g.pitch + static_cast<long long>(gx) : -1;
     }
     HP_CUDA(cudaMalloc(reinterpret_cast<void**>(&b.relations), local.size() * sizeof(long long)));
-    HP_CUDA(cudaMemcpy(b.relations, local.data(), local.size() * sizeof(long long), cudaMemcpyHostToDevice));
+    HP_CUDA(cudaMemcpyAsync(b.relations, local.data(), local.size() * sizeof(long long), cudaMemcpyHostToDevice, s->ex->stream));
+    HP_CUDA(cudaStreamSynchronize(s->ex->stream));
     s->bdys.push_back(b);
     drop_graphs(s);
     return static_cast<int>(s->bdys.size()) - 1;

@@ -174,7 +174,7 @@ def test_long_thin_film_run_stays_close(ex, scheme):
     cur_o, cur_g = orc.download(), gpu.download()
     assert np.abs(cur_g[..., 0] - cur_o[..., 0]).max() <= 1e-5
     vol_o, vol_g = (cur_o[..., 0] - bed).sum(), (cur_g[..., 0] - bed).sum()
-    assert abs(vol_g - vol_o) <= 1e-9 * vol_o
+    assert abs(vol_g - vol_o) <= 1e-5 * vol_o
     assert abs(wet_count(cur_g, bed) - wet_count(cur_o, bed)) <= 2
 
 

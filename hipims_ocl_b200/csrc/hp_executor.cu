@@ -12,6 +12,7 @@
 #include <string>
 #include <vector>
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include "../../include/hipims_cuda.h"
@@ -81,6 +82,8 @@ struct hp_scheme {
     // graphs: [0] one pair of iterations (A->B, B->A), [1] kGraphPairs pairs
     cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};
     int graph_launches[2] = {0, 0};
+    bool use_tma = false;
+    hp::TmaMapsPOD maps_a{}, maps_b{};   // descriptors with buffer A / buffer B as the source
     hp::Comm* comm = nullptr;
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t ev_edges = nullptr, ev_halo = nullptr;
@@ -142,9 +145,14 @@ int enqueue_iteration(hp_scheme* s, bool alt, int* launched) {
         if (mh || !(s->cfg.quirks & HP_QUIRK_REDUCE_BUFFER_A)) a.reduce_mode = hp::kReduceDst;
         else a.reduce_mode = alt ? hp::kReduceDst : hp::kReduceSrc;   // Q1: always buffer A
     }
+    auto step = [&](const hp::StepArgs& args) {
+        if (s->use_tma) return s->K->step_tma(static_cast<int>(s->cfg.scheme), rb, args, alt ? &s->maps_b : &s->maps_a,
+                                              s->ex->prop.multiProcessorCount, st);
+        return s->K->step(static_cast<int>(s->cfg.scheme), rb, args, st);
+    };
     if (s->comm == nullptr) {
         a.finalize = 1;
-        n += s->K->step(static_cast<int>(s->cfg.scheme), rb, a, st);
+        n += step(a);
     } else {
         // Row strips: edge rows first, their halo exchange overlaps the interior rows, then the
         // wave-speed maximum is all-reduced on the device and one thread runs the time controller.
@@ -154,14 +162,14 @@ int enqueue_iteration(hp_scheme* s, bool alt, int* launched) {
         const int e0 = y0 + halo < y1 ? y0 + halo : y1, e1 = y1 - halo > e0 ? y1 - halo : e0;
         hp::StepArgs lo = a, hi = a, mid = a;
         lo.y1 = e0; hi.y0 = e1; mid.y0 = e0; mid.y1 = e1;
-        n += s->K->step(static_cast<int>(s->cfg.scheme), rb, lo, st);
-        n += s->K->step(static_cast<int>(s->cfg.scheme), rb, hi, st);
+        n += step(lo);
+        n += step(hi);
         if (cudaEventRecord(s->ev_edges, st) != cudaSuccess) return fail(HP_ERR_CUDA, "cudaEventRecord failed");
         if (cudaStreamWaitEvent(s->comm_stream, s->ev_edges, 0) != cudaSuccess) return fail(HP_ERR_CUDA, "cudaStreamWaitEvent failed");
         const char* err = hp::comm_exchange_halos(s->comm, a.dst, s->grid, halo, s->rb, s->comm_stream);
         if (err) return fail(HP_ERR_NCCL, "halo exchange: %s", err);
         if (cudaEventRecord(s->ev_halo, s->comm_stream) != cudaSuccess) return fail(HP_ERR_CUDA, "cudaEventRecord failed");
-        n += s->K->step(static_cast<int>(s->cfg.scheme), rb, mid, st);
+        n += step(mid);
         if (cudaStreamWaitEvent(st, s->ev_halo, 0) != cudaSuccess) return fail(HP_ERR_CUDA, "cudaStreamWaitEvent failed");
         err = hp::comm_allreduce_max(s->comm, s->max_bits, st);
         if (err) return fail(HP_ERR_NCCL, "allreduce: %s", err);
@@ -194,6 +202,47 @@ int build_graph(hp_scheme* s, int slot, int pairs) {
 
 // zero-filled device allocation; the fill is ordered on the scheme's own stream (a legacy
 // default-stream cudaMemset is NOT ordered against a non-blocking stream)
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+int encode_plane_map(void* out128, void* plane, const hp::Grid& g, size_t rb, int halo) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        HP_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) return fail(HP_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+        encode = reinterpret_cast<EncodeFn>(fn);
+    }
+    const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(g.cols), static_cast<cuuint64_t>(g.rows)};
+    const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(g.pitch) * rb};
+    const cuuint32_t box[2] = {static_cast<cuuint32_t>(hp::tma_box_w(static_cast<int>(rb), halo)), static_cast<cuuint32_t>(hp::tma_box_h(halo))};
+    const cuuint32_t estride[2] = {1, 1};
+    CUtensorMap tm;
+    const CUresult r = encode(&tm, rb == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, plane, gdim, gstride,
+                              box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(HP_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+    static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap size");
+    memcpy(out128, &tm, 128);
+    return HP_OK;
+}
+
+int build_tma_maps(hp_scheme* s) {
+    const int halo = 1;
+    int rc;
+    hp::Planes* bufs[2] = {&s->A, &s->B};
+    hp::TmaMapsPOD* maps[2] = {&s->maps_a, &s->maps_b};
+    for (int b = 0; b < 2; ++b) {
+        if ((rc = encode_plane_map(maps[b]->bytes[0], bufs[b]->eta, s->grid, s->rb, halo))) return rc;
+        if ((rc = encode_plane_map(maps[b]->bytes[1], bufs[b]->qx, s->grid, s->rb, halo))) return rc;
+        if ((rc = encode_plane_map(maps[b]->bytes[2], bufs[b]->qy, s->grid, s->rb, halo))) return rc;
+        if ((rc = encode_plane_map(maps[b]->bytes[3], s->bed, s->grid, s->rb, halo))) return rc;
+    }
+    return HP_OK;
+}
+
 template <class T> int dev_alloc(hp_scheme* s, T** p, size_t bytes) {
     HP_CUDA(cudaMalloc(reinterpret_cast<void**>(p), bytes));
     HP_CUDA(cudaMemsetAsync(*p, 0, bytes, s->ex->stream));
@@ -392,6 +441,9 @@ int hp_scheme_create(hp_executor* ex, const hp_scheme_config* cfg, hp_scheme** o
         s->staging_bytes = rows_fit * row_bytes;
         if ((rc = dev_alloc(s, reinterpret_cast<char**>(&s->staging), s->staging_bytes))) break;
         if ((rc = write_clock(s, 0.0, cfg->initial_timestep, 0.0, 0.0))) break;
+        // TMA-staged kernels: the fast flavour's Godunov step (others use the plain-load kernels)
+        s->use_tma = s->K->step_tma != nullptr && !(cfg->options & HP_OPT_NO_TMA) && cfg->scheme == HP_SCHEME_GODUNOV;
+        if (s->use_tma && (rc = build_tma_maps(s))) break;
     } while (0);
     if (rc != HP_OK) { hp_scheme_destroy(s); return rc; }
     *out = s;

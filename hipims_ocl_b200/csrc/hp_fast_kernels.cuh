@@ -1,0 +1,387 @@
+// hp_fast_kernels.cuh -- the throughput path: TMA-staged tiles, shared faces, low-op-count maths.
+//
+// Included by hp_kernels.cu for the "fast" flavour only.  Same per-cell semantics as the
+// reference-order kernels (hp_math.cuh), restructured for the B200:
+//
+//   * persistent CTAs (a multiple of the SM count), each looping over 64x8-cell tiles;
+//   * the haloed tile of eta, qx, qy, zb arrives in shared memory through TMA
+//     (cp.async.bulk.tensor.2d + mbarrier), double buffered, so the next tile streams in while
+//     the current one is computed and every plane is read from HBM once per step;
+//   * every cell FACE is solved once per step and shared by its two cells through shared
+//     memory -- the reference solves each face twice.  Only the owner-relative
+//     hydrostatic term differs between the two cells; it is added per cell in closed form;
+//   * divisions and square roots are the cost of the reference's arithmetic on this machine
+//     (4.8k instructions per cell-update measured, profiles/r01_v1_godunov_f64_4096.txt): the
+//     velocities are formed once per cell, the HLLC star speed |a + du/4| needs no square root,
+//     the two middle-state quotients share one reciprocal, the sign of S_M needs none, the bed
+//     slope source and the z^2 part of the pressure flux cancel analytically, and the
+//     remaining reciprocals / roots are MUFU seeds + Newton steps.  All of it is algebraically
+//     identical to the reference; results agree to rounding (tests/test_cuda_parity.py).
+#pragma once
+
+#include <cuda.h>
+
+#include "hp_math.cuh"
+
+namespace HP_NS {
+
+// ---------------------------------------------------------------------------------------------
+// Low-op-count elementary functions (full working precision to ~1 ulp, no slow paths).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double fm_rcp(double a) {
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
+    double e = fma(-a, x, 1.0); x = fma(x, e, x);
+    e = fma(-a, x, 1.0); x = fma(x, e, x);
+    return x;
+}
+__device__ __forceinline__ float fm_rcp(float a) {
+    float x;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(x) : "f"(a));
+    const float e = fmaf(-a, x, 1.0f);
+    return fmaf(x, e, x);
+}
+// sqrt for a >= 0 (returns 0 for a == 0)
+__device__ __forceinline__ double fm_sqrt(double a) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    double g = a * y, h = 0.5 * y;
+    double r = fma(-g, h, 0.5); g = fma(g, r, g); h = fma(h, r, h);
+    r = fma(-g, h, 0.5); g = fma(g, r, g); h = fma(h, r, h);
+    const double d = fma(-g, g, a);
+    g = fma(d, h, g);
+    return a > 0.0 ? g : 0.0;
+}
+__device__ __forceinline__ float fm_sqrt(float a) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(a));
+    float g = a * y;
+    const float h = 0.5f * y;
+    const float d = fmaf(-g, g, a);
+    g = fmaf(d, h, g);
+    return a > 0.0f ? g : 0.0f;
+}
+__device__ __forceinline__ double fm_rcbrt(double a) { return rcbrt(a); }
+__device__ __forceinline__ float fm_rcbrt(float a) { return rcbrtf(a); }
+
+// ---------------------------------------------------------------------------------------------
+// TMA / mbarrier primitives
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(bar) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// Tile geometry
+// ---------------------------------------------------------------------------------------------
+template <class R> struct Tile {
+    static constexpr int TX = 64, TY = 8, NT = 256;
+    static constexpr int BW = sizeof(R) == 8 ? TX + 2 : TX + 4;   // box width: inner extent must be a multiple of 16 bytes
+    static constexpr int BH = TY + 2;
+    static constexpr int PLANE_BYTES = (BW * BH * int(sizeof(R)) + 127) / 128 * 128;
+    static constexpr int STAGE_BYTES = 4 * PLANE_BYTES;           // eta, qx, qy, zb
+    static constexpr int NXF = (TX + 1) * TY, NYF = TX * (TY + 1);
+    static constexpr int FX_BYTES = 3 * NXF * int(sizeof(R)), FY_BYTES = 3 * NYF * int(sizeof(R));
+    static constexpr int SMEM_BYTES = 2 * STAGE_BYTES + 3 * PLANE_BYTES + FX_BYTES + FY_BYTES + 64;
+};
+
+struct TmaMaps { CUtensorMap eta, qx, qy, zb; };
+
+// One shared face in the normal frame: state of the two sides -> core flux {m, n, t}.
+// "core" = without the -g/2 z'^2 part of the pressure, which is owner specific and handled in
+// closed form by the cell update (see header comment).
+template <class R>
+__device__ __forceinline__ Flux3<R> face_core_flux(const Params<R>& k, R etaL, R zL, R unL, R utL, R cL, R etaR, R zR, R unR,
+                                                   R utR, R cR) {
+    const R hg = R(0.5) * k.g;
+    const R zmax = zL > zR ? zL : zR;
+    const R hL = (etaL - zmax > R(0)) ? (etaL - zmax) : R(0);
+    const R hR = (etaR - zmax > R(0)) ? (etaR - zmax) : R(0);
+    const bool dryL = hL < k.eps, dryR = hR < k.eps;
+    if (dryL && dryR) {
+        const R hm = R(0.5) * (hL + hR);
+        return Flux3<R>{R(0), hg * hm * hm, R(0)};
+    }
+    if (dryL) { unL = R(0); utL = R(0); }
+    if (dryR) { unR = R(0); utR = R(0); }
+    // celerity: the cell's own sqrt(g h) is reused whenever the face sits on the cell's own bed
+    const R aL = (zmax == zL) ? cL : fm_sqrt(k.g * hL);
+    const R aR = (zmax == zR) ? cR : fm_sqrt(k.g * hR);
+    const R qnL = hL * unL, qnR = hR * unR;
+    const R as = hp_abs(R(0.5) * (aL + aR) + R(0.25) * (unL - unR));     // sqrt(g h*) without the sqrt
+    const R us = R(0.5) * (unL + unR) + aL - aR;
+    const R sL = dryL ? unR - 2 * aR : hp_fmin(unL - aL, us - as);
+    const R sR = dryR ? unL + 2 * aL : hp_fmax(unR + aR, us + as);
+    const Flux3<R> FL{qnL, unL * qnL + hg * hL * hL, qnL * utL};
+    const Flux3<R> FR{qnR, unR * qnR + hg * hR * hR, qnR * utR};
+    if (sL >= R(0)) return FL;
+    if (!(sR >= R(0))) return FR;
+    const R inv = fm_rcp(sR - sL);
+    const R ss = sL * sR;
+    const R f1 = (sR * FL.m - sL * FR.m + ss * (hR - hL)) * inv;
+    const R f2 = (sR * FL.n - sL * FR.n + ss * (qnR - qnL)) * inv;
+    const R mR = hR * (unR - sR), mL = hL * (unL - sL);
+    const R num = sL * mR - sR * mL, den = mR - mL;                       // S_M = num / den, only its sign matters
+    const bool smPos = (num == R(0)) ? (den != R(0)) : ((num > R(0)) == (den > R(0)) && den != R(0));
+    return Flux3<R>{f1, f2, f1 * (smPos ? utL : utR)};
+}
+
+// Owner-side bookkeeping of one face for the cell update: reconstructed bed seen by the owner,
+// the neighbour side's reconstructed depth, and the stop-counter increments
+// (CLSchemeGodunov.clc:83-137).
+template <class R, bool ownIsLeft>
+__device__ __forceinline__ void face_owner_terms(const Params<R>& k, R etaOwn, R zOwn, R unOwn, R ownQn, R etaNb, R zNb, R unNb,
+                                                 R& bed, R& hNb, int& stop) {
+    const R zmax = zOwn > zNb ? zOwn : zNb;
+    const R hOwn = (etaOwn - zmax > R(0)) ? (etaOwn - zmax) : R(0);
+    hNb = (etaNb - zmax > R(0)) ? (etaNb - zmax) : R(0);
+    bed = zmax < etaOwn ? zmax : etaOwn;                                  // zmax - max(0, zmax - eta_own)
+    const R hL = ownIsLeft ? hOwn : hNb, hR = ownIsLeft ? hNb : hOwn;
+    const R unL = ownIsLeft ? unOwn : unNb, unR = ownIsLeft ? unNb : unOwn;
+    if (ownIsLeft) { if (hL <= k.eps && ownQn > R(0)) ++stop; }
+    else           { if (hR <= k.eps && ownQn < R(0)) ++stop; }
+    if (hR <= k.eps && unL < R(0)) ++stop;
+    if (hL <= k.eps && unR > R(0)) ++stop;
+}
+
+// Point-implicit friction with one reciprocal per component; the "cannot reverse the flow" clamp
+// of the reference (CLFriction.clc:51-65) can never bind because 2qx^2+qy^2 >= qx^2+qy^2.
+template <class R> __device__ __forceinline__ void friction_fast(const Params<R>& k, R h, R rh, R& qx, R& qy, R n, R dt) {
+    const R q2 = qx * qx + qy * qy;
+    const R q = fm_sqrt(q2);
+    if (h < k.eps || q < k.eps) return;
+    const R A = dt * k.g * n * n * rh * rh * fm_rcbrt(h);                 // dt * Cf / h^2
+    const R aq2 = A * q2;
+    qx = qx - qx * aq2 * fm_rcp(q + A * (q2 + qx * qx));
+    qy = qy - qy * aq2 * fm_rcp(q + A * (q2 + qy * qy));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Godunov step on TMA-staged tiles with shared faces.
+// ---------------------------------------------------------------------------------------------
+template <class R>
+__global__ void __launch_bounds__(Tile<R>::NT, 2)
+godunov_step_tma(const StepArgs a, const __grid_constant__ TmaMaps maps) {
+    using T = Tile<R>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char* base = smem_raw;
+    // [stage0: eta qx qy zb][stage1: ...][u][v][c][FX][FY][barriers]
+    R* const s_u = reinterpret_cast<R*>(base + 2 * T::STAGE_BYTES);
+    R* const s_v = reinterpret_cast<R*>(base + 2 * T::STAGE_BYTES + T::PLANE_BYTES);
+    R* const s_c = reinterpret_cast<R*>(base + 2 * T::STAGE_BYTES + 2 * T::PLANE_BYTES);
+    R* const s_fx = reinterpret_cast<R*>(base + 2 * T::STAGE_BYTES + 3 * T::PLANE_BYTES);
+    R* const s_fy = reinterpret_cast<R*>(base + 2 * T::STAGE_BYTES + 3 * T::PLANE_BYTES + T::FX_BYTES);
+    uint64_t* const s_bar = reinterpret_cast<uint64_t*>(base + 2 * T::STAGE_BYTES + 3 * T::PLANE_BYTES + T::FX_BYTES + T::FY_BYTES);
+
+    const Params<R> k = make_params<R>(a.params);
+    const Grid g = a.grid;
+    const int tid = threadIdx.x;
+    const R dt = read_timestep<R>(a.clock);
+    const R inv_delta = fm_rcp(k.delta);
+    const R hg = R(0.5) * k.g;
+
+    const int tiles_x = (g.cols + T::TX - 1) / T::TX;
+    const int tiles_y = (a.y1 - a.y0 + T::TY - 1) / T::TY;
+    const int ntiles = tiles_x * tiles_y;
+
+    const uint32_t bar0 = smem_u32(&s_bar[0]), bar1 = smem_u32(&s_bar[1]);
+    if (tid == 0) {
+        mbar_init(bar0, 1);
+        mbar_init(bar1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto issue = [&](int tile, int stage) {   // one thread: arm the barrier, launch the four plane loads
+        const int tx = tile % tiles_x, ty = tile / tiles_x;
+        const int x = tx * T::TX - 1, y = a.y0 + ty * T::TY - 1;
+        const uint32_t bar = stage ? bar1 : bar0;
+        const uint32_t dst = smem_u32(base + stage * T::STAGE_BYTES);
+        mbar_expect_tx(bar, 4u * T::BW * T::BH * sizeof(R));
+        tma_load_2d(dst + 0 * T::PLANE_BYTES, &maps.eta, x, y, bar);
+        tma_load_2d(dst + 1 * T::PLANE_BYTES, &maps.qx, x, y, bar);
+        tma_load_2d(dst + 2 * T::PLANE_BYTES, &maps.qy, x, y, bar);
+        tma_load_2d(dst + 3 * T::PLANE_BYTES, &maps.zb, x, y, bar);
+    };
+
+    const View<R> s(a.src);
+    const MutView<R> d(a.dst);
+    const R* __restrict__ mann = static_cast<const R*>(a.manning);
+
+    R ws = R(0);
+    uint32_t phase0 = 0, phase1 = 0;
+    int tile = blockIdx.x;
+    if (tid == 0 && tile < ntiles) issue(tile, 0);
+
+    for (int it = 0; tile < ntiles; ++it, tile += gridDim.x) {
+        const int stage = it & 1;
+        const int next = tile + gridDim.x;
+        if (tid == 0 && next < ntiles) issue(next, stage ^ 1);
+        if (stage == 0) { mbar_wait(bar0, phase0); phase0 ^= 1; } else { mbar_wait(bar1, phase1); phase1 ^= 1; }
+
+        const R* const t_eta = reinterpret_cast<const R*>(base + stage * T::STAGE_BYTES);
+        const R* const t_qx = reinterpret_cast<const R*>(base + stage * T::STAGE_BYTES + T::PLANE_BYTES);
+        const R* const t_qy = reinterpret_cast<const R*>(base + stage * T::STAGE_BYTES + 2 * T::PLANE_BYTES);
+        const R* const t_zb = reinterpret_cast<const R*>(base + stage * T::STAGE_BYTES + 3 * T::PLANE_BYTES);
+        const int x0 = (tile % tiles_x) * T::TX, y0 = a.y0 + (tile / tiles_x) * T::TY;
+
+        // ---- phase B: per-cell velocities and celerity for the tile and its halo ----------------
+        for (int i = tid; i < (T::TX + 2) * T::BH; i += T::NT) {
+            const int lx = i % (T::TX + 2), ly = i / (T::TX + 2);
+            const int o = ly * T::BW + lx;
+            const R h = t_eta[o] - t_zb[o];
+            const bool wet = !(h < k.eps);
+            const R rh = wet ? fm_rcp(h) : R(0);
+            s_u[o] = t_qx[o] * rh;
+            s_v[o] = t_qy[o] * rh;
+            s_c[o] = fm_sqrt(k.g * (h > R(0) ? h : R(0)));
+        }
+        __syncthreads();
+
+        // ---- phase C: every face of the tile once ------------------------------------------------
+        if (dt > R(0)) {
+            for (int f = tid; f < T::NXF + T::NYF; f += T::NT) {
+                if (f < T::NXF) {
+                    const int j = f / (T::TX + 1), i = f % (T::TX + 1);           // between local cells (i-1, j) and (i, j)
+                    const int oL = (j + 1) * T::BW + i, oR = oL + 1;
+                    const Flux3<R> F = face_core_flux(k, t_eta[oL], t_zb[oL], s_u[oL], s_v[oL], s_c[oL], t_eta[oR], t_zb[oR],
+                                                      s_u[oR], s_v[oR], s_c[oR]);
+                    s_fx[f] = F.m; s_fx[T::NXF + f] = F.n; s_fx[2 * T::NXF + f] = F.t;
+                } else {
+                    const int gq = f - T::NXF;
+                    const int j = gq / T::TX, i = gq % T::TX;                     // between local cells (i, j-1) and (i, j)
+                    const int oL = j * T::BW + i + 1, oR = oL + T::BW;
+                    const Flux3<R> F = face_core_flux(k, t_eta[oL], t_zb[oL], s_v[oL], s_u[oL], s_c[oL], t_eta[oR], t_zb[oR],
+                                                      s_v[oR], s_u[oR], s_c[oR]);
+                    s_fy[gq] = F.m; s_fy[T::NYF + gq] = F.n; s_fy[2 * T::NYF + gq] = F.t;
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- phase D: cell update, two cells per thread -------------------------------------------
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            const int i = tid % T::TX, j = tid / T::TX + half * (T::TY / 2);
+            const int x = x0 + i, y = y0 + j;
+            if (x >= g.cols || y >= a.y1) continue;
+            const int o = (j + 1) * T::BW + i + 1;
+            const size_t id = static_cast<size_t>(y) * g.pitch + x;
+            const int gy = y + g.gy0;
+            Cell<R> c{t_eta[o], s.emax[id], t_qx[o], t_qy[o]};
+            const R zb = t_zb[o];
+            const R u = s_u[o], v = s_v[o];
+            if (a.reduce_mode == hp::kReduceSrc) {
+                const R h = c.eta - zb;
+                if (h > k.eps10 && c.emax > R(-9999.0)) {
+                    const R cc = s_c[o];
+                    const R sp = k.simplified_speed ? cc : hp_fmax(hp_abs(u), hp_abs(v)) + cc;
+                    ws = sp > ws ? sp : ws;
+                }
+            }
+            bool wrote = false;
+            const bool interior = x >= 1 && x <= g.cols - 2 && gy >= 1 && gy <= g.grows - 2;
+            R rh_new = R(0), h_new = R(0);
+            bool have_new = false;
+            if (interior) {
+                if (dt <= R(0)) {
+                    wrote = true;
+                } else if (c.emax <= R(-9999.0) || c.eta == R(-9999.0)) {
+                    wrote = true;
+                } else {
+                    const int oN = o + T::BW, oS = o - T::BW, oE = o + 1, oW = o - 1;
+                    const R etaN = t_eta[oN], etaS = t_eta[oS], etaE = t_eta[oE], etaW = t_eta[oW];
+                    const R zN = t_zb[oN], zS = t_zb[oS], zE = t_zb[oE], zW = t_zb[oW];
+                    int dry = 0;
+                    if (c.eta - zb < k.eps) ++dry;
+                    if (etaN - zN < k.eps) ++dry;
+                    if (etaE - zE < k.eps) ++dry;
+                    if (etaS - zS < k.eps) ++dry;
+                    if (etaW - zW < k.eps) ++dry;
+                    if (dry < 5) {
+                        int stop = 0;
+                        R bN, bS, bE, bW, hnN, hnS, hnE, hnW;
+                        face_owner_terms<R, true>(k, c.eta, zb, v, c.qy, etaN, zN, s_v[oN], bN, hnN, stop);
+                        face_owner_terms<R, false>(k, c.eta, zb, v, c.qy, etaS, zS, s_v[oS], bS, hnS, stop);
+                        face_owner_terms<R, true>(k, c.eta, zb, u, c.qx, etaE, zE, s_u[oE], bE, hnE, stop);
+                        face_owner_terms<R, false>(k, c.eta, zb, u, c.qx, etaW, zW, s_u[oW], bW, hnW, stop);
+                        const int fe = j * (T::TX + 1) + i + 1, fw = fe - 1;       // x-faces east / west of (i, j)
+                        const int fn = (j + 1) * T::TX + i, fs = fn - T::TX;       // y-faces north / south
+                        const R mE = s_fx[fe], mW = s_fx[fw], mN = s_fy[fn], mS = s_fy[fs];
+                        const R nE = s_fx[T::NXF + fe], nW = s_fx[T::NXF + fw], tE = s_fx[2 * T::NXF + fe], tW = s_fx[2 * T::NXF + fw];
+                        const R nN = s_fy[T::NYF + fn], nS = s_fy[T::NYF + fs], tN = s_fy[2 * T::NYF + fn], tS = s_fy[2 * T::NYF + fs];
+                        // flux divergence minus bed-slope source, hydrostatic z^2 terms cancelled analytically
+                        R dEta = ((mE - mW) + (mN - mS)) * inv_delta;
+                        R dQx = ((nE - nW) + (tN - tS) + hg * (bE - bW) * (hnE + hnW)) * inv_delta;
+                        R dQy = ((tE - tW) + (nN - nS) + hg * (bN - bS) * (hnN + hnS)) * inv_delta;
+                        dEta = chop(dEta, k.eps); dQx = chop(dQx, k.eps); dQy = chop(dQy, k.eps);
+                        if (stop > 0) { c.qx = R(0); c.qy = R(0); }
+                        c.eta = c.eta - dt * dEta; c.qx = c.qx - dt * dQx; c.qy = c.qy - dt * dQy;
+                        h_new = c.eta - zb;
+                        if (!(h_new < k.eps)) { rh_new = fm_rcp(h_new); have_new = true; }
+                        if (k.friction) friction_fast(k, h_new, rh_new, c.qx, c.qy, mann[id], dt);
+                        if (c.eta > c.emax && c.emax > R(-9990.0)) c.emax = c.eta;
+                        if (h_new < k.eps) c.eta = zb;
+                        wrote = true;
+                    }
+                }
+                if (wrote) d.store(id, c);
+            }
+            if (a.reduce_mode == hp::kReduceDst) {
+                if (!wrote) { c.eta = d.eta[id]; c.emax = d.emax[id]; c.qx = d.qx[id]; c.qy = d.qy[id]; have_new = false; }
+                const R h = c.eta - zb;
+                if (h > k.eps10 && c.emax > R(-9999.0)) {
+                    const R cc = fm_sqrt(k.g * h);
+                    R sp = cc;
+                    if (!k.simplified_speed) {
+                        const R rh = have_new ? rh_new : fm_rcp(h);
+                        sp = hp_fmax(hp_abs(c.qx * rh), hp_abs(c.qy * rh)) + cc;
+                    }
+                    ws = sp > ws ? sp : ws;
+                }
+            }
+        }
+        // generic-proxy accesses to this stage are done; the next TMA write into it is async-proxy
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+    }
+    block_reduce_finalize<R>(ws, a, k);
+}
+
+template <class R> static int launch_godunov_tma(const StepArgs& a_in, const TmaMaps& maps, int sm_count, cudaStream_t st) {
+    using T = Tile<R>;
+    StepArgs a = a_in;
+    if (a.y1 <= a.y0) return 0;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(godunov_step_tma<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES);
+        configured = true;
+    }
+    const int tiles = ((a.grid.cols + T::TX - 1) / T::TX) * ((a.y1 - a.y0 + T::TY - 1) / T::TY);
+    int grid = 2 * sm_count;                       // two resident CTAs per SM, persistent
+    if (grid > tiles) grid = tiles;
+    a.total_ctas = grid;
+    godunov_step_tma<R><<<grid, T::NT, T::SMEM_BYTES, st>>>(a, maps);
+    return 1;
+}
+
+}  // namespace HP_NS

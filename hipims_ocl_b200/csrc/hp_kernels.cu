@@ -398,9 +398,27 @@ template <class R> __global__ void __launch_bounds__(256) copy_plane_rows_kernel
     }
 }
 
+}  // namespace HP_NS
+
+#ifndef HP_FLAVOUR_STRICT
+#include "hp_fast_kernels.cuh"
+#endif
+
+namespace HP_NS {
+
 // ---------------------------------------------------------------------------------------------
 // Launch interface
 // ---------------------------------------------------------------------------------------------
+#ifndef HP_FLAVOUR_STRICT
+static_assert(sizeof(TmaMaps) == sizeof(hp::TmaMapsPOD), "descriptor block layout");
+static_assert(Tile<double>::BW == hp::tma_box_w(8, 1) && Tile<float>::BW == hp::tma_box_w(4, 1) && Tile<double>::BH == hp::tma_box_h(1), "tile box");
+static int launch_step_tma(int scheme, int real_bytes, const StepArgs& a, const hp::TmaMapsPOD* maps, int sm_count, cudaStream_t st) {
+    if (scheme != 0) return -1;
+    const TmaMaps& m = *reinterpret_cast<const TmaMaps*>(maps);
+    return real_bytes == 8 ? launch_godunov_tma<double>(a, m, sm_count, st) : launch_godunov_tma<float>(a, m, sm_count, st);
+}
+#endif
+
 static int g_sm_count = 0;
 static int sm_count() {
     if (g_sm_count == 0) {
@@ -488,6 +506,11 @@ static int launch_copy_plane_rows(int real_bytes, const void* dense, void* plane
 }
 
 static const hp::KernelTable g_table = {
+#ifndef HP_FLAVOUR_STRICT
+    launch_step_tma,
+#else
+    nullptr,
+#endif
     launch_step, launch_reduce_only, launch_advance, launch_update_timestep, launch_bdy_uniform, launch_bdy_gridded,
     launch_bdy_cell, launch_aos_to_soa, launch_soa_to_aos, launch_copy_plane_rows,
 };

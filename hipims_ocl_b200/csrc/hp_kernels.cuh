@@ -69,8 +69,18 @@ struct BdyCellArgs {
     unsigned int def_depth, def_discharge;
 };
 
+// Four TMA descriptors (eta, qx, qy of the source buffer and zb), opaque 128-byte CUtensorMaps.
+struct alignas(64) TmaMapsPOD { unsigned char bytes[4][128]; };
+// haloed tile box of the TMA-staged kernels: (64 + halo) x (8 + halo) cells; the inner extent is
+// padded so that it is a multiple of 16 bytes
+constexpr int kTmaTileX = 64, kTmaTileY = 8;
+constexpr int tma_box_w(int real_bytes, int halo) { return real_bytes == 8 ? kTmaTileX + 2 * halo : (kTmaTileX + 2 * halo + 3) / 4 * 4; }
+constexpr int tma_box_h(int halo) { return kTmaTileY + 2 * halo; }
+
 // The launch interface of one compiled flavour (strict / fast).
 struct KernelTable {
+    // TMA-staged step (fast flavour only, NULL otherwise); returns -1 if the scheme has no such kernel
+    int (*step_tma)(int scheme, int real_bytes, const StepArgs& a, const TmaMapsPOD* maps, int sm_count, cudaStream_t st);
     // returns the number of kernels launched
     int (*step)(int scheme, int real_bytes, const StepArgs& a, cudaStream_t st);
     int (*reduce_only)(int real_bytes, const StepArgs& a, cudaStream_t st);       // tst_Reduce

@@ -95,7 +95,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 // ---------------------------------------------------------------------------------------------
 template <class R> struct Tile {
     static constexpr int TX = 64, TY = 8, NT = 256;
-    static constexpr int BW = sizeof(R) == 8 ? TX + 2 : TX + 4;   // box width: inner extent must be a multiple of 16 bytes
+    // TMA wants the box to START on a 16-byte boundary of the inner dimension (measured on this
+    // part: a start coordinate of x0-1 raises "illegal instruction") and its inner extent to be a
+    // multiple of 16 bytes, so the halo columns are padded to CO = 16 / sizeof(R) on both sides.
+    static constexpr int CO = 16 / int(sizeof(R));                // smem column of the tile's first cell
+    static constexpr int BW = TX + 2 * CO;
     static constexpr int BH = TY + 2;
     static constexpr int PLANE_BYTES = (BW * BH * int(sizeof(R)) + 127) / 128 * 128;
     static constexpr int STAGE_BYTES = 4 * PLANE_BYTES;           // eta, qx, qy, zb
@@ -213,7 +217,7 @@ godunov_step_tma(const StepArgs a, const __grid_constant__ TmaMaps maps) {
 
     auto issue = [&](int tile, int stage) {   // one thread: arm the barrier, launch the four plane loads
         const int tx = tile % tiles_x, ty = tile / tiles_x;
-        const int x = tx * T::TX - 1, y = a.y0 + ty * T::TY - 1;
+        const int x = tx * T::TX - T::CO, y = a.y0 + ty * T::TY - 1;
         const uint32_t bar = stage ? bar1 : bar0;
         const uint32_t dst = smem_u32(base + stage * T::STAGE_BYTES);
         mbar_expect_tx(bar, 4u * T::BW * T::BH * sizeof(R));
@@ -246,7 +250,7 @@ godunov_step_tma(const StepArgs a, const __grid_constant__ TmaMaps maps) {
 
         // ---- phase B: per-cell velocities and celerity for the tile and its halo ----------------
         for (int i = tid; i < (T::TX + 2) * T::BH; i += T::NT) {
-            const int lx = i % (T::TX + 2), ly = i / (T::TX + 2);
+            const int lx = i % (T::TX + 2) + T::CO - 1, ly = i / (T::TX + 2);
             const int o = ly * T::BW + lx;
             const R h = t_eta[o] - t_zb[o];
             const bool wet = !(h < k.eps);
@@ -262,14 +266,14 @@ godunov_step_tma(const StepArgs a, const __grid_constant__ TmaMaps maps) {
             for (int f = tid; f < T::NXF + T::NYF; f += T::NT) {
                 if (f < T::NXF) {
                     const int j = f / (T::TX + 1), i = f % (T::TX + 1);           // between local cells (i-1, j) and (i, j)
-                    const int oL = (j + 1) * T::BW + i, oR = oL + 1;
+                    const int oL = (j + 1) * T::BW + i + T::CO - 1, oR = oL + 1;
                     const Flux3<R> F = face_core_flux(k, t_eta[oL], t_zb[oL], s_u[oL], s_v[oL], s_c[oL], t_eta[oR], t_zb[oR],
                                                       s_u[oR], s_v[oR], s_c[oR]);
                     s_fx[f] = F.m; s_fx[T::NXF + f] = F.n; s_fx[2 * T::NXF + f] = F.t;
                 } else {
                     const int gq = f - T::NXF;
                     const int j = gq / T::TX, i = gq % T::TX;                     // between local cells (i, j-1) and (i, j)
-                    const int oL = j * T::BW + i + 1, oR = oL + T::BW;
+                    const int oL = j * T::BW + i + T::CO, oR = oL + T::BW;
                     const Flux3<R> F = face_core_flux(k, t_eta[oL], t_zb[oL], s_v[oL], s_u[oL], s_c[oL], t_eta[oR], t_zb[oR],
                                                       s_v[oR], s_u[oR], s_c[oR]);
                     s_fy[gq] = F.m; s_fy[T::NYF + gq] = F.n; s_fy[2 * T::NYF + gq] = F.t;
@@ -284,7 +288,7 @@ godunov_step_tma(const StepArgs a, const __grid_constant__ TmaMaps maps) {
             const int i = tid % T::TX, j = tid / T::TX + half * (T::TY / 2);
             const int x = x0 + i, y = y0 + j;
             if (x >= g.cols || y >= a.y1) continue;
-            const int o = (j + 1) * T::BW + i + 1;
+            const int o = (j + 1) * T::BW + i + T::CO;
             const size_t id = static_cast<size_t>(y) * g.pitch + x;
             const int gy = y + g.gy0;
             Cell<R> c{t_eta[o], s.emax[id], t_qx[o], t_qy[o]};

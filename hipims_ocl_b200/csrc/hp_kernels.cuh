@@ -71,10 +71,10 @@ struct BdyCellArgs {
 
 // Four TMA descriptors (eta, qx, qy of the source buffer and zb), opaque 128-byte CUtensorMaps.
 struct alignas(64) TmaMapsPOD { unsigned char bytes[4][128]; };
-// haloed tile box of the TMA-staged kernels: (64 + halo) x (8 + halo) cells; the inner extent is
-// padded so that it is a multiple of 16 bytes
+// haloed tile box of the TMA-staged kernels: 64 x 8 cells plus halo; the box must start on a
+// 16-byte boundary of the inner dimension, so it carries 16 / real_bytes halo columns per side
 constexpr int kTmaTileX = 64, kTmaTileY = 8;
-constexpr int tma_box_w(int real_bytes, int halo) { return real_bytes == 8 ? kTmaTileX + 2 * halo : (kTmaTileX + 2 * halo + 3) / 4 * 4; }
+constexpr int tma_box_w(int real_bytes, int /*halo*/) { return kTmaTileX + 2 * (16 / real_bytes); }
 constexpr int tma_box_h(int halo) { return kTmaTileY + 2 * halo; }
 
 // The launch interface of one compiled flavour (strict / fast).

@@ -61,7 +61,15 @@ __device__ __forceinline__ float fm_sqrt(float a) {
     g = fmaf(d, h, g);
     return a > 0.0f ? g : 0.0f;
 }
-__device__ __forceinline__ double fm_rcbrt(double a) { return rcbrt(a); }
+// a^(-1/3) for a > 0: single-precision seed (MUFU lg2/ex2) + two Newton steps y <- y (4 - a y^3) / 3
+__device__ __forceinline__ double fm_rcbrt(double a) {
+    double y = static_cast<double>(exp2f(-0.333333343f * __log2f(static_cast<float>(a))));
+    double t = y * y * y;
+    y = y * fma(-0.33333333333333333 * a, t, 1.3333333333333333);
+    t = y * y * y;
+    y = y * fma(-0.33333333333333333 * a, t, 1.3333333333333333);
+    return y;
+}
 __device__ __forceinline__ float fm_rcbrt(float a) { return rcbrtf(a); }
 
 // ---------------------------------------------------------------------------------------------
@@ -95,6 +103,7 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 // ---------------------------------------------------------------------------------------------
 template <class R> struct Tile {
     static constexpr int TX = 64, TY = 8, NT = 256;
+    static constexpr int CTAS_PER_SM = sizeof(R) == 8 ? 2 : 4;    // register- and shared-memory-limited
     // TMA wants the box to START on a 16-byte boundary of the inner dimension (measured on this
     // part: a start coordinate of x0-1 raises "illegal instruction") and its inner extent to be a
     // multiple of 16 bytes, so the halo columns are padded to CO = 16 / sizeof(R) on both sides.
@@ -159,12 +168,14 @@ __device__ __forceinline__ void face_owner_terms(const Params<R>& k, R etaOwn, R
     const R hOwn = (etaOwn - zmax > R(0)) ? (etaOwn - zmax) : R(0);
     hNb = (etaNb - zmax > R(0)) ? (etaNb - zmax) : R(0);
     bed = zmax < etaOwn ? zmax : etaOwn;                                  // zmax - max(0, zmax - eta_own)
-    const R hL = ownIsLeft ? hOwn : hNb, hR = ownIsLeft ? hNb : hOwn;
-    const R unL = ownIsLeft ? unOwn : unNb, unR = ownIsLeft ? unNb : unOwn;
-    if (ownIsLeft) { if (hL <= k.eps && ownQn > R(0)) ++stop; }
-    else           { if (hR <= k.eps && ownQn < R(0)) ++stop; }
-    if (hR <= k.eps && unL < R(0)) ++stop;
-    if (hL <= k.eps && unR > R(0)) ++stop;
+    if (hOwn <= k.eps || hNb <= k.eps) {                                  // only possible at wet/dry fronts
+        const R hL = ownIsLeft ? hOwn : hNb, hR = ownIsLeft ? hNb : hOwn;
+        const R unL = ownIsLeft ? unOwn : unNb, unR = ownIsLeft ? unNb : unOwn;
+        if (ownIsLeft) { if (hL <= k.eps && ownQn > R(0)) ++stop; }
+        else           { if (hR <= k.eps && ownQn < R(0)) ++stop; }
+        if (hR <= k.eps && unL < R(0)) ++stop;
+        if (hL <= k.eps && unR > R(0)) ++stop;
+    }
 }
 
 // Point-implicit friction with one reciprocal per component; the "cannot reverse the flow" clamp
@@ -183,7 +194,7 @@ template <class R> __device__ __forceinline__ void friction_fast(const Params<R>
 // Godunov step on TMA-staged tiles with shared faces.
 // ---------------------------------------------------------------------------------------------
 template <class R>
-__global__ void __launch_bounds__(Tile<R>::NT, 2)
+__global__ void __launch_bounds__(Tile<R>::NT, Tile<R>::CTAS_PER_SM)
 godunov_step_tma(const StepArgs a, const __grid_constant__ TmaMaps maps) {
     using T = Tile<R>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -248,6 +259,17 @@ godunov_step_tma(const StepArgs a, const __grid_constant__ TmaMaps maps) {
         const R* const t_zb = reinterpret_cast<const R*>(base + stage * T::STAGE_BYTES + 3 * T::PLANE_BYTES);
         const int x0 = (tile % tiles_x) * T::TX, y0 = a.y0 + (tile / tiles_x) * T::TY;
 
+        // point-wise planes (no halo): issue the global loads now, they are consumed in phase D
+        R pre_emax[2], pre_mann[2];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int x = x0 + tid % T::TX, y = y0 + tid / T::TX + half * (T::TY / 2);
+            const bool in = x < g.cols && y < a.y1;
+            const size_t id = static_cast<size_t>(in ? y : a.y0) * g.pitch + (in ? x : 0);
+            pre_emax[half] = s.emax[id];
+            pre_mann[half] = k.friction ? mann[id] : R(0);
+        }
+
         // ---- phase B: per-cell velocities and celerity for the tile and its halo ----------------
         for (int i = tid; i < (T::TX + 2) * T::BH; i += T::NT) {
             const int lx = i % (T::TX + 2) + T::CO - 1, ly = i / (T::TX + 2);
@@ -283,7 +305,7 @@ godunov_step_tma(const StepArgs a, const __grid_constant__ TmaMaps maps) {
         __syncthreads();
 
         // ---- phase D: cell update, two cells per thread -------------------------------------------
-#pragma unroll 1
+#pragma unroll
         for (int half = 0; half < 2; ++half) {
             const int i = tid % T::TX, j = tid / T::TX + half * (T::TY / 2);
             const int x = x0 + i, y = y0 + j;
@@ -291,7 +313,7 @@ godunov_step_tma(const StepArgs a, const __grid_constant__ TmaMaps maps) {
             const int o = (j + 1) * T::BW + i + T::CO;
             const size_t id = static_cast<size_t>(y) * g.pitch + x;
             const int gy = y + g.gy0;
-            Cell<R> c{t_eta[o], s.emax[id], t_qx[o], t_qy[o]};
+            Cell<R> c{t_eta[o], pre_emax[half], t_qx[o], t_qy[o]};
             const R zb = t_zb[o];
             const R u = s_u[o], v = s_v[o];
             if (a.reduce_mode == hp::kReduceSrc) {
@@ -342,7 +364,7 @@ godunov_step_tma(const StepArgs a, const __grid_constant__ TmaMaps maps) {
                         c.eta = c.eta - dt * dEta; c.qx = c.qx - dt * dQx; c.qy = c.qy - dt * dQy;
                         h_new = c.eta - zb;
                         if (!(h_new < k.eps)) { rh_new = fm_rcp(h_new); have_new = true; }
-                        if (k.friction) friction_fast(k, h_new, rh_new, c.qx, c.qy, mann[id], dt);
+                        if (k.friction) friction_fast(k, h_new, rh_new, c.qx, c.qy, pre_mann[half], dt);
                         if (c.eta > c.emax && c.emax > R(-9990.0)) c.emax = c.eta;
                         if (h_new < k.eps) c.eta = zb;
                         wrote = true;
@@ -381,7 +403,7 @@ template <class R> static int launch_godunov_tma(const StepArgs& a_in, const Tma
         configured = true;
     }
     const int tiles = ((a.grid.cols + T::TX - 1) / T::TX) * ((a.y1 - a.y0 + T::TY - 1) / T::TY);
-    int grid = 2 * sm_count;                       // two resident CTAs per SM, persistent
+    int grid = T::CTAS_PER_SM * sm_count;          // all resident CTAs of every SM, persistent
     if (grid > tiles) grid = tiles;
     a.total_ctas = grid;
     godunov_step_tma<R><<<grid, T::NT, T::SMEM_BYTES, st>>>(a, maps);

@@ -113,6 +113,7 @@ def _bind(lib, prefix):
         "k_mch_1st": (None, [cfgp, vp, vp, vp, vp, vp, vp, vp]),
         "k_mch_2nd": (None, [cfgp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "k_reduce": (C.c_double, [cfgp, vp, vp]),
+        "k_advance": (None, [cfgp, vp, vp, C.c_double]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, prefix + name)
@@ -241,5 +242,13 @@ class CpuSim:
         self._f("k_mch_2nd")(C.byref(self.c), _ptr(d), _ptr(state), _ptr(bed), _ptr(manning),
                              *[_ptr(f) for f in faces])
 
-    def k_reduce(self, state, bed):
-        return self._f("k_reduce")(C.byref(self.c), _ptr(state), _ptr(bed))
+    def k_reduce(self, state, bed, rows=None):
+        c = self.c
+        if rows is not None:   # reduce over a sub-block of whole rows
+            c = HpoConfig.from_buffer_copy(self.c)
+            c.rows = rows
+        return self._f("k_reduce")(C.byref(c), _ptr(state), _ptr(bed))
+
+    def k_advance(self, clock, counters, vmax):
+        """clock: 5 reals {time, timestep, time_hydro, target, batch}; counters: 2 uint32."""
+        self._f("k_advance")(C.byref(self.c), _ptr(clock), _ptr(counters), float(vmax))

@@ -103,7 +103,10 @@ typedef struct hpo_bdy_cell {
     void   P##k_mch_2nd(const hpo_config*, const void* dt, void* state, const void* bed,        \
                         const void* manning, const void* fN, const void* fE, const void* fS,    \
                         const void* fW);                                                        \
-    double P##k_reduce(const hpo_config*, const void* state, const void* bed);
+    double P##k_reduce(const hpo_config*, const void* state, const void* bed);                  \
+    /* tst_Advance_Normal on a caller-owned clock {time, timestep, time_hydro, target, batch}  \
+       (reals) + {successful, skipped} (uint32) with an already reduced maximum wave speed */   \
+    void   P##k_advance(const hpo_config*, void* clock_reals5, uint32_t* counters2, double vmax);
 
 HPO_DECLARE(hpo_f64_)
 HPO_DECLARE(hpo_f32_)

@@ -244,6 +244,11 @@ template <class R, class Kernels> class Sim {
         KERNELS::reduce(*c, static_cast<const hpo::Vec4<R>*>(st), static_cast<const R*>(bed), red.data(), w);               \
         R m = R(0); for (size_t i = 0; i < w; ++i) if (red[i] > m) m = red[i];                                              \
         return static_cast<double>(m); }                                                                                    \
+    void P##k_advance(const hpo_config* c, void* clock, uint32_t* counters, double vmax) {                                  \
+        KERNELS::configure(*c, 1);                                                                                          \
+        R* k = static_cast<R*>(clock);                                                                                      \
+        R red = static_cast<R>(vmax);                                                                                       \
+        KERNELS::advance(*c, &k[0], &k[1], &k[2], &red, 1, &k[3], &k[4], &counters[0], &counters[1]); }                     \
     }
 
 #endif

@@ -230,7 +230,7 @@ int encode_plane_map(void* out128, void* plane, const hp::Grid& g, size_t rb, in
 }
 
 int build_tma_maps(hp_scheme* s) {
-    const int halo = 1;
+    const int halo = s->cfg.scheme == HP_SCHEME_MUSCL_HANCOCK ? 2 : 1;
     int rc;
     hp::Planes* bufs[2] = {&s->A, &s->B};
     hp::TmaMapsPOD* maps[2] = {&s->maps_a, &s->maps_b};
@@ -442,7 +442,8 @@ int hp_scheme_create(hp_executor* ex, const hp_scheme_config* cfg, hp_scheme** o
         if ((rc = dev_alloc(s, reinterpret_cast<char**>(&s->staging), s->staging_bytes))) break;
         if ((rc = write_clock(s, 0.0, cfg->initial_timestep, 0.0, 0.0))) break;
         // TMA-staged kernels: the fast flavour's Godunov step (others use the plain-load kernels)
-        s->use_tma = s->K->step_tma != nullptr && !(cfg->options & HP_OPT_NO_TMA) && cfg->scheme == HP_SCHEME_GODUNOV;
+        s->use_tma = s->K->step_tma != nullptr && !(cfg->options & HP_OPT_NO_TMA) &&
+                     (cfg->scheme == HP_SCHEME_GODUNOV || cfg->scheme == HP_SCHEME_MUSCL_HANCOCK);
         if (s->use_tma && (rc = build_tma_maps(s))) break;
     } while (0);
     if (rc != HP_OK) { hp_scheme_destroy(s); return rc; }

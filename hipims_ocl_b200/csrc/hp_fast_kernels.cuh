@@ -122,7 +122,7 @@ struct TmaMaps { CUtensorMap eta, qx, qy, zb; };
 // One shared face in the normal frame: state of the two sides -> core flux {m, n, t}.
 // "core" = without the -g/2 z'^2 part of the pressure, which is owner specific and handled in
 // closed form by the cell update (see header comment).
-template <class R>
+template <class R, bool CACHED_CELERITY = true>
 __device__ __forceinline__ Flux3<R> face_core_flux(const Params<R>& k, R etaL, R zL, R unL, R utL, R cL, R etaR, R zR, R unR,
                                                    R utR, R cR) {
     const R hg = R(0.5) * k.g;
@@ -137,8 +137,8 @@ __device__ __forceinline__ Flux3<R> face_core_flux(const Params<R>& k, R etaL, R
     if (dryL) { unL = R(0); utL = R(0); }
     if (dryR) { unR = R(0); utR = R(0); }
     // celerity: the cell's own sqrt(g h) is reused whenever the face sits on the cell's own bed
-    const R aL = (zmax == zL) ? cL : fm_sqrt(k.g * hL);
-    const R aR = (zmax == zR) ? cR : fm_sqrt(k.g * hR);
+    const R aL = (CACHED_CELERITY && zmax == zL) ? cL : fm_sqrt(k.g * hL);
+    const R aR = (CACHED_CELERITY && zmax == zR) ? cR : fm_sqrt(k.g * hR);
     const R qnL = hL * unL, qnR = hR * unR;
     const R as = hp_abs(R(0.5) * (aL + aR) + R(0.25) * (unL - unR));     // sqrt(g h*) without the sqrt
     const R us = R(0.5) * (unL + unR) + aL - aR;
@@ -407,6 +407,284 @@ template <class R> static int launch_godunov_tma(const StepArgs& a_in, const Tma
     if (grid > tiles) grid = tiles;
     a.total_ctas = grid;
     godunov_step_tma<R><<<grid, T::NT, T::SMEM_BYTES, st>>>(a, maps);
+    return 1;
+}
+
+// =============================================================================================
+// MUSCL-Hancock, predictor + corrector fused, on TMA-staged tiles with shared faces.
+//
+// Phase A  TMA: eta, qx, qy, zb for the tile and a halo of two cells (the corrector needs the
+//          neighbours' predictor output, which needs their neighbours); eta_max only matters as two
+//          per-cell flags (boundary cell, "dry" neighbour) and is read with plain loads.
+// Phase B  predictor for the tile + one halo cell: MINMOD slopes (no division), half-step evolve.
+//          Kept per cell in shared memory: the evolved state and the eight slopes -- the reference
+//          writes 4 face vectors per cell to global memory and reads 8 back
+//          (src/Schemes/CLSchemeMUSCLHancock.clc:137-143, 600-635).
+// Phase C  every face once: both sides' face estimates are rebuilt from (evolved state +- slope/2).
+// Phase D  corrector; state ping-pongs and every owned cell is written (see step_mh_v1).
+// =============================================================================================
+template <class R> struct TileMH {
+    static constexpr int TX = 64, TY = 8, NT = 256;
+    static constexpr int CTAS_PER_SM = sizeof(R) == 8 ? 2 : 3;
+    static constexpr int CO = 16 / int(sizeof(R));                // >= 2 halo columns, box starts 16-byte aligned
+    static constexpr int BW = TX + 2 * CO, BH = TY + 4;
+    static constexpr int PLANE_BYTES = (BW * BH * int(sizeof(R)) + 127) / 128 * 128;
+    static constexpr int FLAG_BYTES = (BW * BH + 127) / 128 * 128;
+    static constexpr int PW = TX + 2, PH = TY + 2;                // predictor cells: tile + one halo cell
+    static constexpr int PPLANE = PW * PH;                        // elements per predictor plane
+    static constexpr int NPRED = 11;                              // eta2 qx2 qy2 | sx(eta,h,qx,qy) | sy(eta,h,qx,qy)
+    static constexpr int NXF = (TX + 1) * TY, NYF = TX * (TY + 1), NF = NXF + NYF;
+    static constexpr int OFF_FLAGS = 4 * PLANE_BYTES;
+    static constexpr int OFF_PRED = OFF_FLAGS + FLAG_BYTES;
+    static constexpr int OFF_FLUX = OFF_PRED + (NPRED * PPLANE * int(sizeof(R)) + 127) / 128 * 128;
+    static constexpr int OFF_BAR = OFF_FLUX + (3 * NF * int(sizeof(R)) + 127) / 128 * 128;
+    static constexpr int SMEM_BYTES = OFF_BAR + 64;
+};
+
+template <class R> __device__ __forceinline__ R minmod(R a, R b) {
+    // phi(r) a with r = b / a, phi = max(0, min(r, 1)) (CLSlopeLimiterMINMOD.clc:49-70, beta = 1)
+    return (a * b <= R(0)) ? R(0) : (hp_abs(b) < hp_abs(a) ? b : a);
+}
+
+template <class R>
+__global__ void __launch_bounds__(TileMH<R>::NT, TileMH<R>::CTAS_PER_SM)
+mh_step_tma(const StepArgs a, const __grid_constant__ TmaMaps maps) {
+    using T = TileMH<R>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char* base = smem_raw;
+    const R* const t_eta = reinterpret_cast<const R*>(base);
+    const R* const t_qx = reinterpret_cast<const R*>(base + T::PLANE_BYTES);
+    const R* const t_qy = reinterpret_cast<const R*>(base + 2 * T::PLANE_BYTES);
+    const R* const t_zb = reinterpret_cast<const R*>(base + 3 * T::PLANE_BYTES);
+    unsigned char* const s_flag = base + T::OFF_FLAGS;            // bit0: eta_max <= -9998, bit1: eta_max < eps
+    R* const s_p = reinterpret_cast<R*>(base + T::OFF_PRED);      // [NPRED][PH][PW]
+    R* const s_f = reinterpret_cast<R*>(base + T::OFF_FLUX);      // [3][NF]
+    uint64_t* const s_bar = reinterpret_cast<uint64_t*>(base + T::OFF_BAR);
+
+    const Params<R> k = make_params<R>(a.params);
+    const Grid g = a.grid;
+    const int tid = threadIdx.x;
+    const R dt = read_timestep<R>(a.clock);
+    const R inv_delta = fm_rcp(k.delta);
+    const R hg = R(0.5) * k.g, half = R(0.5);
+
+    const int tiles_x = (g.cols + T::TX - 1) / T::TX;
+    const int tiles_y = (a.y1 - a.y0 + T::TY - 1) / T::TY;
+    const int ntiles = tiles_x * tiles_y;
+    const uint32_t bar = smem_u32(&s_bar[0]);
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const View<R> s(a.src);
+    const MutView<R> d(a.dst);
+    const R* __restrict__ mann = static_cast<const R*>(a.manning);
+    R ws = R(0);
+    uint32_t phase = 0;
+
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int x0 = (tile % tiles_x) * T::TX, y0 = a.y0 + (tile / tiles_x) * T::TY;
+        if (tid == 0) {
+            mbar_expect_tx(bar, 4u * T::BW * T::BH * sizeof(R));
+            const uint32_t dst = smem_u32(base);
+            tma_load_2d(dst + 0 * T::PLANE_BYTES, &maps.eta, x0 - T::CO, y0 - 2, bar);
+            tma_load_2d(dst + 1 * T::PLANE_BYTES, &maps.qx, x0 - T::CO, y0 - 2, bar);
+            tma_load_2d(dst + 2 * T::PLANE_BYTES, &maps.qy, x0 - T::CO, y0 - 2, bar);
+            tma_load_2d(dst + 3 * T::PLANE_BYTES, &maps.zb, x0 - T::CO, y0 - 2, bar);
+        }
+        // eta_max: flags for tile + halo 2 (plain loads), own values kept for phase D
+        for (int i = tid; i < (T::TX + 4) * T::BH; i += T::NT) {
+            const int lx = i % (T::TX + 4) + T::CO - 2, ly = i / (T::TX + 4);
+            const int x = x0 + lx - T::CO, y = y0 + ly - 2;
+            unsigned char fl = 0;
+            if (x >= 0 && x < g.cols && y >= 0 && y < g.rows) {
+                const R em = s.emax[static_cast<size_t>(y) * g.pitch + x];
+                fl = (em <= R(-9998.0) ? 1 : 0) | (em < k.eps ? 2 : 0);
+            }
+            s_flag[ly * T::BW + lx] = fl;
+        }
+        R pre_emax[2], pre_mann[2];
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            const int x = x0 + tid % T::TX, y = y0 + tid / T::TX + hf * (T::TY / 2);
+            const bool in = x < g.cols && y < a.y1;
+            const size_t id = static_cast<size_t>(in ? y : a.y0) * g.pitch + (in ? x : 0);
+            pre_emax[hf] = s.emax[id];
+            pre_mann[hf] = k.friction ? mann[id] : R(0);
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        __syncthreads();   // flags visible
+
+        // ---- phase B: predictor -------------------------------------------------------------------
+        for (int i = tid; i < T::PPLANE; i += T::NT) {
+            const int lx = i % T::PW, ly = i / T::PW;               // predictor-plane coordinates
+            const int ci = lx - 1, cj = ly - 1;                     // tile-local cell coordinates
+            const int o = (cj + 2) * T::BW + ci + T::CO;            // raw-plane offset
+            const int x = x0 + ci, y = y0 + cj, gy = y + g.gy0;
+            const R eta = t_eta[o], qx = t_qx[o], qy = t_qy[o], zb = t_zb[o];
+            R e2 = eta, qx2 = qx, qy2 = qy;
+            R sxE = R(0), sxH = R(0), sxQx = R(0), sxQy = R(0), syE = R(0), syH = R(0), syQx = R(0), syQy = R(0);
+            const bool valid = dt > R(0) && x >= 1 && x <= g.cols - 2 && gy >= 1 && gy <= g.grows - 2 && y >= 1 && y <= g.rows - 2;
+            const int oN = o + T::BW, oS = o - T::BW, oE = o + 1, oW = o - 1;
+            const R h = eta - zb;
+            if (valid && !(h < R(1E-5)) && !((s_flag[oN] | s_flag[oE] | s_flag[oS] | s_flag[oW]) & 1)) {
+                const R etaE = t_eta[oE], etaW = t_eta[oW], etaN = t_eta[oN], etaS = t_eta[oS];
+                const R hE = etaE - t_zb[oE], hW = etaW - t_zb[oW], hN = etaN - t_zb[oN], hS = etaS - t_zb[oS];
+                if (!(hW < k.eps || hE < k.eps)) {
+                    sxE = minmod(eta - etaW, etaE - eta); sxH = minmod(h - hW, hE - h);
+                    sxQx = minmod(qx - t_qx[oW], t_qx[oE] - qx); sxQy = minmod(qy - t_qy[oW], t_qy[oE] - qy);
+                }
+                if (!(hS < k.eps || hN < k.eps)) {
+                    syE = minmod(eta - etaS, etaN - eta); syH = minmod(h - hS, hN - h);
+                    syQx = minmod(qx - t_qx[oS], t_qx[oN] - qx); syQy = minmod(qy - t_qy[oS], t_qy[oN] - qy);
+                }
+                // face estimates at the old time level and their analytic fluxes
+                const R hEf = h + half * sxH, hWf = h - half * sxH, hNf = h + half * syH, hSf = h - half * syH;
+                const R qxE = qx + half * sxQx, qxW = qx - half * sxQx, qyE = qy + half * sxQy, qyW = qy - half * sxQy;
+                const R qxN = qx + half * syQx, qxS = qx - half * syQx, qyN = qy + half * syQy, qyS = qy - half * syQy;
+                const R uE = hEf < k.eps ? R(0) : qxE * fm_rcp(hEf), uW = hWf < k.eps ? R(0) : qxW * fm_rcp(hWf);
+                const R vN = hNf < k.eps ? R(0) : qyN * fm_rcp(hNf), vS = hSf < k.eps ? R(0) : qyS * fm_rcp(hSf);
+                // flux divergence - bed-slope source; the hydrostatic parts collapse to g/2 (hE+hW) d(eta)
+                R dEta = ((qxE - qxW) + (qyN - qyS)) * inv_delta;
+                R dQx = (uE * qxE - uW * qxW + vN * qxN - vS * qxS + hg * sxE * (hEf + hWf)) * inv_delta;
+                R dQy = (uE * qyE - uW * qyW + vN * qyN - vS * qyS + hg * syE * (hNf + hSf)) * inv_delta;
+                dEta = chop(dEta, k.eps); dQx = chop(dQx, k.eps); dQy = chop(dQy, k.eps);
+                e2 = eta - half * dt * dEta; qx2 = qx - half * dt * dQx; qy2 = qy - half * dt * dQy;
+            }
+            s_p[0 * T::PPLANE + i] = e2;   s_p[1 * T::PPLANE + i] = qx2;  s_p[2 * T::PPLANE + i] = qy2;
+            s_p[3 * T::PPLANE + i] = sxE;  s_p[4 * T::PPLANE + i] = sxH;  s_p[5 * T::PPLANE + i] = sxQx; s_p[6 * T::PPLANE + i] = sxQy;
+            s_p[7 * T::PPLANE + i] = syE;  s_p[8 * T::PPLANE + i] = syH;  s_p[9 * T::PPLANE + i] = syQx; s_p[10 * T::PPLANE + i] = syQy;
+        }
+        __syncthreads();
+
+        // ---- phase C: every face once --------------------------------------------------------------
+        if (dt > R(0)) {
+            for (int f = tid; f < T::NF; f += T::NT) {
+                const bool isx = f < T::NXF;
+                const int gq = isx ? f : f - T::NXF;
+                const int w = isx ? T::TX + 1 : T::TX;
+                const int j = gq / w, i = gq - j * w;
+                // x-face: cells (i-1, j) | (i, j);  y-face: cells (i, j-1) | (i, j)
+                const int pL = isx ? (j + 1) * T::PW + i : j * T::PW + i + 1;
+                const int pR = isx ? pL + 1 : pL + T::PW;
+                const int oL = isx ? (j + 2) * T::BW + i - 1 + T::CO : (j + 1) * T::BW + i + T::CO;
+                const int oR = isx ? oL + 1 : oL + T::BW;
+                const int sb = isx ? 3 : 7;                         // slope block of this direction
+                const R etaL = s_p[pL] + half * s_p[sb * T::PPLANE + pL], etaR = s_p[pR] - half * s_p[sb * T::PPLANE + pR];
+                const R hfL = (s_p[pL] - t_zb[oL]) + half * s_p[(sb + 1) * T::PPLANE + pL];
+                const R hfR = (s_p[pR] - t_zb[oR]) - half * s_p[(sb + 1) * T::PPLANE + pR];
+                const R qxL = s_p[T::PPLANE + pL] + half * s_p[(sb + 2) * T::PPLANE + pL], qxR = s_p[T::PPLANE + pR] - half * s_p[(sb + 2) * T::PPLANE + pR];
+                const R qyL = s_p[2 * T::PPLANE + pL] + half * s_p[(sb + 3) * T::PPLANE + pL], qyR = s_p[2 * T::PPLANE + pR] - half * s_p[(sb + 3) * T::PPLANE + pR];
+                const R rL = hfL <= k.eps ? R(0) : fm_rcp(hfL), rR = hfR <= k.eps ? R(0) : fm_rcp(hfR);   // CLSchemeMUSCLHancock.clc:1140-1150
+                const R uL = qxL * rL, vL = qyL * rL, uR = qxR * rR, vR = qyR * rR;
+                const Flux3<R> F = isx ? face_core_flux<R, false>(k, etaL, etaL - hfL, uL, vL, R(0), etaR, etaR - hfR, uR, vR, R(0))
+                                       : face_core_flux<R, false>(k, etaL, etaL - hfL, vL, uL, R(0), etaR, etaR - hfR, vR, uR, R(0));
+                s_f[f] = F.m; s_f[T::NF + f] = F.n; s_f[2 * T::NF + f] = F.t;
+            }
+        }
+        __syncthreads();
+
+        // ---- phase D: corrector, two cells per thread ------------------------------------------------
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            const int i = tid % T::TX, j = tid / T::TX + hf * (T::TY / 2);
+            const int x = x0 + i, y = y0 + j;
+            if (x >= g.cols || y >= a.y1) continue;
+            const int o = (j + 2) * T::BW + i + T::CO, p = (j + 1) * T::PW + i + 1;
+            const size_t id = static_cast<size_t>(y) * g.pitch + x;
+            const int gy = y + g.gy0;
+            Cell<R> c{t_eta[o], pre_emax[hf], t_qx[o], t_qy[o]};
+            const R zb = t_zb[o];
+            const bool interior = x >= 2 && x <= g.cols - 3 && gy >= 2 && gy <= g.grows - 3;   // ring of two is frozen
+            if (interior && dt > R(0) && !(c.emax <= R(-9999.0) || c.eta == R(-9999.0))) {
+                int dry = (c.eta - zb < k.eps) ? 1 : 0;
+                dry += (s_flag[o + T::BW] >> 1) + (s_flag[o + 1] >> 1) + (s_flag[o - T::BW] >> 1) + (s_flag[o - 1] >> 1);
+                if (dry < 5) {
+                    const R e2 = s_p[p], hc2 = e2 - zb;
+                    const R sxE = s_p[3 * T::PPLANE + p], sxH = s_p[4 * T::PPLANE + p];
+                    const R syE = s_p[7 * T::PPLANE + p], syH = s_p[8 * T::PPLANE + p];
+                    int stop = 0;
+                    R bN, bS, bE, bW, hnN, hnS, hnE, hnW;
+                    // owner-side terms of one face: own face estimate (etaO, hO) against the neighbour's
+                    auto owner = [&](const bool ownIsLeft, const bool isx, const R etaO, const R hO, const int pn, const int on,
+                                     R& bed, R& hNb) {
+                        const int sb = isx ? 3 : 7;
+                        const R sgn = ownIsLeft ? -half : half;        // the neighbour's facing estimate
+                        const R etaN_ = s_p[pn] + sgn * s_p[sb * T::PPLANE + pn];
+                        const R hN_ = (s_p[pn] - t_zb[on]) + sgn * s_p[(sb + 1) * T::PPLANE + pn];
+                        const R zO = etaO - hO, zN_ = etaN_ - hN_;
+                        const R zmax = zO > zN_ ? zO : zN_;
+                        const R hOwn = (etaO - zmax > R(0)) ? (etaO - zmax) : R(0);
+                        hNb = (etaN_ - zmax > R(0)) ? (etaN_ - zmax) : R(0);
+                        bed = zmax < etaO ? zmax : etaO;
+                        if (hOwn <= k.eps || hNb <= k.eps) {               // wet/dry front: stop tests (:1172-1204)
+                            const int qb = isx ? 1 : 2;                    // normal discharge plane
+                            const R qO = s_p[qb * T::PPLANE + p] + (ownIsLeft ? half : -half) * s_p[(sb + qb + 1) * T::PPLANE + p];
+                            const R qN_ = s_p[qb * T::PPLANE + pn] + sgn * s_p[(sb + qb + 1) * T::PPLANE + pn];
+                            const R unO = hO <= k.eps ? R(0) : qO * fm_rcp(hO), unN = hN_ <= k.eps ? R(0) : qN_ * fm_rcp(hN_);
+                            const R ownQn = isx ? c.qx : c.qy;
+                            const R hL = ownIsLeft ? hOwn : hNb, hR = ownIsLeft ? hNb : hOwn;
+                            const R unL = ownIsLeft ? unO : unN, unR = ownIsLeft ? unN : unO;
+                            if (ownIsLeft) { if (hL <= k.eps && ownQn > R(0)) ++stop; }
+                            else           { if (hR <= k.eps && ownQn < R(0)) ++stop; }
+                            if (hR <= k.eps && unL < R(0)) ++stop;
+                            if (hL <= k.eps && unR > R(0)) ++stop;
+                        }
+                    };
+                    owner(true, false, e2 + half * syE, hc2 + half * syH, p + T::PW, o + T::BW, bN, hnN);
+                    owner(false, false, e2 - half * syE, hc2 - half * syH, p - T::PW, o - T::BW, bS, hnS);
+                    owner(true, true, e2 + half * sxE, hc2 + half * sxH, p + 1, o + 1, bE, hnE);
+                    owner(false, true, e2 - half * sxE, hc2 - half * sxH, p - 1, o - 1, bW, hnW);
+                    const int fe = j * (T::TX + 1) + i + 1, fw = fe - 1;
+                    const int fn = T::NXF + (j + 1) * T::TX + i, fs = fn - T::TX;
+                    R dEta = ((s_f[fe] - s_f[fw]) + (s_f[fn] - s_f[fs])) * inv_delta;
+                    R dQx = ((s_f[T::NF + fe] - s_f[T::NF + fw]) + (s_f[2 * T::NF + fn] - s_f[2 * T::NF + fs]) +
+                             hg * (bE - bW) * (hnE + hnW)) * inv_delta;
+                    R dQy = ((s_f[2 * T::NF + fe] - s_f[2 * T::NF + fw]) + (s_f[T::NF + fn] - s_f[T::NF + fs]) +
+                             hg * (bN - bS) * (hnN + hnS)) * inv_delta;
+                    dEta = chop(dEta, k.eps); dQx = chop(dQx, k.eps); dQy = chop(dQy, k.eps);
+                    if (stop > 0) { c.qx = R(0); c.qy = R(0); }
+                    c.eta = c.eta - dt * dEta; c.qx = c.qx - dt * dQx; c.qy = c.qy - dt * dQy;
+                    const R h_new = c.eta - zb;
+                    if (k.friction && !(h_new < k.eps)) friction_fast(k, h_new, fm_rcp(h_new), c.qx, c.qy, pre_mann[hf], dt);
+                    if (h_new < k.eps) c.eta = zb;
+                    if (c.eta > c.emax && c.emax > R(-9990.0)) c.emax = c.eta;
+                }
+            }
+            d.store(id, c);
+            if (a.reduce_mode != hp::kReduceNone) {
+                const R h = c.eta - zb;
+                if (h > k.eps10 && c.emax > R(-9999.0)) {
+                    const R cc = fm_sqrt(k.g * h);
+                    R sp = cc;
+                    if (!k.simplified_speed) { const R rh = fm_rcp(h); sp = hp_fmax(hp_abs(c.qx * rh), hp_abs(c.qy * rh)) + cc; }
+                    ws = sp > ws ? sp : ws;
+                }
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+    }
+    block_reduce_finalize<R>(ws, a, k);
+}
+
+template <class R> static int launch_mh_tma(const StepArgs& a_in, const TmaMaps& maps, int sm_count, cudaStream_t st) {
+    using T = TileMH<R>;
+    StepArgs a = a_in;
+    if (a.y1 <= a.y0) return 0;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(mh_step_tma<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES);
+        configured = true;
+    }
+    const int tiles = ((a.grid.cols + T::TX - 1) / T::TX) * ((a.y1 - a.y0 + T::TY - 1) / T::TY);
+    int grid = T::CTAS_PER_SM * sm_count;
+    if (grid > tiles) grid = tiles;
+    a.total_ctas = grid;
+    mh_step_tma<R><<<grid, T::NT, T::SMEM_BYTES, st>>>(a, maps);
     return 1;
 }
 

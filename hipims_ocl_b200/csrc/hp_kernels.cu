@@ -412,10 +412,12 @@ namespace HP_NS {
 #ifndef HP_FLAVOUR_STRICT
 static_assert(sizeof(TmaMaps) == sizeof(hp::TmaMapsPOD), "descriptor block layout");
 static_assert(Tile<double>::BW == hp::tma_box_w(8, 1) && Tile<float>::BW == hp::tma_box_w(4, 1) && Tile<double>::BH == hp::tma_box_h(1), "tile box");
+static_assert(TileMH<double>::BW == hp::tma_box_w(8, 2) && TileMH<float>::BW == hp::tma_box_w(4, 2) && TileMH<double>::BH == hp::tma_box_h(2), "tile box");
 static int launch_step_tma(int scheme, int real_bytes, const StepArgs& a, const hp::TmaMapsPOD* maps, int sm_count, cudaStream_t st) {
-    if (scheme != 0) return -1;
     const TmaMaps& m = *reinterpret_cast<const TmaMaps*>(maps);
-    return real_bytes == 8 ? launch_godunov_tma<double>(a, m, sm_count, st) : launch_godunov_tma<float>(a, m, sm_count, st);
+    if (scheme == 0) return real_bytes == 8 ? launch_godunov_tma<double>(a, m, sm_count, st) : launch_godunov_tma<float>(a, m, sm_count, st);
+    if (scheme == 1) return real_bytes == 8 ? launch_mh_tma<double>(a, m, sm_count, st) : launch_mh_tma<float>(a, m, sm_count, st);
+    return -1;
 }
 #endif
 

@@ -37,6 +37,11 @@ WORKLOADS = {
     "dambreak4096": dict(scheme="godunov", precision="double", cols=4096, rows_per_gpu=4096, scenario="dambreak"),
     "dambreak4096-f32": dict(scheme="godunov", precision="single", cols=4096, rows_per_gpu=4096, scenario="dambreak"),
     "dambreak4096-mh": dict(scheme="muscl-hancock", precision="double", cols=4096, rows_per_gpu=4096, scenario="dambreak"),
+    "dambreak4096-mh-f32": dict(scheme="muscl-hancock", precision="single", cols=4096, rows_per_gpu=4096, scenario="dambreak"),
+    "dambreak4096-inertial": dict(scheme="inertial", precision="double", cols=4096, rows_per_gpu=4096, scenario="dambreak"),
+    "dambreak4096-inertial-f32": dict(scheme="inertial", precision="single", cols=4096, rows_per_gpu=4096, scenario="dambreak"),
+    "pluvial4096-mh": dict(scheme="muscl-hancock", precision="double", cols=4096, rows_per_gpu=4096, scenario="pluvial"),
+    "pluvial4096": dict(scheme="godunov", precision="double", cols=4096, rows_per_gpu=4096, scenario="pluvial"),
     "pluvial16384": dict(scheme="muscl-hancock", precision="double", cols=16384, rows_per_gpu=16384, scenario="pluvial"),
     "river32768": dict(scheme="muscl-hancock", precision="double", cols=32768, rows_per_gpu=4096, scenario="valley"),
 }
@@ -366,7 +371,7 @@ def main():
 def run_variants(hx, ex, args):
     """Short device-resident runs of the other precision / schemes on the same 4096^2 dam break."""
     out = {}
-    for name in ("dambreak4096-f32", "dambreak4096-mh"):
+    for name in ("dambreak4096-f32", "dambreak4096-mh", "dambreak4096-mh-f32", "dambreak4096-inertial-f32"):
         w = WORKLOADS[name]
         cfg = cfg_for(w, w["rows_per_gpu"], w["cols"])
         dtype = np.float64 if cfg.precision == "double" else np.float32

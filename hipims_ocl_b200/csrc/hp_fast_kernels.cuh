@@ -26,53 +26,6 @@
 namespace HP_NS {
 
 // ---------------------------------------------------------------------------------------------
-// Low-op-count elementary functions (full working precision to ~1 ulp, no slow paths).
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ double fm_rcp(double a) {
-    double x;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
-    double e = fma(-a, x, 1.0); x = fma(x, e, x);
-    e = fma(-a, x, 1.0); x = fma(x, e, x);
-    return x;
-}
-__device__ __forceinline__ float fm_rcp(float a) {
-    float x;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(x) : "f"(a));
-    const float e = fmaf(-a, x, 1.0f);
-    return fmaf(x, e, x);
-}
-// sqrt for a >= 0 (returns 0 for a == 0)
-__device__ __forceinline__ double fm_sqrt(double a) {
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
-    double g = a * y, h = 0.5 * y;
-    double r = fma(-g, h, 0.5); g = fma(g, r, g); h = fma(h, r, h);
-    r = fma(-g, h, 0.5); g = fma(g, r, g); h = fma(h, r, h);
-    const double d = fma(-g, g, a);
-    g = fma(d, h, g);
-    return a > 0.0 ? g : 0.0;
-}
-__device__ __forceinline__ float fm_sqrt(float a) {
-    float y;
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(a));
-    float g = a * y;
-    const float h = 0.5f * y;
-    const float d = fmaf(-g, g, a);
-    g = fmaf(d, h, g);
-    return a > 0.0f ? g : 0.0f;
-}
-// a^(-1/3) for a > 0: single-precision seed (MUFU lg2/ex2) + two Newton steps y <- y (4 - a y^3) / 3
-__device__ __forceinline__ double fm_rcbrt(double a) {
-    double y = static_cast<double>(exp2f(-0.333333343f * __log2f(static_cast<float>(a))));
-    double t = y * y * y;
-    y = y * fma(-0.33333333333333333 * a, t, 1.3333333333333333);
-    t = y * y * y;
-    y = y * fma(-0.33333333333333333 * a, t, 1.3333333333333333);
-    return y;
-}
-__device__ __forceinline__ float fm_rcbrt(float a) { return rcbrtf(a); }
-
-// ---------------------------------------------------------------------------------------------
 // TMA / mbarrier primitives
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }

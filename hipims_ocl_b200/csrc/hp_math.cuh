@@ -62,6 +62,56 @@ template <class R> __device__ __forceinline__ R hp_fmod(R a, R b);
 template <> __device__ __forceinline__ double hp_fmod<double>(double a, double b) { return fmod(a, b); }
 template <> __device__ __forceinline__ float hp_fmod<float>(float a, float b) { return fmodf(a, b); }
 
+#ifndef HP_FLAVOUR_STRICT
+// ---------------------------------------------------------------------------------------------
+// Low-op-count elementary functions (full working precision to ~1 ulp, no slow paths).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double fm_rcp(double a) {
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
+    double e = fma(-a, x, 1.0); x = fma(x, e, x);
+    e = fma(-a, x, 1.0); x = fma(x, e, x);
+    return x;
+}
+__device__ __forceinline__ float fm_rcp(float a) {
+    float x;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(x) : "f"(a));
+    const float e = fmaf(-a, x, 1.0f);
+    return fmaf(x, e, x);
+}
+// sqrt for a >= 0 (returns 0 for a == 0)
+__device__ __forceinline__ double fm_sqrt(double a) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    double g = a * y, h = 0.5 * y;
+    double r = fma(-g, h, 0.5); g = fma(g, r, g); h = fma(h, r, h);
+    r = fma(-g, h, 0.5); g = fma(g, r, g); h = fma(h, r, h);
+    const double d = fma(-g, g, a);
+    g = fma(d, h, g);
+    return a > 0.0 ? g : 0.0;
+}
+__device__ __forceinline__ float fm_sqrt(float a) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(a));
+    float g = a * y;
+    const float h = 0.5f * y;
+    const float d = fmaf(-g, g, a);
+    g = fmaf(d, h, g);
+    return a > 0.0f ? g : 0.0f;
+}
+// a^(-1/3) for a > 0: single-precision seed (MUFU lg2/ex2) + two Newton steps y <- y (4 - a y^3) / 3
+__device__ __forceinline__ double fm_rcbrt(double a) {
+    double y = static_cast<double>(exp2f(-0.333333343f * __log2f(static_cast<float>(a))));
+    double t = y * y * y;
+    y = y * fma(-0.33333333333333333 * a, t, 1.3333333333333333);
+    t = y * y * y;
+    y = y * fma(-0.33333333333333333 * a, t, 1.3333333333333333);
+    return y;
+}
+__device__ __forceinline__ float fm_rcbrt(float a) { return rcbrtf(a); }
+
+#endif  // !HP_FLAVOUR_STRICT
+
 // ---------------------------------------------------------------------------------------------
 // HLLC approximate Riemann solver in the face-normal frame.
 // Must reproduce riemannSolver(), src/Solvers/CLSolverHLLC.clc:27-248.
@@ -343,6 +393,22 @@ __device__ __forceinline__ R inertial_flux(const Params<R>& k, R n, R dt, R prev
     return q;
 }
 
+#ifndef HP_FLAVOUR_STRICT
+// Same flux with h^(-7/3) = (1/h)^2 * rcbrt(h) instead of pow(h, 10/3), one reciprocal for the
+// quotient and the Froude limiter written as a clamp |q| <= 0.8 h sqrt(g h).
+template <class R>
+__device__ __forceinline__ R inertial_flux_fast(const Params<R>& k, R n, R dt, R prev, R etaUp, R zUp, R etaDown, R zDown, R inv_delta) {
+    const R h = hp_fmax(etaDown, etaUp) - (zUp < zDown ? zDown : zUp);
+    if (h < k.eps) return R(0);
+    const R slope = (etaDown - etaUp) * inv_delta;
+    const R rh = fm_rcp(h);
+    const R gdt = k.g * dt;
+    const R q = (prev - gdt * h * slope) * fm_rcp(R(1.0) + gdt * n * n * hp_abs(prev) * rh * rh * fm_rcbrt(h));
+    const R qmax = R(0.8) * h * fm_sqrt(k.g * h);
+    return q > qmax ? qmax : (q < -qmax ? -qmax : q);
+}
+#endif
+
 // Reproduces ine_cacheDisabled after its loads, src/Schemes/CLSchemeInertial.clc:92-162.
 template <class R>
 __device__ __forceinline__ bool inertial_update(const Params<R>& k, R dt, Cell<R>& c, R zb, R mann, R etaN, R qyN, R zN,
@@ -354,12 +420,22 @@ __device__ __forceinline__ bool inertial_update(const Params<R>& k, R dt, Cell<R
     if (etaS - zS < k.eps) ++dry;
     if (etaW - zW < k.eps) ++dry;
     if (dry >= 5) return false;
+#ifdef HP_FLAVOUR_STRICT
     const R qN = inertial_flux(k, mann, dt, qyN, etaN, zN, c.eta, zb);
     const R qE = inertial_flux(k, mann, dt, qxE, etaE, zE, c.eta, zb);
     const R qS = inertial_flux(k, mann, dt, c.qy, c.eta, zb, etaS, zS);
     const R qW = inertial_flux(k, mann, dt, c.qx, c.eta, zb, etaW, zW);
     c.qx = qW; c.qy = qS;
     const R dEta = (qE - qW + qN - qS) / k.delta;
+#else
+    const R inv_delta = fm_rcp(k.delta);
+    const R qN = inertial_flux_fast(k, mann, dt, qyN, etaN, zN, c.eta, zb, inv_delta);
+    const R qE = inertial_flux_fast(k, mann, dt, qxE, etaE, zE, c.eta, zb, inv_delta);
+    const R qS = inertial_flux_fast(k, mann, dt, c.qy, c.eta, zb, etaS, zS, inv_delta);
+    const R qW = inertial_flux_fast(k, mann, dt, c.qx, c.eta, zb, etaW, zW, inv_delta);
+    c.qx = qW; c.qy = qS;
+    const R dEta = (qE - qW + qN - qS) * inv_delta;
+#endif
     c.eta = c.eta + dt * dEta;
     if (c.eta > c.emax) c.emax = c.eta;
     if (c.eta - zb < k.eps) c.eta = zb;

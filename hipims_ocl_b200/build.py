@@ -71,6 +71,25 @@ def build(force=False, verbose=False):
     return LIB
 
 
+HOST = os.path.join(HERE, "host")
+HOST_LIB = os.path.join(HERE, "libhipims_host.so")
+HOST_EXE = os.path.join(HERE, "hipims-b200")
+
+
+def build_host(force=False):
+    """C++ host mirror (CScheme*, CDomainCartesian, CBoundary*, XML) above the C ABI + the CLI."""
+    srcs = [os.path.join(HOST, f) for f in ("hipims_host.cpp", "hipims_host.h", "main.cpp")] + [os.path.join(INCLUDE, "hipims_cuda.h")]
+    if not force and os.path.exists(HOST_LIB) and os.path.exists(HOST_EXE) and \
+            all(min(os.path.getmtime(HOST_LIB), os.path.getmtime(HOST_EXE)) >= os.path.getmtime(s) for s in srcs + [LIB]):
+        return HOST_LIB
+    common = ["g++", "-std=c++17", "-O2", "-Wall", "-fPIC", "-I", INCLUDE]
+    link = ["-L", HERE, "-lhipims_cuda", "-Wl,-rpath,$ORIGIN"]
+    _run(common + ["-shared", os.path.join(HOST, "hipims_host.cpp"), "-o", HOST_LIB] + link)
+    _run(common + [os.path.join(HOST, "main.cpp"), os.path.join(HOST, "hipims_host.cpp"), "-o", HOST_EXE] + link)
+    return HOST_LIB
+
+
 if __name__ == "__main__":
     path = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
     print("built", path)
+    print("built", build_host(force="--force" in sys.argv))

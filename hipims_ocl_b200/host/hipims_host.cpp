@@ -1,0 +1,732 @@
+// hipims_host.cpp -- see hipims_host.h.  Host logic only; all device work goes through the C ABI.
+#include "hipims_host.h"
+
+#include <algorithm>
+#include <cctype>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+
+namespace model {
+bool forceAbort = false;
+std::vector<std::string> errorLog;
+// src/main.cpp:631-652: warnings are logged, ModelStop sets forceAbort, Fatal ends the process
+void doError(const std::string& message, unsigned char level) {
+    errorLog.push_back(message);
+    const char* tag = (level & errorCodes::kLevelFatal) ? "FATAL" : (level & errorCodes::kLevelModelStop) ? "STOP" : "WARNING";
+    fprintf(stderr, "[hipims %s] %s\n", tag, message.c_str());
+    if (level & errorCodes::kLevelModelStop) forceAbort = true;
+    if (level & errorCodes::kLevelFatal) exit(1);
+}
+}  // namespace model
+
+namespace {
+enum dataValues { kBedElevation = 0, kDepth, kFreeSurfaceLevel, kVelocityX, kVelocityY, kDischargeX, kDischargeY, kManningCoefficient,
+                  kDisabledCells, kMaxDepth, kMaxFSL, kFroudeNumber, kUnknown = 255 };
+
+bool isValidFloat(const char* s) {
+    if (!s || !*s) return false;
+    char* end = nullptr;
+    strtod(s, &end);
+    return end && *end == 0;
+}
+#define HP_CHECK(call, what)                                                                                      \
+    do { if ((call) < 0) model::doError(std::string(what) + ": " + hp_last_error(), model::errorCodes::kLevelModelStop); } while (0)
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// Util
+// ---------------------------------------------------------------------------------------------
+namespace Util {
+double round(double dValue, unsigned char ucPlaces) {
+    const unsigned int mult = static_cast<unsigned int>(std::pow(10.0, ucPlaces));
+    double v = dValue * mult;
+    const double rem = std::fmod(v, 1);
+    v = (rem >= 0.5) ? std::ceil(v) : std::floor(v);
+    return v / mult;
+}
+std::string toLowercase(const char* s) {
+    std::string r = s ? s : "";
+    std::transform(r.begin(), r.end(), r.begin(), [](unsigned char c) { return std::tolower(c); });
+    return r;
+}
+}  // namespace Util
+
+// ---------------------------------------------------------------------------------------------
+// XML
+// ---------------------------------------------------------------------------------------------
+const char* XMLElement::Attribute(const char* key) const {
+    for (const auto& kv : attributes) if (kv.first == key) return kv.second.c_str();
+    return nullptr;
+}
+const XMLElement* XMLElement::FirstChildElement(const char* tag) const {
+    for (const auto& c : children) if (!tag || c->name == tag) return c.get();
+    return nullptr;
+}
+const XMLElement* XMLElement::NextSiblingElement(const char* tag) const {
+    if (!parent) return nullptr;
+    bool seen = false;
+    for (const auto& c : parent->children) {
+        if (seen && (!tag || c->name == tag)) return c.get();
+        if (c.get() == this) seen = true;
+    }
+    return nullptr;
+}
+
+namespace {
+struct XmlParser {
+    const std::string& s; size_t p = 0; std::string err;
+    explicit XmlParser(const std::string& text) : s(text) {}
+    void skipWs() { while (p < s.size() && std::isspace(static_cast<unsigned char>(s[p]))) ++p; }
+    bool starts(const char* t) const { return s.compare(p, strlen(t), t) == 0; }
+    void skipMisc() {       // whitespace, comments, declarations, DOCTYPE (with an internal subset)
+        for (;;) {
+            skipWs();
+            if (starts("<!--")) { size_t e = s.find("-->", p); p = e == std::string::npos ? s.size() : e + 3; }
+            else if (starts("<?")) { size_t e = s.find("?>", p); p = e == std::string::npos ? s.size() : e + 2; }
+            else if (starts("<!")) {
+                int depth = 0;
+                while (p < s.size()) { char c = s[p++]; if (c == '[') ++depth; else if (c == ']') --depth; else if (c == '>' && depth <= 0) break; }
+            } else return;
+        }
+    }
+    static std::string unescape(const std::string& v) {
+        std::string r; r.reserve(v.size());
+        for (size_t i = 0; i < v.size(); ++i) {
+            if (v[i] != '&') { r += v[i]; continue; }
+            if (v.compare(i, 5, "&amp;") == 0) { r += '&'; i += 4; } else if (v.compare(i, 4, "&lt;") == 0) { r += '<'; i += 3; }
+            else if (v.compare(i, 4, "&gt;") == 0) { r += '>'; i += 3; } else if (v.compare(i, 6, "&quot;") == 0) { r += '"'; i += 5; }
+            else if (v.compare(i, 6, "&apos;") == 0) { r += '\''; i += 5; } else r += v[i];
+        }
+        return r;
+    }
+    std::string name() { size_t b = p; while (p < s.size() && (std::isalnum(static_cast<unsigned char>(s[p])) || strchr("_-:.", s[p]))) ++p; return s.substr(b, p - b); }
+    std::unique_ptr<XMLElement> element(const XMLElement* parent) {
+        if (p >= s.size() || s[p] != '<') { err = "expected '<'"; return nullptr; }
+        ++p;
+        auto e = std::make_unique<XMLElement>();
+        e->parent = parent; e->name = name();
+        if (e->name.empty()) { err = "empty element name"; return nullptr; }
+        for (;;) {
+            skipWs();
+            if (p >= s.size()) { err = "unexpected end inside <" + e->name + ">"; return nullptr; }
+            if (starts("/>")) { p += 2; return e; }
+            if (s[p] == '>') { ++p; break; }
+            std::string key = name();
+            skipWs();
+            if (key.empty() || p >= s.size() || s[p] != '=') { err = "bad attribute in <" + e->name + ">"; return nullptr; }
+            ++p; skipWs();
+            const char q = s[p];
+            if (q != '"' && q != '\'') { err = "unquoted attribute in <" + e->name + ">"; return nullptr; }
+            size_t end = s.find(q, p + 1);
+            if (end == std::string::npos) { err = "unterminated attribute"; return nullptr; }
+            e->attributes.emplace_back(key, unescape(s.substr(p + 1, end - p - 1)));
+            p = end + 1;
+        }
+        for (;;) {
+            size_t lt = s.find('<', p);
+            if (lt == std::string::npos) { err = "missing </" + e->name + ">"; return nullptr; }
+            e->text += unescape(s.substr(p, lt - p));
+            p = lt;
+            if (starts("</")) {
+                p += 2; std::string n = name(); skipWs();
+                if (n != e->name || p >= s.size() || s[p] != '>') { err = "mismatched </" + n + ">"; return nullptr; }
+                ++p; return e;
+            }
+            if (starts("<!--") || starts("<?") || starts("<!")) { skipMisc(); continue; }
+            auto child = element(e.get());
+            if (!child) return nullptr;
+            e->children.push_back(std::move(child));
+        }
+    }
+};
+}  // namespace
+
+bool XMLDocument::Parse(const std::string& xml) {
+    XmlParser ps(xml);
+    ps.skipMisc();
+    root = ps.element(nullptr);
+    error = ps.err;
+    return root != nullptr;
+}
+bool XMLDocument::LoadFile(const std::string& path) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f) { error = "cannot open " + path; return false; }
+    std::stringstream ss; ss << f.rdbuf();
+    return Parse(ss.str());
+}
+
+// ---------------------------------------------------------------------------------------------
+// CSV, raster
+// ---------------------------------------------------------------------------------------------
+bool CCSVDataset::readFile() {
+    std::ifstream f(sFilename);
+    if (!f) return false;
+    std::string line;
+    while (std::getline(f, line)) {
+        while (!line.empty() && (line.back() == '\r' || line.back() == '\n' || line.back() == ' ')) line.pop_back();
+        if (line.empty()) continue;
+        std::vector<std::string> cells; std::string cell; std::stringstream ss(line);
+        while (std::getline(ss, cell, ',')) {
+            size_t b = cell.find_first_not_of(" \t"), e = cell.find_last_not_of(" \t");
+            cells.push_back(b == std::string::npos ? "" : cell.substr(b, e - b + 1));
+        }
+        rows.push_back(cells);
+    }
+    bReady = true;
+    return true;
+}
+
+bool SRaster::read(const std::string& path) {
+    std::ifstream f(path);
+    if (!f) return false;
+    std::string key; double v;
+    std::map<std::string, double> hdr;
+    for (int i = 0; i < 6; ++i) {
+        std::streampos pos = f.tellg();
+        if (!(f >> key)) return false;
+        if (!std::isalpha(static_cast<unsigned char>(key[0]))) { f.seekg(pos); break; }
+        if (!(f >> v)) return false;
+        hdr[Util::toLowercase(key.c_str())] = v;
+    }
+    cols = static_cast<unsigned long>(hdr["ncols"]); rows = static_cast<unsigned long>(hdr["nrows"]);
+    cellsize = hdr.count("cellsize") ? hdr["cellsize"] : 1.0;
+    xll = hdr.count("xllcorner") ? hdr["xllcorner"] : hdr["xllcenter"]; yll = hdr.count("yllcorner") ? hdr["yllcorner"] : hdr["yllcenter"];
+    nodata = hdr.count("nodata_value") ? hdr["nodata_value"] : -9999.0;
+    if (!cols || !rows) return false;
+    values.assign(cols * rows, nodata);
+    for (unsigned long r = 0; r < rows; ++r)            // file is north-first, arrays are south-first
+        for (unsigned long c = 0; c < cols; ++c) if (!(f >> values[(rows - 1 - r) * cols + c])) return false;
+    return true;
+}
+bool SRaster::write(const std::string& path) const {
+    FILE* f = fopen(path.c_str(), "w");
+    if (!f) return false;
+    fprintf(f, "ncols %lu\nnrows %lu\nxllcorner %.10g\nyllcorner %.10g\ncellsize %.10g\nNODATA_value %.10g\n", cols, rows, xll, yll, cellsize, nodata);
+    for (unsigned long r = 0; r < rows; ++r) {
+        for (unsigned long c = 0; c < cols; ++c) fprintf(f, c ? " %.17g" : "%.17g", values[(rows - 1 - r) * cols + c]);
+        fputc('\n', f);
+    }
+    fclose(f);
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Executor
+// ---------------------------------------------------------------------------------------------
+CExecutorControlCUDA* CExecutorControlCUDA::createFromConfig(const XMLElement* pXExecution) {
+    const XMLElement* pX = pXExecution ? pXExecution->FirstChildElement("executor") : nullptr;
+    const std::string name = Util::toLowercase(pX ? pX->Attribute("name") : "cuda");
+    // "OpenCL" configurations are accepted: the CUDA executor is the drop-in for that slot
+    if (name != "cuda" && name != "opencl") {
+        model::doError("Unsupported executor specified in configuration.", model::errorCodes::kLevelFatal);
+        return nullptr;
+    }
+    auto* ex = new CExecutorControlCUDA();
+    if (!ex->setupFromConfig(pX)) { delete ex; return nullptr; }
+    return ex;
+}
+bool CExecutorControlCUDA::setupFromConfig(const XMLElement* pX) {
+    int n = 0;
+    if (hp_device_count(&n) < 0) { model::doError(std::string("No CUDA device: ") + hp_last_error(), model::errorCodes::kLevelModelStop); return false; }
+    uiDeviceCount = static_cast<unsigned int>(n);
+    int device = 1;   // 1-based like getDevice(n)
+    for (const XMLElement* p = pX ? pX->FirstChildElement("parameter") : nullptr; p; p = p->NextSiblingElement("parameter")) {
+        const std::string key = Util::toLowercase(p->Attribute("name"));
+        if (key == "devicenumber" && p->Attribute("value")) device = atoi(p->Attribute("value"));
+        // deviceFilter (GPU|CPU|APU) is accepted and ignored: there is exactly one kind of device here
+    }
+    if (device < 1 || device > n) { model::doError("Invalid device number in configuration.", model::errorCodes::kLevelModelStop); return false; }
+    if (hp_executor_create(device - 1, nullptr, &pExecutor) < 0) { model::doError(hp_last_error(), model::errorCodes::kLevelModelStop); return false; }
+    char buf[256]; int sms = 0; size_t mem = 0;
+    hp_executor_describe(pExecutor, buf, sizeof(buf), &sms, &mem);
+    sDeviceName = buf;
+    return true;
+}
+CExecutorControlCUDA::~CExecutorControlCUDA() { if (pExecutor) hp_executor_destroy(pExecutor); }
+void CExecutorControlCUDA::blockUntilFinished() { if (pExecutor) hp_executor_finish(pExecutor); }
+
+// ---------------------------------------------------------------------------------------------
+// Boundaries
+// ---------------------------------------------------------------------------------------------
+namespace {
+// shared by the uniform and cell series: header row skipped, N numeric columns
+bool readSeries(CCSVDataset* csv, size_t columns, std::vector<double>& out, double& interval, double& length) {
+    bool invalid = false, header = false;
+    out.clear();
+    for (const auto& row : csv->rows) {
+        if (!header) { header = true; continue; }                 // first row is always treated as headers
+        if (row.size() == columns) {
+            for (const auto& c : row) { if (!isValidFloat(c.c_str())) invalid = true; out.push_back(atof(c.c_str())); }
+        } else { invalid = true; for (size_t i = 0; i < columns; ++i) out.push_back(0.0); }
+    }
+    if (invalid) model::doError("Some CSV entries were not valid for a boundary timeseries.", model::errorCodes::kLevelWarning);
+    const size_t n = out.size() / columns;
+    if (n < 2) { model::doError("A boundary timeseries is too short.", model::errorCodes::kLevelWarning); return false; }
+    interval = out[columns] - out[0];
+    length = out[(n - 1) * columns];
+    return true;
+}
+}  // namespace
+
+bool CBoundaryUniform::setupFromConfig(const XMLElement* pElement, const std::string& dir) {
+    sName = pElement->Attribute("name") ? pElement->Attribute("name") : "";
+    const std::string value = Util::toLowercase(pElement->Attribute("value"));
+    if (value.empty() || value == "rain-intensity") ucValue = 0;
+    else if (value == "loss-rate") ucValue = 1;
+    else model::doError("Unrecognised value for uniform timeseries file.", model::errorCodes::kLevelWarning);
+    CCSVDataset csv(dir + Util::toLowercase(pElement->Attribute("source")));
+    if (!csv.readFile()) { model::doError("Could not read a uniform boundary timeseries file.", model::errorCodes::kLevelWarning); return false; }
+    importTimeseries(&csv);
+    return true;
+}
+void CBoundaryUniform::importTimeseries(CCSVDataset* csv) { readSeries(csv, 2, series, dTimeseriesInterval, dTimeseriesLength); }
+void CBoundaryUniform::prepareBoundary(hp_scheme* s, CDomainCartesian*, double) {
+    if (series.size() < 4) return;
+    hp_bdy_uniform conf{static_cast<uint32_t>(series.size() / 2), ucValue, dTimeseriesInterval, dTimeseriesLength};
+    HP_CHECK(hp_boundary_add_uniform(s, &conf, series.data()), "uniform boundary " + sName);
+}
+
+bool CBoundaryCell::setupFromConfig(const XMLElement* pElement, const std::string& dir) {
+    sName = pElement->Attribute("name") ? pElement->Attribute("name") : "";
+    const char* dis = pElement->Attribute("dischargeValue");
+    const char* dep = pElement->Attribute("depthValue");
+    const std::string d = Util::toLowercase(dis), h = Util::toLowercase(dep);
+    bDischargeIsTotal = false;
+    if (!dis || d == "total") { ucDischargeValue = 1; bDischargeIsTotal = true; }
+    else if (d == "cell") { ucDischargeValue = 1; bDischargeIsTotal = true; }     // reference: same enum value as "total"
+    else if (d == "velocity") ucDischargeValue = 2;
+    else if (d == "ignore" || d == "disabled") ucDischargeValue = 0;
+    else if (d == "volume" || d == "surging") ucDischargeValue = 3;
+    else model::doError("Unrecognised discharge parameter specified for timeseries file.", model::errorCodes::kLevelWarning);
+    if (!dep || h == "fsl") ucDepthValue = 1;
+    else if (h == "depth") ucDepthValue = 2;
+    else if (h == "ignore" || h == "disabled") ucDepthValue = 0;
+    else model::doError("Unrecognised depth parameter specified in timeseries file.", model::errorCodes::kLevelWarning);
+    CCSVDataset csv(dir + Util::toLowercase(pElement->Attribute("source")));
+    if (!csv.readFile()) { model::doError("Could not read a boundary timeseries file.", model::errorCodes::kLevelWarning); return false; }
+    importTimeseries(&csv);
+    if (pElement->Attribute("mapFile")) {
+        CCSVDataset map(dir + Util::toLowercase(pElement->Attribute("mapFile")));
+        if (!map.readFile()) { model::doError("Could not read a boundary map file.", model::errorCodes::kLevelWarning); return false; }
+        importMap(&map);
+    }
+    return true;
+}
+void CBoundaryCell::importTimeseries(CCSVDataset* csv) { readSeries(csv, 4, series, dTimeseriesInterval, dTimeseriesLength); }
+void CBoundaryCell::importMap(CCSVDataset* csv) {
+    bool header = false, invalid = false;
+    for (const auto& row : csv->rows) {
+        if (!header) { header = true; continue; }
+        if (row.size() == 2 || (row.size() == 3 && row[2] == sName)) relations.emplace_back(atoi(row[0].c_str()), atoi(row[1].c_str()));
+        else if (row.size() != 3) invalid = true;
+    }
+    if (invalid) model::doError("Some CSV entries were not valid for a boundary map file.", model::errorCodes::kLevelWarning);
+}
+void CBoundaryCell::prepareBoundary(hp_scheme* s, CDomainCartesian* pDomain, double) {
+    if (series.size() < 8 || relations.empty()) return;
+    std::vector<double> ts = series;
+    if (bDischargeIsTotal)                               // CBoundaryCell.cpp:352-356: Q divided by the number of mapped cells
+        for (size_t i = 0; i < ts.size() / 4; ++i) { ts[4 * i + 2] /= relations.size(); ts[4 * i + 3] /= relations.size(); }
+    std::vector<uint64_t> ids;
+    for (const auto& r : relations) ids.push_back(pDomain->getCellID(r.first, r.second));
+    hp_bdy_cell conf{ts.size() / 4, dTimeseriesInterval, dTimeseriesLength, ids.size(), ucDepthValue, ucDischargeValue};
+    HP_CHECK(hp_boundary_add_cell(s, &conf, ids.data(), ts.data()), "cell boundary " + sName);
+}
+
+bool CBoundaryGridded::setupFromConfig(const XMLElement* pElement, const std::string& dir) {
+    sName = pElement->Attribute("name") ? pElement->Attribute("name") : "";
+    sMask = pElement->Attribute("mask") ? pElement->Attribute("mask") : "";
+    sSourceDir = dir;
+    if (!isValidFloat(pElement->Attribute("interval"))) { model::doError("Gridded boundary interval is not a valid number.", model::errorCodes::kLevelWarning); return false; }
+    dInterval = atof(pElement->Attribute("interval"));
+    const std::string value = Util::toLowercase(pElement->Attribute("value"));
+    if (value.empty() || value == "rain-intensity") ucValue = 0;
+    else if (value == "mass-flux") ucValue = 2;           // the reference's host maps this to 1, which its kernel ignores
+    else model::doError("Unrecognised value parameter specified for gridded timeseries data.", model::errorCodes::kLevelWarning);
+    return true;
+}
+void CBoundaryGridded::prepareBoundary(hp_scheme* s, CDomainCartesian* pDomain, double dSimulationLength) {
+    // frames: mask with %n replaced by the frame index (the reference formats a timestamp through
+    // GDAL-readable rasters; here ESRI ASCII grids named by index)
+    std::vector<double> frames; SRaster first; uint64_t entries = 0;
+    for (double t = 0.0; t <= dSimulationLength; t += dInterval) {
+        std::string file = sMask; const size_t pos = file.find("%n");
+        if (pos != std::string::npos) file.replace(pos, 2, std::to_string(entries));
+        SRaster r;
+        if (!r.read(sSourceDir + file)) { model::doError("Gridded boundary raster missing for frame " + std::to_string(entries), model::errorCodes::kLevelWarning); break; }
+        if (entries == 0) first = r;
+        if (r.cols != first.cols || r.rows != first.rows) { model::doError("Gridded boundary rasters differ in size.", model::errorCodes::kLevelWarning); break; }
+        frames.insert(frames.end(), r.values.begin(), r.values.end());
+        ++entries;
+    }
+    if (!entries) return;
+    // the kernel subtracts the offset of the coarse grid's south-west corner from the cell position
+    hp_bdy_gridded conf{dInterval, first.cellsize, first.xll - pDomain->dRealOffsetX, first.yll - pDomain->dRealOffsetY, entries, ucValue, first.rows, first.cols};
+    HP_CHECK(hp_boundary_add_gridded(s, &conf, frames.data()), "gridded boundary " + sName);
+}
+
+bool CBoundaryMap::setupFromConfig(const XMLElement* pX, const std::string& sConfigDir) {
+    if (!pX) return true;
+    std::string dir = pX->Attribute("sourceDir") ? pX->Attribute("sourceDir") : "";
+    if (dir.empty() || dir[0] != '/') dir = sConfigDir + dir;
+    // <domainEdge> elements are accepted and ignored, as in the reference
+    unsigned int autoName = 0;
+    for (const XMLElement* t = pX->FirstChildElement("timeseries"); t; t = t->NextSiblingElement("timeseries")) {
+        const std::string type = Util::toLowercase(t->Attribute("type"));
+        std::unique_ptr<CBoundary> b;
+        if (type == "cell") b.reset(new CBoundaryCell());
+        else if (type == "atmospheric" || type == "uniform") b.reset(new CBoundaryUniform());
+        else if (type == "gridded" || type == "spatially-varying") b.reset(new CBoundaryGridded());
+        else { model::doError("Ignored boundary timeseries of unrecognised type.", model::errorCodes::kLevelWarning); continue; }
+        XMLElement withName;
+        const XMLElement* use = t;
+        if (!t->Attribute("name")) { withName.attributes = t->attributes; withName.attributes.emplace_back("name", "Boundary_" + std::to_string(++autoName)); use = &withName; }
+        if (!b->setupFromConfig(use, dir)) { model::doError("Encountered an error loading a boundary definition.", model::errorCodes::kLevelWarning); continue; }
+        boundaries.push_back(std::move(b));
+    }
+    return true;
+}
+void CBoundaryMap::prepareBoundaries(hp_scheme* s, CDomainCartesian* d, double len) { for (auto& b : boundaries) b->prepareBoundary(s, d, len); }
+CBoundary* CBoundaryMap::getBoundaryByName(const std::string& n) { for (auto& b : boundaries) if (b->getName() == n) return b.get(); return nullptr; }
+
+// ---------------------------------------------------------------------------------------------
+// Domain
+// ---------------------------------------------------------------------------------------------
+unsigned char CDomainCartesian::getDataValueCode(const std::string& v) {   // src/Domain/CDomain.cpp:464-500
+    auto has = [&](const char* k) { return v.find(k) != std::string::npos; };
+    if (has("dem")) return kBedElevation;
+    if (has("maxdepth")) return kMaxDepth; else if (has("depth")) return kDepth;
+    if (has("disabled")) return kDisabledCells;
+    if (has("dischargex")) return kDischargeX;
+    if (has("dischargey")) return kDischargeY;
+    if (has("maxfsl")) return kMaxFSL; else if (has("fsl")) return kFreeSurfaceLevel;
+    if (has("manningcoefficient")) return kManningCoefficient;
+    if (has("velocityx")) return kVelocityX;
+    if (has("velocityy")) return kVelocityY;
+    if (has("froude")) return kFroudeNumber;
+    return kUnknown;
+}
+
+void CDomainCartesian::handleInputData(unsigned long id, double v, unsigned char code, unsigned char rounding) {   // CDomain.cpp:294-397
+    double* st = &dCellStates[4 * id];
+    switch (code) {
+    case kBedElevation: dBedElevations[id] = Util::round(v, rounding); st[0] = Util::round(v, rounding); break;
+    case kFreeSurfaceLevel: st[0] = Util::round(v, rounding); st[1] = Util::round(v, rounding); break;
+    case kDepth: st[0] = Util::round(dBedElevations[id] + v, rounding); st[1] = st[0]; break;
+    case kDisabledCells: if (v > 1.0 && v < 9999.0) st[1] = Util::round(-9999.0, rounding); break;
+    case kDischargeX: st[2] = Util::round(v, rounding); break;
+    case kDischargeY: st[3] = Util::round(v, rounding); break;
+    case kVelocityX: st[2] = Util::round(v * (st[0] - dBedElevations[id]), rounding); break;
+    case kVelocityY: st[3] = Util::round(v * (st[0] - dBedElevations[id]), rounding); break;
+    case kManningCoefficient: dManningValues[id] = Util::round(v, rounding); break;
+    default: break;
+    }
+}
+
+bool CDomainCartesian::loadInitialConditionSource(unsigned char code, const std::string& type, const std::string& source) {
+    if (type == "constant") {
+        if (!isValidFloat(source.c_str())) { model::doError("Invalid source constant given.", model::errorCodes::kLevelWarning); return false; }
+        const double v = atof(source.c_str());
+        for (unsigned long i = 0; i < getCellCount(); ++i) handleInputData(i, v, code, 4);
+        return true;
+    }
+    if (type == "raster") {
+        SRaster r;
+        if (!r.read(sSourceDir + source) || r.cols != ulCols || r.rows != ulRows) { model::doError("Raster source could not be read or does not match the domain.", model::errorCodes::kLevelWarning); return false; }
+        for (unsigned long i = 0; i < getCellCount(); ++i) handleInputData(i, r.values[i], code, 4);
+        return true;
+    }
+    model::doError("Unrecognised data source type.", model::errorCodes::kLevelWarning);
+    return false;
+}
+
+bool CDomainCartesian::configureDomain(const XMLElement* pXDomain, const std::string& sConfigDir) {
+    const XMLElement* pXData = pXDomain->FirstChildElement("data");
+    if (!pXData) { model::doError("The <domain> element has no <data> element.", model::errorCodes::kLevelModelStop); return false; }
+    auto dirOf = [&](const char* a) { std::string d = pXData->Attribute(a) ? pXData->Attribute(a) : ""; if (!d.empty() && d[0] != '/') d = sConfigDir + d; return d; };
+    sSourceDir = dirOf("sourceDir"); sTargetDir = dirOf("targetDir");
+    // 1. structure: the raster tagged "structure" fixes cols/rows/resolution (CDomainCartesian.cpp:69-160)
+    struct Src { std::string type, value, source; unsigned char code; };
+    std::vector<Src> others; Src dem{"", "", "", kUnknown}, depth{"", "", "", kUnknown};
+    for (const XMLElement* s = pXData->FirstChildElement("dataSource"); s; s = s->NextSiblingElement("dataSource")) {
+        Src src{Util::toLowercase(s->Attribute("type")), Util::toLowercase(s->Attribute("value")), s->Attribute("source") ? s->Attribute("source") : "", kUnknown};
+        src.code = getDataValueCode(src.value);
+        if (src.value.find("structure") != std::string::npos) {
+            SRaster r;
+            if (!r.read(sSourceDir + src.source)) { model::doError("Could not open the domain structure raster.", model::errorCodes::kLevelModelStop); return false; }
+            ulCols = r.cols; ulRows = r.rows; dCellResolution = r.cellsize; dRealOffsetX = r.xll; dRealOffsetY = r.yll;
+        }
+        if (src.code == kBedElevation) dem = src;
+        else if (src.code == kDepth || src.code == kFreeSurfaceLevel) depth = src;
+        else others.push_back(src);
+    }
+    if (!ulCols || !ulRows) { model::doError("No structure source defined for the domain.", model::errorCodes::kLevelModelStop); return false; }
+    dCellStates.assign(4 * getCellCount(), 0.0); dBedElevations.assign(getCellCount(), 0.0); dManningValues.assign(getCellCount(), 0.0);
+    if (dem.code == kUnknown || depth.code == kUnknown) model::doError("Missing DEM or depth data source.", model::errorCodes::kLevelWarning);
+    // 2. initial conditions in the order DEM, depth/FSL, everything else (CDomainCartesian.cpp:252-283)
+    if (dem.code != kUnknown && !loadInitialConditionSource(dem.code, dem.type, dem.source)) { model::doError("Could not load DEM data.", model::errorCodes::kLevelWarning); return false; }
+    if (depth.code != kUnknown && !loadInitialConditionSource(depth.code, depth.type, depth.source)) { model::doError("Could not load depth/FSL data.", model::errorCodes::kLevelWarning); return false; }
+    for (const auto& o : others) if (o.code != kUnknown && !loadInitialConditionSource(o.code, o.type, o.source)) { model::doError("Could not load initial conditions.", model::errorCodes::kLevelWarning); return false; }
+    // 3. outputs (CDomainCartesian.cpp:288-339)
+    for (const XMLElement* t = pXData->FirstChildElement("dataTarget"); t; t = t->NextSiblingElement("dataTarget"))
+        outputs.push_back({Util::toLowercase(t->Attribute("value")), t->Attribute("format") ? t->Attribute("format") : "", t->Attribute("target") ? t->Attribute("target") : ""});
+    // 4. boundaries (sourceDir is relative to the configuration file like the data dirs)
+    return boundaryMap.setupFromConfig(pXDomain->FirstChildElement("boundaryConditions"), sConfigDir);
+}
+
+double CDomainCartesian::getVolume() const {
+    double v = 0.0;
+    for (unsigned long i = 0; i < getCellCount(); ++i) {
+        if (dCellStates[4 * i + 1] <= -9999.0 || dBedElevations[i] <= -9999.0) continue;
+        v += std::max(0.0, dCellStates[4 * i] - dBedElevations[i]) * dCellResolution * dCellResolution;
+    }
+    return v;
+}
+
+// src/Datasets/CRasterDataset.cpp:185-267
+double CDomainCartesian::deriveOutput(unsigned char code, const double* st, double bed, double res, double nodata) {
+    const double depth = st[0] - bed;
+    switch (code) {
+    case kMaxFSL: return (st[1] < bed + 1E-8 || bed > 9999.0) ? nodata : st[1];
+    case kFreeSurfaceLevel: return (st[0] < bed + 1E-8 || bed > 9999.0) ? nodata : st[0];
+    case kMaxDepth: { const double d = std::max(0.0, st[1] - bed); return (d < 1E-8 || d <= -9990.0 || d >= 9999.0) ? nodata : d; }
+    case kDepth: { const double d = std::max(0.0, depth); return d < 1E-8 ? nodata : d; }
+    case kDischargeX: return st[2] * res;
+    case kDischargeY: return st[3] * res;
+    case kVelocityX: return depth > 1E-8 ? st[2] / depth : nodata;
+    case kVelocityY: return depth > 1E-8 ? st[3] / depth : nodata;
+    case kFroudeNumber: { const double u = st[2] / depth, v = st[3] / depth; return depth > 1E-8 ? std::sqrt(u * u + v * v) / std::sqrt(9.81 * depth) : nodata; }
+    default: return nodata;
+    }
+}
+
+bool CDomainCartesian::writeOutputs(double dTime) {
+    bool ok = true;
+    for (const auto& o : outputs) {
+        const unsigned char code = getDataValueCode(o.sValue);
+        SRaster r; r.cols = ulCols; r.rows = ulRows; r.cellsize = dCellResolution; r.xll = dRealOffsetX; r.yll = dRealOffsetY; r.nodata = -9999.0;
+        r.values.resize(getCellCount());
+        for (unsigned long i = 0; i < getCellCount(); ++i) r.values[i] = deriveOutput(code, &dCellStates[4 * i], dBedElevations[i], dCellResolution, -9999.0);
+        std::string file = o.sTarget; const size_t pos = file.find("%t");
+        char tbuf[64]; snprintf(tbuf, sizeof(tbuf), "%g", std::floor(dTime * 100.0) / 100.0);   // "%t" -> floor(t*100)/100
+        if (pos != std::string::npos) file.replace(pos, 2, tbuf);
+        const size_t dot = file.find_last_of('.');
+        if (o.sFormat != "AAIGrid") file = (dot == std::string::npos ? file : file.substr(0, dot)) + ".asc";   // GDAL drivers are not available
+        ok = r.write(sTargetDir + file) && ok;
+    }
+    return ok;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Schemes
+// ---------------------------------------------------------------------------------------------
+CScheme* CScheme::createFromConfig(const XMLElement* pXScheme) {       // src/Schemes/CScheme.cpp:141-175
+    const std::string name = Util::toLowercase(pXScheme ? pXScheme->Attribute("name") : nullptr);
+    CScheme* s = nullptr;
+    if (name == "godunov") s = new CSchemeGodunov();
+    else if (name == "muscl-hancock") s = new CSchemeMUSCLHancock();
+    else if (name == "inertial") s = new CSchemeInertial();
+    else { model::doError("Unsupported scheme specified for the domain.", model::errorCodes::kLevelWarning); return nullptr; }
+    s->setupFromConfig(pXScheme);
+    return s;
+}
+CScheme::~CScheme() { cleanupSimulation(); }
+
+void CScheme::setupFromConfig(const XMLElement* pXScheme) {            // CScheme.cpp:79-109, CSchemeGodunov.cpp:128-334
+    for (const XMLElement* p = pXScheme->FirstChildElement("parameter"); p; p = p->NextSiblingElement("parameter")) {
+        const std::string key = Util::toLowercase(p->Attribute("name")), val = Util::toLowercase(p->Attribute("value"));
+        if (key == "courantnumber") { if (isValidFloat(val.c_str())) setCourantNumber(atof(val.c_str())); else model::doError("Invalid Courant number given.", model::errorCodes::kLevelWarning); }
+        else if (key == "drythreshold") { if (isValidFloat(val.c_str())) setDryThreshold(atof(val.c_str())); else model::doError("Invalid dry threshold depth given.", model::errorCodes::kLevelWarning); }
+        else if (key == "timestepmode") {
+            if (val == "auto" || val == "cfl") setTimestepMode(true); else if (val == "fixed") setTimestepMode(false);
+            else model::doError("Invalid timestep mode given.", model::errorCodes::kLevelWarning);
+        }
+        else if (key == "timestepinitial" || key == "timestepfixed") { if (isValidFloat(val.c_str())) setTimestep(atof(val.c_str())); else model::doError("Invalid initial/fixed timestep given.", model::errorCodes::kLevelWarning); }
+        else if (key == "frictioneffects") { if (val == "yes") setFrictionStatus(true); else if (val == "no") setFrictionStatus(false); else model::doError("Invalid friction state given.", model::errorCodes::kLevelWarning); }
+        else if (key == "queuesize" || key == "queueinitialsize" || key == "queuefixedsize") { if (atoi(val.c_str()) > 0) setQueueSize(atoi(val.c_str())); }
+        else if (key == "riemannsolver") { if (val != "hllc") model::doError("Invalid Riemann solver given.", model::errorCodes::kLevelWarning); }
+        else if (key == "groupsize" || key == "cachedgroupsize" || key == "noncachedgroupsize" || key == "localcachelevel" || key == "localcacheconstraints" ||
+                 key == "queuemode" || key == "timestepreductiondivisions" || key == "contiguousextrapolationdata") { /* launch geometry and cache strategy are the executor's business */ }
+        else model::doError("Unrecognised parameter: " + key, model::errorCodes::kLevelWarning);
+    }
+}
+
+bool CScheme::prepareAll(CExecutorControlCUDA* pExec, CDomainCartesian* pDom, unsigned char ucPrecision, double dSimulationLength) {
+    pExecutor = pExec; pDomain = pDom; ucFloatPrecision = ucPrecision;
+    hp_scheme_config c{};
+    c.struct_size = sizeof(c); c.scheme = ucSchemeType; c.real_bytes = ucPrecision == model::floatPrecision::kSingle ? 4 : 8;
+    c.quirks = uiQuirks; c.options = uiOptions; c.dynamic_timestep = bDynamicTimestep ? 1 : 0; c.friction = bFrictionEffects ? 1 : 0;
+    c.cols = pDom->getCols(); c.rows = pDom->getRows(); c.global_rows = pDom->getRows();
+    c.delta = pDom->getCellResolution(); c.courant = dCourantNumber; c.dry_threshold = dThresholdVerySmall; c.end_time = dSimulationLength;
+    c.fixed_timestep = dTimestep; c.initial_timestep = dTimestep;
+    if (hp_scheme_create(pExec->getDevice(), &c, &pScheme) < 0) { model::doError(std::string("Could not prepare the scheme: ") + hp_last_error(), model::errorCodes::kLevelModelStop); pScheme = nullptr; return false; }
+    pDom->getBoundaries()->prepareBoundaries(pScheme, pDom, dSimulationLength);
+    dCurrentTimestep = dTimestep;
+    return true;
+}
+
+void CScheme::prepareSimulation() {        // CSchemeGodunov.cpp:1053-1071
+    if (!pScheme) return;
+    const unsigned long n = pDomain->getCellCount();
+    if (ucFloatPrecision == model::floatPrecision::kSingle) {
+        std::vector<float> st(pDomain->dCellStates.begin(), pDomain->dCellStates.end()), bed(pDomain->dBedElevations.begin(), pDomain->dBedElevations.end()),
+            man(pDomain->dManningValues.begin(), pDomain->dManningValues.end());
+        HP_CHECK(hp_scheme_upload_cells(pScheme, st.data(), bed.data(), man.data()), "upload");
+        HP_CHECK(hp_scheme_sync(pScheme), "upload");
+    } else {
+        HP_CHECK(hp_scheme_upload_cells(pScheme, pDomain->dCellStates.data(), pDomain->dBedElevations.data(), pDomain->dManningValues.data()), "upload");
+        HP_CHECK(hp_scheme_sync(pScheme), "upload");
+    }
+    (void)n;
+    HP_CHECK(hp_scheme_set_clock(pScheme, 0.0, dTimestep, 0.0), "clock");
+    ulCurrentCellsCalculated = 0;
+}
+
+void CScheme::runSimulation(double dTarget, double) {      // CSchemeGodunov.cpp:1374-1453 + one Threaded_runBatch pass
+    if (!pScheme) return;
+    if (dTarget != dTargetTime) {
+        dTargetTime = dTarget;
+        HP_CHECK(hp_scheme_set_target_time(pScheme, dTarget), "target time");
+        if (dCurrentTimestep <= 0.0) HP_CHECK(hp_scheme_update_timestep(pScheme), "timestep update");   // forecast sync, :1191-1196
+    }
+    HP_CHECK(hp_scheme_iterate(pScheme, uiQueueAdditionSize), "iterate");
+    ulCurrentCellsCalculated += static_cast<unsigned long long>(uiQueueAdditionSize) * pDomain->getCellCount();
+    HP_CHECK(hp_scheme_sync(pScheme), "sync");
+    readKeyStatistics();
+}
+
+void CScheme::readKeyStatistics() {
+    hp_scheme_stats st{};
+    if (hp_scheme_read_stats(pScheme, &st) < 0) { model::doError(hp_last_error(), model::errorCodes::kLevelModelStop); return; }
+    dCurrentTime = st.time; dCurrentTimestep = st.timestep; dBatchTimesteps = st.batch_timesteps;
+    uiBatchSuccessful = st.batch_successful; uiBatchSkipped = st.batch_skipped;
+}
+
+void CScheme::readDomainAll() {
+    if (!pScheme) return;
+    if (ucFloatPrecision == model::floatPrecision::kSingle) {
+        std::vector<float> st(pDomain->dCellStates.size());
+        HP_CHECK(hp_scheme_download_cells(pScheme, st.data()), "download");
+        std::copy(st.begin(), st.end(), pDomain->dCellStates.begin());
+    } else {
+        HP_CHECK(hp_scheme_download_cells(pScheme, pDomain->dCellStates.data()), "download");
+    }
+}
+void CScheme::forceTimestep(double dt) { if (pScheme) HP_CHECK(hp_scheme_force_timestep(pScheme, dt), "force timestep"); }
+void CScheme::cleanupSimulation() { if (pScheme) { hp_scheme_destroy(pScheme); pScheme = nullptr; } }
+
+// ---------------------------------------------------------------------------------------------
+// Model
+// ---------------------------------------------------------------------------------------------
+CModel::~CModel() { pScheme.reset(); pExecutor.reset(); }
+
+bool CModel::loadConfiguration(const std::string& sPath, bool bDeviceless) {
+    XMLDocument doc;
+    if (!doc.LoadFile(sPath)) { model::doError("Cannot load configuration: " + doc.error, model::errorCodes::kLevelModelStop); return false; }
+    const XMLElement* root = doc.RootElement();
+    if (!root || std::string(root->Name()) != "configuration") { model::doError("Configuration file has no <configuration> root.", model::errorCodes::kLevelModelStop); return false; }
+    const size_t slash = sPath.find_last_of('/');
+    const std::string dir = slash == std::string::npos ? "" : sPath.substr(0, slash + 1);
+    if (const XMLElement* m = root->FirstChildElement("metadata")) {
+        if (m->FirstChildElement("name")) sName = m->FirstChildElement("name")->text;
+        if (m->FirstChildElement("description")) sDescription = m->FirstChildElement("description")->text;
+    }
+    if (!bDeviceless) {
+        pExecutor.reset(CExecutorControlCUDA::createFromConfig(root->FirstChildElement("execution")));
+        if (!pExecutor) return false;
+    }
+    const XMLElement* sim = root->FirstChildElement("simulation");
+    if (!sim) { model::doError("No <simulation> element.", model::errorCodes::kLevelModelStop); return false; }
+    for (const XMLElement* p = sim->FirstChildElement("parameter"); p; p = p->NextSiblingElement("parameter")) {   // CModel.cpp:65-135
+        const std::string key = Util::toLowercase(p->Attribute("name")), val = Util::toLowercase(p->Attribute("value"));
+        if (key == "duration") { if (isValidFloat(val.c_str())) dSimulationTime = atof(val.c_str()); else model::doError("Invalid simulation length given.", model::errorCodes::kLevelWarning); }
+        else if (key == "outputfrequency") { if (isValidFloat(val.c_str())) dOutputFrequency = atof(val.c_str()); else model::doError("Invalid output frequency given.", model::errorCodes::kLevelWarning); }
+        else if (key == "floatingpointprecision") {
+            if (val == "single") ucFloatPrecision = model::floatPrecision::kSingle; else if (val == "double") ucFloatPrecision = model::floatPrecision::kDouble;
+            else model::doError("Invalid float precision given.", model::errorCodes::kLevelWarning);
+        }
+        else if (key == "realstart") { /* wall-clock labelling only */ }
+        else model::doError("Unrecognised parameter: " + key, model::errorCodes::kLevelWarning);
+    }
+    const XMLElement* set = sim->FirstChildElement("domainSet");
+    const XMLElement* dom = set ? set->FirstChildElement("domain") : nullptr;
+    if (!dom) { model::doError("No <domain> defined.", model::errorCodes::kLevelModelStop); return false; }
+    if (dom->NextSiblingElement("domain")) model::doError("Only the first <domain> is used; multi-domain sets map onto row strips (see DESIGN.md).", model::errorCodes::kLevelWarning);
+    if (Util::toLowercase(dom->Attribute("type")) != "cartesian") { model::doError("Unsupported domain type.", model::errorCodes::kLevelModelStop); return false; }
+    pDomain.reset(new CDomainCartesian());
+    // boundary files are relative to the configuration file
+    if (!pDomain->configureDomain(dom, dir)) return false;
+    pScheme.reset(CScheme::createFromConfig(dom->FirstChildElement("scheme")));
+    if (!pScheme) return false;
+    if (bDeviceless) return true;      // host-side parsing only (CPU tests)
+    return pScheme->prepareAll(pExecutor.get(), pDomain.get(), ucFloatPrecision, dSimulationTime);
+}
+
+bool CModel::runModel() {
+    if (!pScheme || !pScheme->isReady()) return false;
+    pScheme->prepareSimulation();
+    double nextOutput = dOutputFrequency > 0.0 ? dOutputFrequency : dSimulationTime;
+    while (!model::forceAbort && pScheme->getCurrentTime() < dSimulationTime - 1E-5) {
+        const double target = std::min(nextOutput, dSimulationTime);
+        while (!model::forceAbort && pScheme->getCurrentTime() < target - 1E-5) pScheme->runSimulation(target, 0.0);
+        pScheme->readDomainAll();
+        pDomain->writeOutputs(pScheme->getCurrentTime());
+        nextOutput += dOutputFrequency > 0.0 ? dOutputFrequency : dSimulationTime;
+    }
+    return !model::forceAbort;
+}
+
+// ---------------------------------------------------------------------------------------------
+// C facade for the tests (ctypes)
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+void* hph_model_load(const char* path, int deviceless) {
+    model::forceAbort = false; model::errorLog.clear();
+    CModel* m = new CModel();
+    if (!m->loadConfiguration(path, deviceless != 0)) { delete m; return nullptr; }
+    return m;
+}
+int hph_model_run(void* h) { return static_cast<CModel*>(h)->runModel() ? 0 : -1; }
+void hph_model_destroy(void* h) { delete static_cast<CModel*>(h); }
+void hph_model_info(void* h, unsigned long* cols, unsigned long* rows, double* resolution, double* duration, double* output_frequency,
+                    int* precision, int* scheme, unsigned int* boundaries) {
+    CModel* m = static_cast<CModel*>(h);
+    *cols = m->getDomain()->getCols(); *rows = m->getDomain()->getRows(); *resolution = m->getDomain()->getCellResolution();
+    *duration = m->getSimulationLength(); *output_frequency = m->getOutputFrequency(); *precision = m->getFloatPrecision();
+    *scheme = m->getScheme()->getSchemeType(); *boundaries = m->getDomain()->getBoundaries()->getBoundaryCount();
+}
+void hph_model_scheme_params(void* h, double* courant, double* dry, double* timestep, int* dynamic, int* friction, unsigned int* queue) {
+    CScheme* s = static_cast<CModel*>(h)->getScheme();
+    *courant = s->dCourantNumber; *dry = s->dThresholdVerySmall; *timestep = s->dTimestep; *dynamic = s->bDynamicTimestep; *friction = s->bFrictionEffects;
+    *queue = s->getBatchSize();
+}
+const double* hph_model_states(void* h) { return static_cast<CModel*>(h)->getDomain()->dCellStates.data(); }
+const double* hph_model_bed(void* h) { return static_cast<CModel*>(h)->getDomain()->dBedElevations.data(); }
+const double* hph_model_manning(void* h) { return static_cast<CModel*>(h)->getDomain()->dManningValues.data(); }
+void hph_model_clock(void* h, double* time, double* timestep, unsigned int* ok, unsigned int* skipped) {
+    CScheme* s = static_cast<CModel*>(h)->getScheme();
+    *time = s->getCurrentTime(); *timestep = s->getCurrentTimestep(); *ok = s->getIterationsSuccessful(); *skipped = s->getIterationsSkipped();
+}
+// boundary i: kind 0 uniform / 1 gridded / 2 cell; returns the series length in doubles
+int hph_model_boundary(void* h, unsigned int i, int* kind, int* def_a, int* def_b, double* interval, double* length, const double** series,
+                       unsigned int* relations) {
+    CBoundaryMap* map = static_cast<CModel*>(h)->getDomain()->getBoundaries();
+    if (i >= map->boundaries.size()) return -1;
+    CBoundary* b = map->boundaries[i].get();
+    *relations = 0; *series = nullptr; *def_b = 0;
+    if (auto* u = dynamic_cast<CBoundaryUniform*>(b)) { *kind = 0; *def_a = u->ucValue; *interval = u->dTimeseriesInterval; *length = u->dTimeseriesLength; *series = u->series.data(); return static_cast<int>(u->series.size()); }
+    if (auto* c = dynamic_cast<CBoundaryCell*>(b)) { *kind = 2; *def_a = c->ucDepthValue; *def_b = c->ucDischargeValue; *interval = c->dTimeseriesInterval; *length = c->dTimeseriesLength; *series = c->series.data(); *relations = static_cast<unsigned int>(c->relations.size()); return static_cast<int>(c->series.size()); }
+    if (auto* g = dynamic_cast<CBoundaryGridded*>(b)) { *kind = 1; *def_a = g->ucValue; *interval = g->dInterval; *length = 0; return 0; }
+    return -1;
+}
+int hph_error_count(void) { return static_cast<int>(model::errorLog.size()); }
+const char* hph_error(int i) { return (i >= 0 && i < static_cast<int>(model::errorLog.size())) ? model::errorLog[i].c_str() : ""; }
+double hph_round(double v, int places) { return Util::round(v, static_cast<unsigned char>(places)); }
+double hph_derive_output(const char* value, const double* state4, double bed, double resolution) {
+    return CDomainCartesian::deriveOutput(CDomainCartesian::getDataValueCode(value), state4, bed, resolution, -9999.0);
+}
+}

@@ -1,0 +1,270 @@
+// hipims_host.h -- C++ host side above the C ABI (include/hipims_cuda.h), mirroring the
+// reference's executor / scheme / domain / boundary surface for the hot path.
+//
+// Class and method names, XML attributes and error behaviour follow the reference so that the
+// parity tests read like its own code would:
+//   model::doError                    src/main.cpp:631-652        (levels; ModelStop sets forceAbort)
+//   CExecutorControl::createFromConfig src/Base/CExecutorControl.cpp:66-98 (executor name "CUDA")
+//   CScheme (abstract)                src/Schemes/CScheme.h:73-162
+//   CSchemeGodunov / MUSCLHancock / Inertial   src/Schemes/CScheme*.cpp
+//   CDomainCartesian                  src/Domain/Cartesian/CDomainCartesian.cpp, src/Domain/CDomain.cpp
+//   CBoundary / CBoundaryCell / Uniform / Gridded / CBoundaryMap   src/Boundaries/*.cpp
+//   CModel (minimal driver)           src/CModel.cpp:217, 1041-1139
+// The classes talk to the device ONLY through the C ABI.  They do not implement the reference's
+// control plane (polling UI, MPI, GDAL); rasters are ESRI ASCII grids.
+#pragma once
+
+#include <cstdint>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/hipims_cuda.h"
+
+namespace model {
+namespace errorCodes { enum errorCodes { kLevelFatal = 1, kLevelModelStop = 2, kLevelModelContinue = 4, kLevelWarning = 8, kLevelInformation = 16 }; }
+namespace floatPrecision { enum floatPrecision { kSingle = 0, kDouble = 1 }; }
+namespace schemeTypes { enum schemeTypes { kGodunov = 0, kMUSCLHancock = 1, kInertialSimplification = 2 }; }
+extern bool forceAbort;
+extern std::vector<std::string> errorLog;       // every doError message, newest last
+void doError(const std::string& message, unsigned char level);
+}  // namespace model
+
+// ---------------------------------------------------------------------------------------------
+// Minimal XML DOM with the tinyxml2 calls the reference's config code uses.
+// ---------------------------------------------------------------------------------------------
+class XMLElement {
+  public:
+    const char* Name() const { return name.c_str(); }
+    const char* Attribute(const char* key) const;                 // NULL when absent
+    const XMLElement* FirstChildElement(const char* tag = nullptr) const;
+    const XMLElement* NextSiblingElement(const char* tag = nullptr) const;
+    std::string name, text;
+    std::vector<std::pair<std::string, std::string>> attributes;
+    std::vector<std::unique_ptr<XMLElement>> children;
+    const XMLElement* parent = nullptr;
+};
+class XMLDocument {
+  public:
+    bool Parse(const std::string& xml);
+    bool LoadFile(const std::string& path);
+    const XMLElement* RootElement() const { return root.get(); }
+    std::string error;
+  private:
+    std::unique_ptr<XMLElement> root;
+};
+
+// src/Datasets/CCSVDataset.*: rows of comma separated cells, first row is a header
+class CCSVDataset {
+  public:
+    explicit CCSVDataset(const std::string& path) : sFilename(path) {}
+    bool readFile();
+    bool isReady() const { return bReady; }
+    std::vector<std::vector<std::string>> rows;
+  private:
+    std::string sFilename;
+    bool bReady = false;
+};
+
+// ESRI ASCII grid (GDAL-free stand-in for CRasterDataset); rows are stored south-first like the
+// reference's cell arrays (src/Datasets/CRasterDataset.cpp:411 flips on load).
+struct SRaster {
+    unsigned long cols = 0, rows = 0;
+    double xll = 0, yll = 0, cellsize = 1, nodata = -9999;
+    std::vector<double> values;
+    bool read(const std::string& path);
+    bool write(const std::string& path) const;
+};
+
+namespace Util {
+double round(double value, unsigned char places);   // src/util.cpp:79-93 (negatives go towards -inf)
+std::string toLowercase(const char* s);
+}
+
+class CDomainCartesian;
+class CScheme;
+
+// ---------------------------------------------------------------------------------------------
+// Executor: replaces CExecutorControlOpenCL + COCLDevice.
+// ---------------------------------------------------------------------------------------------
+class CExecutorControlCUDA {
+  public:
+    static CExecutorControlCUDA* createFromConfig(const XMLElement* pXExecution);   // <executor name="CUDA"|"OpenCL">
+    ~CExecutorControlCUDA();
+    bool setupFromConfig(const XMLElement* pXExecutor);      // parameter deviceNumber (1-based like getDevice(n))
+    bool isReady() const { return pExecutor != nullptr; }
+    unsigned int getDeviceCount() const { return uiDeviceCount; }
+    hp_executor* getDevice() const { return pExecutor; }
+    std::string getDeviceShortName() const { return sDeviceName; }
+    void blockUntilFinished();
+  private:
+    hp_executor* pExecutor = nullptr;
+    unsigned int uiDeviceCount = 0;
+    std::string sDeviceName;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Boundaries
+// ---------------------------------------------------------------------------------------------
+class CBoundary {
+  public:
+    virtual ~CBoundary() {}
+    virtual bool setupFromConfig(const XMLElement* pElement, const std::string& sBoundarySourceDir) = 0;
+    virtual void prepareBoundary(hp_scheme* pScheme, CDomainCartesian* pDomain, double dSimulationLength) = 0;   // uploads conf + series
+    virtual void importMap(CCSVDataset*) {}
+    std::string getName() const { return sName; }
+  protected:
+    std::string sName;
+};
+
+class CBoundaryUniform : public CBoundary {
+  public:
+    bool setupFromConfig(const XMLElement*, const std::string&) override;
+    void prepareBoundary(hp_scheme*, CDomainCartesian*, double) override;
+    void importTimeseries(CCSVDataset*);
+    std::vector<double> series;            // {t, value} pairs
+    unsigned int ucValue = 0;              // 0 rain-intensity, 1 loss-rate
+    double dTimeseriesInterval = 0, dTimeseriesLength = 0;
+};
+
+class CBoundaryCell : public CBoundary {
+  public:
+    bool setupFromConfig(const XMLElement*, const std::string&) override;
+    void prepareBoundary(hp_scheme*, CDomainCartesian*, double) override;
+    void importTimeseries(CCSVDataset*);
+    void importMap(CCSVDataset*) override;
+    std::vector<double> series;            // {t, depth|fsl, Qx, Qy}
+    std::vector<std::pair<unsigned int, unsigned int>> relations;   // cell x, y
+    unsigned int ucDepthValue = 1, ucDischargeValue = 1;
+    bool bDischargeIsTotal = true;         // kValueTotal == kValuePerCell in the reference (CBoundary.h:54-57)
+    double dTimeseriesInterval = 0, dTimeseriesLength = 0;
+};
+
+class CBoundaryGridded : public CBoundary {
+  public:
+    bool setupFromConfig(const XMLElement*, const std::string&) override;
+    void prepareBoundary(hp_scheme*, CDomainCartesian*, double) override;
+    std::string sMask, sSourceDir;
+    double dInterval = 0;
+    unsigned int ucValue = 0;              // 0 rain-intensity, 2 mass-flux
+};
+
+class CBoundaryMap {
+  public:
+    bool setupFromConfig(const XMLElement* pXBoundaries, const std::string& sConfigDir);
+    void prepareBoundaries(hp_scheme* pScheme, CDomainCartesian* pDomain, double dSimulationLength);
+    unsigned int getBoundaryCount() const { return static_cast<unsigned int>(boundaries.size()); }
+    CBoundary* getBoundaryByName(const std::string& name);
+    std::vector<std::unique_ptr<CBoundary>> boundaries;   // XML order
+};
+
+// ---------------------------------------------------------------------------------------------
+// Domain
+// ---------------------------------------------------------------------------------------------
+struct sDataTargetInfo { std::string sValue, sFormat, sTarget; };
+
+class CDomainCartesian {
+  public:
+    bool configureDomain(const XMLElement* pXDomain, const std::string& sConfigDir);   // structure -> ICs (DEM, depth, others)
+    unsigned long getCols() const { return ulCols; }
+    unsigned long getRows() const { return ulRows; }
+    unsigned long getCellCount() const { return ulCols * ulRows; }
+    unsigned long getCellID(unsigned long x, unsigned long y) const { return y * ulCols + x; }
+    double getCellResolution() const { return dCellResolution; }
+    void handleInputData(unsigned long ulCellID, double dValue, unsigned char ucValue, unsigned char ucRounding);
+    static unsigned char getDataValueCode(const std::string& sLower);
+    double getVolume() const;
+    bool writeOutputs(double dTime);                       // derives depth / velocity / fsl / maxdepth / ... rasters
+    static double deriveOutput(unsigned char ucValue, const double* state, double bed, double resolution, double nodata);
+    CBoundaryMap* getBoundaries() { return &boundaryMap; }
+    // host cell arrays, reference layout (src/Domain/CDomain.h:28-33); always double on the host side
+    std::vector<double> dCellStates;      // cells x {eta, eta_max, qx, qy}
+    std::vector<double> dBedElevations, dManningValues;
+    std::vector<sDataTargetInfo> outputs;
+    std::string sSourceDir, sTargetDir;
+    double dRealOffsetX = 0, dRealOffsetY = 0;
+  private:
+    bool loadInitialConditionSource(unsigned char ucValue, const std::string& type, const std::string& source);
+    unsigned long ulCols = 0, ulRows = 0;
+    double dCellResolution = 1.0;
+    CBoundaryMap boundaryMap;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Schemes
+// ---------------------------------------------------------------------------------------------
+class CScheme {
+  public:
+    static CScheme* createFromConfig(const XMLElement* pXScheme);    // <scheme name="godunov|muscl-hancock|inertial">
+    virtual ~CScheme();
+    virtual void setupFromConfig(const XMLElement* pXScheme);
+    bool prepareAll(CExecutorControlCUDA* pExec, CDomainCartesian* pDomain, unsigned char ucFloatPrecision, double dSimulationLength);
+    void prepareSimulation();                          // uploads cells and clock
+    void runSimulation(double dTargetTime, double dRealTime);   // sets the target and schedules a batch
+    void readKeyStatistics();
+    void readDomainAll();                              // device -> CDomain host arrays
+    void saveCurrentState() { readDomainAll(); }
+    void forceTimestep(double dTimestep);
+    void cleanupSimulation();
+    bool isReady() const { return pScheme != nullptr; }
+    double getCurrentTime() const { return dCurrentTime; }
+    double getCurrentTimestep() const { return dCurrentTimestep; }
+    unsigned int getIterationsSuccessful() const { return uiBatchSuccessful; }
+    unsigned int getIterationsSkipped() const { return uiBatchSkipped; }
+    unsigned long long getCellsCalculated() const { return ulCurrentCellsCalculated; }
+    unsigned int getBatchSize() const { return uiQueueAdditionSize; }
+    double getAverageTimestep() const { return uiBatchSuccessful ? dBatchTimesteps / uiBatchSuccessful : 0.0; }
+    // parameters (setters named as in src/Schemes/CScheme.cpp / CSchemeGodunov.cpp)
+    void setCourantNumber(double v) { dCourantNumber = v; }
+    void setDryThreshold(double v) { dThresholdVerySmall = v; }
+    void setTimestepMode(bool dynamic) { bDynamicTimestep = dynamic; }
+    void setTimestep(double v) { dTimestep = v; }
+    void setFrictionStatus(bool v) { bFrictionEffects = v; }
+    void setQueueSize(unsigned int v) { uiQueueAdditionSize = v; }
+    void setQuirks(uint32_t q) { uiQuirks = q; }
+    void setOptions(uint32_t o) { uiOptions = o; }
+    unsigned char getSchemeType() const { return ucSchemeType; }
+    hp_scheme* getHandle() const { return pScheme; }
+    double dCourantNumber = 0.5, dThresholdVerySmall = 1e-10, dTimestep = 0.001;
+    bool bDynamicTimestep = true, bFrictionEffects = true;
+  protected:
+    explicit CScheme(unsigned char type) : ucSchemeType(type) {}
+    unsigned char ucSchemeType;
+    unsigned char ucFloatPrecision = model::floatPrecision::kDouble;
+    hp_scheme* pScheme = nullptr;
+    CDomainCartesian* pDomain = nullptr;
+    CExecutorControlCUDA* pExecutor = nullptr;
+    unsigned int uiQueueAdditionSize = 256;
+    uint32_t uiQuirks = HP_QUIRK_REDUCE_BUFFER_A | HP_QUIRK_BDY_COVERAGE, uiOptions = 0;
+    double dCurrentTime = 0, dCurrentTimestep = 0, dBatchTimesteps = 0, dTargetTime = 0;
+    unsigned int uiBatchSuccessful = 0, uiBatchSkipped = 0;
+    unsigned long long ulCurrentCellsCalculated = 0;
+};
+class CSchemeGodunov : public CScheme { public: CSchemeGodunov() : CScheme(model::schemeTypes::kGodunov) {} };
+class CSchemeMUSCLHancock : public CScheme { public: CSchemeMUSCLHancock() : CScheme(model::schemeTypes::kMUSCLHancock) {} };
+class CSchemeInertial : public CScheme { public: CSchemeInertial() : CScheme(model::schemeTypes::kInertialSimplification) {} };
+
+// ---------------------------------------------------------------------------------------------
+// Minimal model driver: configuration file -> run to `duration`, writing outputs every
+// `outputFrequency` seconds (src/CModel.cpp:217, 1041-1139 without the polling UI).
+// ---------------------------------------------------------------------------------------------
+class CModel {
+  public:
+    ~CModel();
+    // src/main.cpp:376 + src/Datasets/CXMLDataset.cpp:115-260; bDeviceless parses only (no executor, CPU tests)
+    bool loadConfiguration(const std::string& sPath, bool bDeviceless = false);
+    bool runModel();
+    double getSimulationLength() const { return dSimulationTime; }
+    double getOutputFrequency() const { return dOutputFrequency; }
+    unsigned char getFloatPrecision() const { return ucFloatPrecision; }
+    CDomainCartesian* getDomain() { return pDomain.get(); }
+    CScheme* getScheme() { return pScheme.get(); }
+    std::string sName, sDescription;
+  private:
+    double dSimulationTime = 0, dOutputFrequency = 0;
+    unsigned char ucFloatPrecision = model::floatPrecision::kDouble;
+    std::unique_ptr<CExecutorControlCUDA> pExecutor;
+    std::unique_ptr<CDomainCartesian> pDomain;
+    std::unique_ptr<CScheme> pScheme;
+};

@@ -10,8 +10,9 @@ import numpy as np
 
 def round4(a):
     """Util::round(value, 4) of the reference (src/util.cpp:79-93)."""
-    a = np.asarray(a, dtype=np.float64)
-    return np.where(a < 0.0, np.ceil(a * 1e4 - 0.5), np.floor(a * 1e4 + 0.5)) / 1e4
+    m = np.asarray(a, dtype=np.float64) * 10000
+    rem = np.fmod(m, 1)                       # negative for negative values, so they always floor
+    return np.where(rem >= 0.5, np.ceil(m), np.floor(m)) / 10000
 
 
 def make_states(bed, depth, qx=None, qy=None, dtype=np.float64):

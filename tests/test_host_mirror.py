@@ -1,0 +1,250 @@
+"""The C++ host mirror (hipims_ocl_b200/host): same XML schema, class surface and semantics as the
+reference's CModel / CDomainCartesian / CScheme* / CBoundary* for the hot path, above the C ABI."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from hipims_ocl_b200 import build as hpbuild
+from hipims_ocl_b200 import config as hc
+from hipims_ocl_b200 import scenarios as sc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+XML = """<?xml version="1.0"?>
+<!DOCTYPE configuration PUBLIC "HiPIMS Configuration Schema 1.1" "http://www.lukesmith.org.uk/research/namespace/hipims/1.1/"[]>
+<configuration>
+	<metadata>
+		<name>Synthetic pluvial test</name>
+		<description>Same schema as test/newcastle-centre.xml of the reference</description>
+	</metadata>
+	<execution>
+		<executor name="OpenCL">
+			<parameter name="deviceFilter" value="GPU" />
+		</executor>
+	</execution>
+	<simulation>
+		<parameter name="duration" value="{duration}" />
+		<parameter name="outputFrequency" value="{outfreq}" />
+		<parameter name="floatingPointPrecision" value="{precision}" />
+		<domainSet>
+			<domain type="cartesian" deviceNumber="1">
+				<data sourceDir="topography/" targetDir="output/">
+					<dataSource type="constant" value="velocityX" source="0.0" />
+					<dataSource type="constant" value="velocityY" source="0.0" />
+					<dataSource type="constant" value="depth" source="0.0" />
+					<dataSource type="constant" value="manningCoefficient" source="0.030" />
+					<dataSource type="raster" value="structure,dem" source="dem.asc" />
+					<dataTarget type="raster" value="depth" format="HFA" target="depth_%t.img" />
+					<dataTarget type="raster" value="velocityX" format="HFA" target="velX_%t.img" />
+					<dataTarget type="raster" value="fsl" format="AAIGrid" target="fsl_%t.asc" />
+					<dataTarget type="raster" value="maxdepth" format="HFA" target="maxdepth_%t.img" />
+				</data>
+				<scheme name="{scheme}">
+					<parameter name="courantNumber" value="0.50" />
+					<parameter name="frictionEffects" value="yes" />
+					<parameter name="groupSize" value="32x8" />
+					<parameter name="queueSize" value="16" />
+				</scheme>
+				<boundaryConditions sourceDir="boundaries/">
+					<domainEdge edge="north" treatment="closed" />
+					<!-- rain and losses, like the reference's test -->
+					<timeseries type="atmospheric" name="Drainage" value="loss-rate" source="drainage.csv" />
+					<timeseries type="atmospheric" name="Rainfall" value="rain-intensity" source="rainfall.csv" />
+					<timeseries type="cell" name="Inflow" depthValue="ignore" dischargeValue="total" source="inflow.csv" mapFile="inflow_map.csv" />
+				</boundaryConditions>
+			</domain>
+		</domainSet>
+	</simulation>
+</configuration>
+"""
+
+
+def write_asc(path, a, cellsize, xll=424520.0, yll=565146.0):
+    rows, cols = a.shape
+    with open(path, "w") as f:
+        f.write("ncols %d\nnrows %d\nxllcorner %r\nyllcorner %r\ncellsize %r\nNODATA_value -9999\n" % (cols, rows, xll, yll, cellsize))
+        for r in range(rows - 1, -1, -1):           # north first in the file
+            f.write(" ".join(repr(float(v)) for v in a[r]) + "\n")
+
+
+def read_asc(path):
+    with open(path) as f:
+        hdr = {}
+        for _ in range(6):
+            k, v = f.readline().split()
+            hdr[k.lower()] = float(v)
+        data = np.loadtxt(f)
+    return data[::-1], hdr
+
+
+@pytest.fixture()
+def model_dir(tmp_path):
+    def make(scheme="Godunov", precision="double", duration=30, outfreq=10, rows=30, cols=40):
+        for d in ("topography", "output", "boundaries"):
+            os.makedirs(tmp_path / d, exist_ok=True)
+        bed = sc.fractal_dem(rows, cols, 5, amplitude=3.0) + 0.00004   # not on the 4-decimal grid: ingestion must round
+        write_asc(tmp_path / "topography" / "dem.asc", bed, 2.0)
+        (tmp_path / "boundaries" / "rainfall.csv").write_text("Time (s),Rainfall intensity (mm/hr)\n0,70\n3600,70\n7200,0\n10800,0\n\n\n")
+        (tmp_path / "boundaries" / "drainage.csv").write_text("Time (s),Drainage losses (mm/hr)\n0,12\n100000000,12\n\n")
+        (tmp_path / "boundaries" / "inflow.csv").write_text("t,depth,qx,qy\n0,0,0,0\n10,0,3.0,0\n100000,0,3.0,0\n")
+        (tmp_path / "boundaries" / "inflow_map.csv").write_text("x,y\n1,10\n1,11\n1,12\n")
+        cfg = tmp_path / "model.xml"
+        cfg.write_text(XML.format(scheme=scheme, precision=precision, duration=duration, outfreq=outfreq))
+        return str(cfg), bed
+    return make
+
+
+@pytest.fixture(scope="module")
+def host():
+    hpbuild.build()
+    hpbuild.build_host()
+    lib = C.CDLL(hpbuild.HOST_LIB)
+    lib.hph_model_load.restype = C.c_void_p
+    lib.hph_model_load.argtypes = [C.c_char_p, C.c_int]
+    lib.hph_model_run.argtypes = [C.c_void_p]
+    lib.hph_model_destroy.argtypes = [C.c_void_p]
+    for name in ("hph_model_states", "hph_model_bed", "hph_model_manning"):
+        getattr(lib, name).restype = C.POINTER(C.c_double)
+        getattr(lib, name).argtypes = [C.c_void_p]
+    lib.hph_error.restype = C.c_char_p
+    lib.hph_round.restype = C.c_double
+    lib.hph_round.argtypes = [C.c_double, C.c_int]
+    lib.hph_derive_output.restype = C.c_double
+    lib.hph_derive_output.argtypes = [C.c_char_p, C.POINTER(C.c_double), C.c_double, C.c_double]
+    return lib
+
+
+def info(lib, h):
+    cols, rows, bnd = C.c_ulong(), C.c_ulong(), C.c_uint()
+    res, dur, freq = C.c_double(), C.c_double(), C.c_double()
+    prec, scheme = C.c_int(), C.c_int()
+    lib.hph_model_info(C.c_void_p(h), C.byref(cols), C.byref(rows), C.byref(res), C.byref(dur), C.byref(freq), C.byref(prec), C.byref(scheme), C.byref(bnd))
+    return dict(cols=cols.value, rows=rows.value, resolution=res.value, duration=dur.value, output_frequency=freq.value,
+                precision=prec.value, scheme=scheme.value, boundaries=bnd.value)
+
+
+def arrays(lib, h, rows, cols):
+    n = rows * cols
+    st = np.ctypeslib.as_array(lib.hph_model_states(C.c_void_p(h)), shape=(n * 4,)).reshape(rows, cols, 4).copy()
+    bed = np.ctypeslib.as_array(lib.hph_model_bed(C.c_void_p(h)), shape=(n,)).reshape(rows, cols).copy()
+    man = np.ctypeslib.as_array(lib.hph_model_manning(C.c_void_p(h)), shape=(n,)).reshape(rows, cols).copy()
+    return st, bed, man
+
+
+def boundaries(lib, h, count):
+    out = []
+    for i in range(count):
+        kind, da, db, rel = C.c_int(), C.c_int(), C.c_int(), C.c_uint()
+        interval, length = C.c_double(), C.c_double()
+        series = C.POINTER(C.c_double)()
+        n = lib.hph_model_boundary(C.c_void_p(h), i, C.byref(kind), C.byref(da), C.byref(db), C.byref(interval), C.byref(length), C.byref(series), C.byref(rel))
+        out.append(dict(kind=kind.value, def_a=da.value, def_b=db.value, interval=interval.value, length=length.value,
+                        relations=rel.value, series=[series[j] for j in range(max(n, 0))]))
+    return out
+
+
+def test_rounding_matches_reference_util_round(host):
+    # src/util.cpp:79-93: half up for positives, negatives always towards -infinity
+    assert host.hph_round(1.23455, 4) == 1.2346 and host.hph_round(1.23454, 4) == 1.2345
+    assert host.hph_round(-1.23451, 4) == -1.2346 and host.hph_round(-0.00001, 4) == -0.0001
+    for v in (3.14159265, -2.000049, 0.00005, 17.99995):
+        assert host.hph_round(v, 4) == float(sc.round4(v))
+
+
+def test_output_value_derivation(host):
+    # src/Datasets/CRasterDataset.cpp:185-267
+    st = (C.c_double * 4)(12.5, 13.0, 1.0, -0.5)
+    d = lambda name, bed=10.0: host.hph_derive_output(name.encode(), st, bed, 2.0)
+    assert d("depth") == 2.5 and d("fsl") == 12.5 and d("maxdepth") == 3.0 and d("maxfsl") == 13.0
+    assert d("velocityx") == 0.4 and d("velocityy") == -0.2 and d("dischargex") == 2.0
+    assert abs(d("froude") - np.hypot(0.4, -0.2) / np.sqrt(9.81 * 2.5)) < 1e-15
+    assert d("depth", 12.5) == -9999.0 and d("velocityx", 12.5) == -9999.0 and d("fsl", 12.5) == -9999.0
+
+
+def test_configuration_is_parsed_like_the_reference(host, model_dir):
+    cfg, bed_in = model_dir(scheme="MUSCL-Hancock", precision="single", duration=7200, outfreq=600)
+    h = host.hph_model_load(cfg.encode(), 1)
+    assert h, [host.hph_error(i) for i in range(host.hph_error_count())]
+    i = info(host, h)
+    assert (i["cols"], i["rows"], i["resolution"]) == (40, 30, 2.0)
+    assert (i["duration"], i["output_frequency"], i["precision"], i["scheme"], i["boundaries"]) == (7200.0, 600.0, 0, 1, 3)
+    courant, dry, ts = C.c_double(), C.c_double(), C.c_double()
+    dyn, fric, queue = C.c_int(), C.c_int(), C.c_uint()
+    host.hph_model_scheme_params(C.c_void_p(h), C.byref(courant), C.byref(dry), C.byref(ts), C.byref(dyn), C.byref(fric), C.byref(queue))
+    assert (courant.value, dry.value, ts.value, dyn.value, fric.value, queue.value) == (0.5, 1e-10, 0.001, 1, 1, 16)
+    st, bed, man = arrays(host, h, 30, 40)
+    np.testing.assert_array_equal(bed, sc.round4(bed_in))               # 4-decimal ingestion, south-first rows
+    np.testing.assert_array_equal(st[..., 0], bed)                      # depth 0 => eta = bed
+    np.testing.assert_array_equal(st[..., 1], bed)                      # ... and eta_max = eta
+    assert (st[..., 2:] == 0).all() and (man == 0.03).all()
+    b = boundaries(host, h, 3)                                          # XML order
+    assert [x["kind"] for x in b] == [0, 0, 2]
+    assert b[0]["def_a"] == hc.UNIFORM_LOSS_RATE and b[0]["series"] == [0.0, 12.0, 1.0e8, 12.0] and b[0]["interval"] == 1.0e8
+    assert b[1]["def_a"] == hc.UNIFORM_RAIN_INTENSITY and b[1]["interval"] == 3600.0 and b[1]["length"] == 10800.0
+    assert b[2]["def_a"] == hc.DEPTH_IGNORE and b[2]["def_b"] == hc.DISCHARGE_IS_DISCHARGE and b[2]["relations"] == 3
+    msgs = [host.hph_error(i).decode() for i in range(host.hph_error_count())]
+    assert not any("Unrecognised" in m for m in msgs), msgs
+    host.hph_model_destroy(C.c_void_p(h))
+
+
+def test_bad_configurations_report_through_doError(host, model_dir, tmp_path):
+    cfg, _ = model_dir()
+    text = open(cfg).read()
+    bad = tmp_path / "bad_scheme.xml"
+    bad.write_text(text.replace('<scheme name="Godunov">', '<scheme name="lax-wendroff">'))
+    assert not host.hph_model_load(str(bad).encode(), 1)
+    assert "Unsupported scheme" in host.hph_error(host.hph_error_count() - 1).decode()
+    bad = tmp_path / "bad_xml.xml"
+    bad.write_text(text.replace("</simulation>", ""))
+    assert not host.hph_model_load(str(bad).encode(), 1)
+    assert "Cannot load configuration" in host.hph_error(host.hph_error_count() - 1).decode()
+    ref_cfg = "/root/reference/test/newcastle-centre.xml"
+    if os.path.exists(ref_cfg):      # the reference's own file parses; its HFA raster needs GDAL
+        assert not host.hph_model_load(ref_cfg.encode(), 1)
+        assert "structure raster" in host.hph_error(host.hph_error_count() - 1).decode()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scheme,name", [("Godunov", "godunov"), ("MUSCL-Hancock", "muscl-hancock"), ("Inertial", "inertial")])
+def test_model_run_matches_oracle_driven_the_same_way(host, model_dir, scheme, name):
+    from oracle import cpu_sim
+    from tests.helpers import make_cfg
+    cfg, _ = model_dir(scheme=scheme, duration=30, outfreq=10)
+    h = host.hph_model_load(cfg.encode(), 0)
+    assert h, [host.hph_error(i) for i in range(host.hph_error_count())]
+    st0, bed, man = arrays(host, h, 30, 40)
+    assert host.hph_model_run(C.c_void_p(h)) == 0
+    st1, _, _ = arrays(host, h, 30, 40)
+    t, dt, ok, skipped = C.c_double(), C.c_double(), C.c_uint(), C.c_uint()
+    host.hph_model_clock(C.c_void_p(h), C.byref(t), C.byref(dt), C.byref(ok), C.byref(skipped))
+    # the oracle, sequenced like CModel::runModel: targets at every output time, queue of 16
+    ocfg = make_cfg(name, "double", 30, 40, delta=2.0, end_time=30.0)
+    orc = cpu_sim.CpuSim("oracle", ocfg)
+    orc.upload(st0, bed, man)
+    orc.add_uniform(hc.UNIFORM_LOSS_RATE, [0.0, 1.0e8], [12.0, 12.0])
+    orc.add_uniform(hc.UNIFORM_RAIN_INTENSITY, [0.0, 3600.0, 7200.0, 10800.0], [70.0, 70.0, 0.0, 0.0])
+    orc.add_cell(hc.DEPTH_IGNORE, hc.DISCHARGE_IS_DISCHARGE, [10 * 40 + 1, 11 * 40 + 1, 12 * 40 + 1],
+                 [[0, 0, 0, 0], [10, 0, 1.0, 0], [100000, 0, 1.0, 0]])
+    for target in (10.0, 20.0, 30.0):
+        orc.set_target(target)
+        if orc.stats()["timestep"] <= 0.0:
+            orc.update_timestep()
+        while orc.stats()["time"] < target - 1e-5:
+            orc.iterate(16)
+    so = orc.stats()
+    assert abs(t.value - so["time"]) < 1e-9 and t.value == 30.0
+    assert (ok.value, skipped.value) == (so["batch_successful"], so["batch_skipped"])
+    want = orc.download()
+    assert np.abs(st1[..., 0] - want[..., 0]).max() <= 1e-9
+    assert np.abs(st1[..., 2:] - want[..., 2:]).max() <= 1e-7
+    # rasters: derived exactly as CRasterDataset::domainToRaster does, written north-first, every 10 s
+    out = os.path.join(os.path.dirname(cfg), "output")
+    assert sorted(os.listdir(out)) == sorted("%s_%d.asc" % (v, k) for v in ("depth", "velX", "fsl", "maxdepth") for k in (10, 20, 30))
+    depth, hdr = read_asc(os.path.join(out, "depth_30.asc"))
+    expect = np.maximum(st1[..., 0] - bed, 0.0)
+    expect = np.where(expect < 1e-8, -9999.0, expect)
+    np.testing.assert_allclose(depth, expect, rtol=0, atol=1e-15)
+    assert hdr["cellsize"] == 2.0 and hdr["nodata_value"] == -9999.0
+    host.hph_model_destroy(C.c_void_p(h))

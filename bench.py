@@ -189,9 +189,9 @@ def cpu_rate(w, n, steps, warmup, threads=0):
 
 def cpu_baseline(w, budget_s=12.0):
     cores = os.cpu_count() or 1
-    rate, _, kind = cpu_rate(w, 512, 2, 1)
     n = min(w["cols"], 2048)
-    steps = int(max(2, min(50, budget_s * rate / (n * n))))
+    rate, _, kind = cpu_rate(w, n, 3, 1)          # calibrate at the sample size, then fill the budget
+    steps = int(max(3, min(2000, budget_s * rate / (n * n))))
     rate, dt, kind = cpu_rate(w, n, steps, 1)
     return {"value": rate, "unit": "cell-updates/s", "cores": cores, "kind": kind,
             "sample": "%d steps of a %dx%d crop of the workload, all %d host threads (OpenMP), %.1f s" % (steps, n, n, cores, dt)}

@@ -56,7 +56,7 @@ def build(force=False, verbose=False):
     jobs = [
         ["nvcc"] + ARCH + COMMON + ptxas + ["-DHP_NS=hp_strict", "-DHP_FLAVOUR_STRICT", "-fmad=false", "-c",
                                             os.path.join(CSRC, "hp_kernels.cu"), "-o", os.path.join(obj, "hp_kernels_strict.o")],
-        ["nvcc"] + ARCH + COMMON + ptxas + ["-DHP_NS=hp_fast", "-c", os.path.join(CSRC, "hp_kernels.cu"), "-o",
+        ["nvcc"] + ARCH + COMMON + ptxas + ["-DHP_NS=hp_fast"] + (["-DHP_GODUNOV_STAGES=" + os.environ["HP_GODUNOV_STAGES"]] if "HP_GODUNOV_STAGES" in os.environ else []) + ["-c", os.path.join(CSRC, "hp_kernels.cu"), "-o",
                                             os.path.join(obj, "hp_kernels_fast.o")],
         ["nvcc"] + ARCH + COMMON + ["-c", os.path.join(CSRC, "hp_executor.cu"), "-o", os.path.join(obj, "hp_executor.o")],
         ["nvcc"] + ARCH + COMMON + (["-I", nccl_inc] if nccl_inc else []) + ["-x", "cu", "-c", os.path.join(CSRC, "hp_comm.cpp"),

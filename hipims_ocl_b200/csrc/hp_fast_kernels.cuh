@@ -25,6 +25,12 @@
 
 namespace HP_NS {
 
+// max / min as one compare + select (fmax/fmin also canonicalise NaNs, which costs instructions)
+template <class R> __device__ __forceinline__ R fm_max(R a, R b) { return a > b ? a : b; }
+template <class R> __device__ __forceinline__ R fm_min(R a, R b) { return a < b ? a : b; }
+// |v| < eps => 0: the reference's "round delta values to zero if small" (CLSchemeGodunov.clc:340-348)
+template <class R> __device__ __forceinline__ R fm_chop(R v, R eps) { return hp_abs(v) < eps ? R(0) : v; }
+
 // ---------------------------------------------------------------------------------------------
 // TMA / mbarrier primitives
 // ---------------------------------------------------------------------------------------------
@@ -51,12 +57,26 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
                  ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(bar) : "memory");
 }
 
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int x, int y) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y) : "memory");
+}
+
+#ifndef HP_GODUNOV_STAGES
+#define HP_GODUNOV_STAGES 1
+#endif
+#ifndef HP_F32_CTAS
+#define HP_F32_CTAS 9
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // Tile geometry
 // ---------------------------------------------------------------------------------------------
 template <class R> struct Tile {
-    static constexpr int TX = 64, TY = 8, NT = 256;
-    static constexpr int CTAS_PER_SM = sizeof(R) == 8 ? 2 : 4;    // register- and shared-memory-limited
+    static constexpr int TX = hp::kTmaTileX, TY = hp::kTmaTileY, NT = TX * TY / 2;   // two cells per thread
+    // STAGES = 2: the next tile streams in during compute (16 warps/SM in fp64).  STAGES = 1: no ring,
+    // shared memory then allows 24 warps/SM; the next tile is prefetched into L2 instead.
+    static constexpr int STAGES = HP_GODUNOV_STAGES;
+    static constexpr int CTAS_PER_SM = sizeof(R) == 8 ? (STAGES == 1 ? 6 : 4) : (STAGES == 1 ? HP_F32_CTAS : 8);
     // TMA wants the box to START on a 16-byte boundary of the inner dimension (measured on this
     // part: a start coordinate of x0-1 raises "illegal instruction") and its inner extent to be a
     // multiple of 16 bytes, so the halo columns are padded to CO = 16 / sizeof(R) on both sides.
@@ -67,7 +87,7 @@ template <class R> struct Tile {
     static constexpr int STAGE_BYTES = 4 * PLANE_BYTES;           // eta, qx, qy, zb
     static constexpr int NXF = (TX + 1) * TY, NYF = TX * (TY + 1);
     static constexpr int FX_BYTES = 3 * NXF * int(sizeof(R)), FY_BYTES = 3 * NYF * int(sizeof(R));
-    static constexpr int SMEM_BYTES = 2 * STAGE_BYTES + 3 * PLANE_BYTES + FX_BYTES + FY_BYTES + 64;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 3 * PLANE_BYTES + FX_BYTES + FY_BYTES + 64;
 };
 
 struct TmaMaps { CUtensorMap eta, qx, qy, zb; };
@@ -95,8 +115,8 @@ __device__ __forceinline__ Flux3<R> face_core_flux(const Params<R>& k, R etaL, R
     const R qnL = hL * unL, qnR = hR * unR;
     const R as = hp_abs(R(0.5) * (aL + aR) + R(0.25) * (unL - unR));     // sqrt(g h*) without the sqrt
     const R us = R(0.5) * (unL + unR) + aL - aR;
-    const R sL = dryL ? unR - 2 * aR : hp_fmin(unL - aL, us - as);
-    const R sR = dryR ? unL + 2 * aL : hp_fmax(unR + aR, us + as);
+    const R sL = dryL ? unR - 2 * aR : fm_min(unL - aL, us - as);
+    const R sR = dryR ? unL + 2 * aL : fm_max(unR + aR, us + as);
     const Flux3<R> FL{qnL, unL * qnL + hg * hL * hL, qnL * utL};
     const Flux3<R> FR{qnR, unR * qnR + hg * hR * hR, qnR * utR};
     if (sL >= R(0)) return FL;
@@ -107,7 +127,7 @@ __device__ __forceinline__ Flux3<R> face_core_flux(const Params<R>& k, R etaL, R
     const R f2 = (sR * FL.n - sL * FR.n + ss * (qnR - qnL)) * inv;
     const R mR = hR * (unR - sR), mL = hL * (unL - sL);
     const R num = sL * mR - sR * mL, den = mR - mL;                       // S_M = num / den, only its sign matters
-    const bool smPos = (num == R(0)) ? (den != R(0)) : ((num > R(0)) == (den > R(0)) && den != R(0));
+    const bool smPos = num * den >= R(0) && den != R(0);                  // NaN (0/0) counts as "not >= 0", like the reference
     return Flux3<R>{f1, f2, f1 * (smPos ? utL : utR)};
 }
 
@@ -153,12 +173,12 @@ godunov_step_tma(const StepArgs a, const __grid_constant__ TmaMaps maps) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char* base = smem_raw;
     // [stage0: eta qx qy zb][stage1: ...][u][v][c][FX][FY][barriers]
-    R* const s_u = reinterpret_cast<R*>(base + 2 * T::STAGE_BYTES);
-    R* const s_v = reinterpret_cast<R*>(base + 2 * T::STAGE_BYTES + T::PLANE_BYTES);
-    R* const s_c = reinterpret_cast<R*>(base + 2 * T::STAGE_BYTES + 2 * T::PLANE_BYTES);
-    R* const s_fx = reinterpret_cast<R*>(base + 2 * T::STAGE_BYTES + 3 * T::PLANE_BYTES);
-    R* const s_fy = reinterpret_cast<R*>(base + 2 * T::STAGE_BYTES + 3 * T::PLANE_BYTES + T::FX_BYTES);
-    uint64_t* const s_bar = reinterpret_cast<uint64_t*>(base + 2 * T::STAGE_BYTES + 3 * T::PLANE_BYTES + T::FX_BYTES + T::FY_BYTES);
+    R* const s_u = reinterpret_cast<R*>(base + T::STAGES * T::STAGE_BYTES);
+    R* const s_v = reinterpret_cast<R*>(base + T::STAGES * T::STAGE_BYTES + T::PLANE_BYTES);
+    R* const s_c = reinterpret_cast<R*>(base + T::STAGES * T::STAGE_BYTES + 2 * T::PLANE_BYTES);
+    R* const s_fx = reinterpret_cast<R*>(base + T::STAGES * T::STAGE_BYTES + 3 * T::PLANE_BYTES);
+    R* const s_fy = reinterpret_cast<R*>(base + T::STAGES * T::STAGE_BYTES + 3 * T::PLANE_BYTES + T::FX_BYTES);
+    uint64_t* const s_bar = reinterpret_cast<uint64_t*>(base + T::STAGES * T::STAGE_BYTES + 3 * T::PLANE_BYTES + T::FX_BYTES + T::FY_BYTES);
 
     const Params<R> k = make_params<R>(a.params);
     const Grid g = a.grid;
@@ -170,6 +190,8 @@ godunov_step_tma(const StepArgs a, const __grid_constant__ TmaMaps maps) {
     const int tiles_x = (g.cols + T::TX - 1) / T::TX;
     const int tiles_y = (a.y1 - a.y0 + T::TY - 1) / T::TY;
     const int ntiles = tiles_x * tiles_y;
+    const double inv_tiles_x = 1.0 / tiles_x;
+    auto tile_row = [&](int tile) { return static_cast<int>((tile + 0.5) * inv_tiles_x); };   // exact for < 2^31 tiles
 
     const uint32_t bar0 = smem_u32(&s_bar[0]), bar1 = smem_u32(&s_bar[1]);
     if (tid == 0) {
@@ -180,7 +202,7 @@ godunov_step_tma(const StepArgs a, const __grid_constant__ TmaMaps maps) {
     __syncthreads();
 
     auto issue = [&](int tile, int stage) {   // one thread: arm the barrier, launch the four plane loads
-        const int tx = tile % tiles_x, ty = tile / tiles_x;
+        const int ty = tile_row(tile), tx = tile - ty * tiles_x;
         const int x = tx * T::TX - T::CO, y = a.y0 + ty * T::TY - 1;
         const uint32_t bar = stage ? bar1 : bar0;
         const uint32_t dst = smem_u32(base + stage * T::STAGE_BYTES);
@@ -189,6 +211,12 @@ godunov_step_tma(const StepArgs a, const __grid_constant__ TmaMaps maps) {
         tma_load_2d(dst + 1 * T::PLANE_BYTES, &maps.qx, x, y, bar);
         tma_load_2d(dst + 2 * T::PLANE_BYTES, &maps.qy, x, y, bar);
         tma_load_2d(dst + 3 * T::PLANE_BYTES, &maps.zb, x, y, bar);
+    };
+
+    auto prefetch_l2 = [&](int tile) {        // warm L2 with the next tile's boxes
+        const int ty = tile_row(tile), tx = tile - ty * tiles_x;
+        const int x = tx * T::TX - T::CO, y = a.y0 + ty * T::TY - 1;
+        tma_prefetch_2d(&maps.eta, x, y); tma_prefetch_2d(&maps.qx, x, y); tma_prefetch_2d(&maps.qy, x, y); tma_prefetch_2d(&maps.zb, x, y);
     };
 
     const View<R> s(a.src);
@@ -201,16 +229,22 @@ godunov_step_tma(const StepArgs a, const __grid_constant__ TmaMaps maps) {
     if (tid == 0 && tile < ntiles) issue(tile, 0);
 
     for (int it = 0; tile < ntiles; ++it, tile += gridDim.x) {
-        const int stage = it & 1;
+        const int stage = T::STAGES == 2 ? (it & 1) : 0;
         const int next = tile + gridDim.x;
-        if (tid == 0 && next < ntiles) issue(next, stage ^ 1);
+        if (T::STAGES == 2) {
+            if (tid == 0 && next < ntiles) issue(next, stage ^ 1);
+        } else {
+            if (tid == 0 && it > 0) issue(tile, 0);
+            if (tid == 32 && next < ntiles) prefetch_l2(next);
+        }
         if (stage == 0) { mbar_wait(bar0, phase0); phase0 ^= 1; } else { mbar_wait(bar1, phase1); phase1 ^= 1; }
 
         const R* const t_eta = reinterpret_cast<const R*>(base + stage * T::STAGE_BYTES);
         const R* const t_qx = reinterpret_cast<const R*>(base + stage * T::STAGE_BYTES + T::PLANE_BYTES);
         const R* const t_qy = reinterpret_cast<const R*>(base + stage * T::STAGE_BYTES + 2 * T::PLANE_BYTES);
         const R* const t_zb = reinterpret_cast<const R*>(base + stage * T::STAGE_BYTES + 3 * T::PLANE_BYTES);
-        const int x0 = (tile % tiles_x) * T::TX, y0 = a.y0 + (tile / tiles_x) * T::TY;
+        const int trow = tile_row(tile);
+        const int x0 = (tile - trow * tiles_x) * T::TX, y0 = a.y0 + trow * T::TY;
 
         // point-wise planes (no halo): issue the global loads now, they are consumed in phase D
         R pre_emax[2], pre_mann[2];
@@ -273,7 +307,7 @@ godunov_step_tma(const StepArgs a, const __grid_constant__ TmaMaps maps) {
                 const R h = c.eta - zb;
                 if (h > k.eps10 && c.emax > R(-9999.0)) {
                     const R cc = s_c[o];
-                    const R sp = k.simplified_speed ? cc : hp_fmax(hp_abs(u), hp_abs(v)) + cc;
+                    const R sp = k.simplified_speed ? cc : fm_max(hp_abs(u), hp_abs(v)) + cc;
                     ws = sp > ws ? sp : ws;
                 }
             }
@@ -290,13 +324,9 @@ godunov_step_tma(const StepArgs a, const __grid_constant__ TmaMaps maps) {
                     const int oN = o + T::BW, oS = o - T::BW, oE = o + 1, oW = o - 1;
                     const R etaN = t_eta[oN], etaS = t_eta[oS], etaE = t_eta[oE], etaW = t_eta[oW];
                     const R zN = t_zb[oN], zS = t_zb[oS], zE = t_zb[oE], zW = t_zb[oW];
-                    int dry = 0;
-                    if (c.eta - zb < k.eps) ++dry;
-                    if (etaN - zN < k.eps) ++dry;
-                    if (etaE - zE < k.eps) ++dry;
-                    if (etaS - zS < k.eps) ++dry;
-                    if (etaW - zW < k.eps) ++dry;
-                    if (dry < 5) {
+                    const bool all_dry = c.eta - zb < k.eps && etaN - zN < k.eps && etaE - zE < k.eps && etaS - zS < k.eps &&
+                                         etaW - zW < k.eps;                      // dry count of five, CLSchemeGodunov.clc:248-255
+                    if (!all_dry) {
                         int stop = 0;
                         R bN, bS, bE, bW, hnN, hnS, hnE, hnW;
                         face_owner_terms<R, true>(k, c.eta, zb, v, c.qy, etaN, zN, s_v[oN], bN, hnN, stop);
@@ -312,7 +342,7 @@ godunov_step_tma(const StepArgs a, const __grid_constant__ TmaMaps maps) {
                         R dEta = ((mE - mW) + (mN - mS)) * inv_delta;
                         R dQx = ((nE - nW) + (tN - tS) + hg * (bE - bW) * (hnE + hnW)) * inv_delta;
                         R dQy = ((tE - tW) + (nN - nS) + hg * (bN - bS) * (hnN + hnS)) * inv_delta;
-                        dEta = chop(dEta, k.eps); dQx = chop(dQx, k.eps); dQy = chop(dQy, k.eps);
+                        dEta = fm_chop(dEta, k.eps); dQx = fm_chop(dQx, k.eps); dQy = fm_chop(dQy, k.eps);
                         if (stop > 0) { c.qx = R(0); c.qy = R(0); }
                         c.eta = c.eta - dt * dEta; c.qx = c.qx - dt * dQx; c.qy = c.qy - dt * dQy;
                         h_new = c.eta - zb;
@@ -333,7 +363,7 @@ godunov_step_tma(const StepArgs a, const __grid_constant__ TmaMaps maps) {
                     R sp = cc;
                     if (!k.simplified_speed) {
                         const R rh = have_new ? rh_new : fm_rcp(h);
-                        sp = hp_fmax(hp_abs(c.qx * rh), hp_abs(c.qy * rh)) + cc;
+                        sp = fm_max(hp_abs(c.qx * rh), hp_abs(c.qy * rh)) + cc;
                     }
                     ws = sp > ws ? sp : ws;
                 }
@@ -377,7 +407,7 @@ template <class R> static int launch_godunov_tma(const StepArgs& a_in, const Tma
 // Phase D  corrector; state ping-pongs and every owned cell is written (see step_mh_v1).
 // =============================================================================================
 template <class R> struct TileMH {
-    static constexpr int TX = 64, TY = 8, NT = 256;
+    static constexpr int TX = hp::kTmaTileXMH, TY = hp::kTmaTileY, NT = 256;
     static constexpr int CTAS_PER_SM = sizeof(R) == 8 ? 2 : 3;
     static constexpr int CO = 16 / int(sizeof(R));                // >= 2 halo columns, box starts 16-byte aligned
     static constexpr int BW = TX + 2 * CO, BH = TY + 4;
@@ -504,7 +534,7 @@ mh_step_tma(const StepArgs a, const __grid_constant__ TmaMaps maps) {
                 R dEta = ((qxE - qxW) + (qyN - qyS)) * inv_delta;
                 R dQx = (uE * qxE - uW * qxW + vN * qxN - vS * qxS + hg * sxE * (hEf + hWf)) * inv_delta;
                 R dQy = (uE * qyE - uW * qyW + vN * qyN - vS * qyS + hg * syE * (hNf + hSf)) * inv_delta;
-                dEta = chop(dEta, k.eps); dQx = chop(dQx, k.eps); dQy = chop(dQy, k.eps);
+                dEta = fm_chop(dEta, k.eps); dQx = fm_chop(dQx, k.eps); dQy = fm_chop(dQy, k.eps);
                 e2 = eta - half * dt * dEta; qx2 = qx - half * dt * dQx; qy2 = qy - half * dt * dQy;
             }
             s_p[0 * T::PPLANE + i] = e2;   s_p[1 * T::PPLANE + i] = qx2;  s_p[2 * T::PPLANE + i] = qy2;
@@ -598,7 +628,7 @@ mh_step_tma(const StepArgs a, const __grid_constant__ TmaMaps maps) {
                              hg * (bE - bW) * (hnE + hnW)) * inv_delta;
                     R dQy = ((s_f[2 * T::NF + fe] - s_f[2 * T::NF + fw]) + (s_f[T::NF + fn] - s_f[T::NF + fs]) +
                              hg * (bN - bS) * (hnN + hnS)) * inv_delta;
-                    dEta = chop(dEta, k.eps); dQx = chop(dQx, k.eps); dQy = chop(dQy, k.eps);
+                    dEta = fm_chop(dEta, k.eps); dQx = fm_chop(dQx, k.eps); dQy = fm_chop(dQy, k.eps);
                     if (stop > 0) { c.qx = R(0); c.qy = R(0); }
                     c.eta = c.eta - dt * dEta; c.qx = c.qx - dt * dQx; c.qy = c.qy - dt * dQy;
                     const R h_new = c.eta - zb;
@@ -613,7 +643,7 @@ mh_step_tma(const StepArgs a, const __grid_constant__ TmaMaps maps) {
                 if (h > k.eps10 && c.emax > R(-9999.0)) {
                     const R cc = fm_sqrt(k.g * h);
                     R sp = cc;
-                    if (!k.simplified_speed) { const R rh = fm_rcp(h); sp = hp_fmax(hp_abs(c.qx * rh), hp_abs(c.qy * rh)) + cc; }
+                    if (!k.simplified_speed) { const R rh = fm_rcp(h); sp = fm_max(hp_abs(c.qx * rh), hp_abs(c.qy * rh)) + cc; }
                     ws = sp > ws ? sp : ws;
                 }
             }

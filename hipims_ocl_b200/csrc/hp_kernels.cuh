@@ -73,8 +73,10 @@ struct BdyCellArgs {
 struct alignas(64) TmaMapsPOD { unsigned char bytes[4][128]; };
 // haloed tile box of the TMA-staged kernels: 64 x 8 cells plus halo; the box must start on a
 // 16-byte boundary of the inner dimension, so it carries 16 / real_bytes halo columns per side
-constexpr int kTmaTileX = 64, kTmaTileY = 8;
-constexpr int tma_box_w(int real_bytes, int /*halo*/) { return kTmaTileX + 2 * (16 / real_bytes); }
+constexpr int kTmaTileX = 32, kTmaTileY = 8;        // Godunov tile
+constexpr int kTmaTileXMH = 64;                     // MUSCL-Hancock tile (halo of two)
+constexpr int tma_tile_x(int halo) { return halo == 2 ? kTmaTileXMH : kTmaTileX; }
+constexpr int tma_box_w(int real_bytes, int halo) { return tma_tile_x(halo) + 2 * (16 / real_bytes); }
 constexpr int tma_box_h(int halo) { return kTmaTileY + 2 * halo; }
 
 // The launch interface of one compiled flavour (strict / fast).

@@ -424,9 +424,16 @@ template <class R> struct TileMH {
     static constexpr int SMEM_BYTES = OFF_BAR + 64;
 };
 
-template <class R> __device__ __forceinline__ R minmod(R a, R b) {
-    // phi(r) a with r = b / a, phi = max(0, min(r, 1)) (CLSlopeLimiterMINMOD.clc:49-70, beta = 1)
-    return (a * b <= R(0)) ? R(0) : (hp_abs(b) < hp_abs(a) ? b : a);
+// phi(r) a with r = b / a, phi = max(0, min(r, 1)) (CLSlopeLimiterMINMOD.clc:49-70, beta = 1): the argument of
+// smaller magnitude when the signs agree, else 0.  A zero argument is picked by the magnitude test
+// itself, so only the sign bits need comparing (integer pipe instead of an fp64 multiply + compare).
+__device__ __forceinline__ double minmod(double a, double b) {
+    const double t = fabs(b) < fabs(a) ? b : a;
+    return ((__double2hiint(a) ^ __double2hiint(b)) < 0) ? 0.0 : t;
+}
+__device__ __forceinline__ float minmod(float a, float b) {
+    const float t = fabsf(b) < fabsf(a) ? b : a;
+    return ((__float_as_int(a) ^ __float_as_int(b)) < 0) ? 0.0f : t;
 }
 
 template <class R>
@@ -467,8 +474,31 @@ mh_step_tma(const StepArgs a, const __grid_constant__ TmaMaps maps) {
     R ws = R(0);
     uint32_t phase = 0;
 
+    const double inv_tiles_x = 1.0 / tiles_x;
+    auto tile_origin = [&](int tile, int& x0, int& y0) {      // exact without an integer division
+        const int ty = static_cast<int>((tile + 0.5) * inv_tiles_x);
+        x0 = (tile - ty * tiles_x) * T::TX; y0 = a.y0 + ty * T::TY;
+    };
+    // eta_max of tile + halo 2 only matters as two flags per cell; the values are loaded one tile ahead
+    constexpr int NEM = ((T::TX + 4) * T::BH + T::NT - 1) / T::NT;
+    R em_next[NEM];
+    auto load_emax = [&](int tile) {
+        int x0, y0;
+        tile_origin(tile, x0, y0);
+#pragma unroll
+        for (int r = 0; r < NEM; ++r) {
+            const int i = tid + r * T::NT;
+            const int x = x0 + i % (T::TX + 4) - 2, y = y0 + i / (T::TX + 4) - 2;
+            const bool in = i < (T::TX + 4) * T::BH && x >= 0 && x < g.cols && y >= 0 && y < g.rows;
+            em_next[r] = in ? s.emax[static_cast<size_t>(y) * g.pitch + x] : R(1);   // outside: neither flag
+        }
+    };
+    if (static_cast<int>(blockIdx.x) < ntiles) load_emax(blockIdx.x);
+
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int x0 = (tile % tiles_x) * T::TX, y0 = a.y0 + (tile / tiles_x) * T::TY;
+        int x0, y0;
+        tile_origin(tile, x0, y0);
+        const int next = tile + gridDim.x;
         if (tid == 0) {
             mbar_expect_tx(bar, 4u * T::BW * T::BH * sizeof(R));
             const uint32_t dst = smem_u32(base);
@@ -477,16 +507,20 @@ mh_step_tma(const StepArgs a, const __grid_constant__ TmaMaps maps) {
             tma_load_2d(dst + 2 * T::PLANE_BYTES, &maps.qy, x0 - T::CO, y0 - 2, bar);
             tma_load_2d(dst + 3 * T::PLANE_BYTES, &maps.zb, x0 - T::CO, y0 - 2, bar);
         }
-        // eta_max: flags for tile + halo 2 (plain loads), own values kept for phase D
-        for (int i = tid; i < (T::TX + 4) * T::BH; i += T::NT) {
-            const int lx = i % (T::TX + 4) + T::CO - 2, ly = i / (T::TX + 4);
-            const int x = x0 + lx - T::CO, y = y0 + ly - 2;
-            unsigned char fl = 0;
-            if (x >= 0 && x < g.cols && y >= 0 && y < g.rows) {
-                const R em = s.emax[static_cast<size_t>(y) * g.pitch + x];
-                fl = (em <= R(-9998.0) ? 1 : 0) | (em < k.eps ? 2 : 0);
+        if (tid == 32 && next < ntiles) {          // warm L2 with the next tile's boxes
+            int nx0, ny0;
+            tile_origin(next, nx0, ny0);
+            tma_prefetch_2d(&maps.eta, nx0 - T::CO, ny0 - 2); tma_prefetch_2d(&maps.qx, nx0 - T::CO, ny0 - 2);
+            tma_prefetch_2d(&maps.qy, nx0 - T::CO, ny0 - 2); tma_prefetch_2d(&maps.zb, nx0 - T::CO, ny0 - 2);
+        }
+#pragma unroll
+        for (int r = 0; r < NEM; ++r) {
+            const int i = tid + r * T::NT;
+            if (i < (T::TX + 4) * T::BH) {
+                const R em = em_next[r];
+                s_flag[(i / (T::TX + 4)) * T::BW + i % (T::TX + 4) + T::CO - 2] =
+                    static_cast<unsigned char>((em <= R(-9998.0) ? 1 : 0) | (em < k.eps ? 2 : 0));
             }
-            s_flag[ly * T::BW + lx] = fl;
         }
         R pre_emax[2], pre_mann[2];
 #pragma unroll
@@ -543,6 +577,8 @@ mh_step_tma(const StepArgs a, const __grid_constant__ TmaMaps maps) {
         }
         __syncthreads();
 
+        if (next < ntiles) load_emax(next);     // in flight during phases C and D
+
         // ---- phase C: every face once --------------------------------------------------------------
         if (dt > R(0)) {
             for (int f = tid; f < T::NF; f += T::NT) {
@@ -590,6 +626,7 @@ mh_step_tma(const StepArgs a, const __grid_constant__ TmaMaps maps) {
                     const R sxE = s_p[3 * T::PPLANE + p], sxH = s_p[4 * T::PPLANE + p];
                     const R syE = s_p[7 * T::PPLANE + p], syH = s_p[8 * T::PPLANE + p];
                     int stop = 0;
+                    bool front = false;
                     R bN, bS, bE, bW, hnN, hnS, hnE, hnW;
                     // owner-side terms of one face: own face estimate (etaO, hO) against the neighbour's
                     auto owner = [&](const bool ownIsLeft, const bool isx, const R etaO, const R hO, const int pn, const int on,
@@ -600,27 +637,41 @@ mh_step_tma(const StepArgs a, const __grid_constant__ TmaMaps maps) {
                         const R hN_ = (s_p[pn] - t_zb[on]) + sgn * s_p[(sb + 1) * T::PPLANE + pn];
                         const R zO = etaO - hO, zN_ = etaN_ - hN_;
                         const R zmax = zO > zN_ ? zO : zN_;
-                        const R hOwn = (etaO - zmax > R(0)) ? (etaO - zmax) : R(0);
                         hNb = (etaN_ - zmax > R(0)) ? (etaN_ - zmax) : R(0);
                         bed = zmax < etaO ? zmax : etaO;
-                        if (hOwn <= k.eps || hNb <= k.eps) {               // wet/dry front: stop tests (:1172-1204)
-                            const int qb = isx ? 1 : 2;                    // normal discharge plane
-                            const R qO = s_p[qb * T::PPLANE + p] + (ownIsLeft ? half : -half) * s_p[(sb + qb + 1) * T::PPLANE + p];
-                            const R qN_ = s_p[qb * T::PPLANE + pn] + sgn * s_p[(sb + qb + 1) * T::PPLANE + pn];
-                            const R unO = hO <= k.eps ? R(0) : qO * fm_rcp(hO), unN = hN_ <= k.eps ? R(0) : qN_ * fm_rcp(hN_);
-                            const R ownQn = isx ? c.qx : c.qy;
-                            const R hL = ownIsLeft ? hOwn : hNb, hR = ownIsLeft ? hNb : hOwn;
-                            const R unL = ownIsLeft ? unO : unN, unR = ownIsLeft ? unN : unO;
-                            if (ownIsLeft) { if (hL <= k.eps && ownQn > R(0)) ++stop; }
-                            else           { if (hR <= k.eps && ownQn < R(0)) ++stop; }
-                            if (hR <= k.eps && unL < R(0)) ++stop;
-                            if (hL <= k.eps && unR > R(0)) ++stop;
-                        }
+                        front = front || (etaO - zmax <= k.eps) || (hNb <= k.eps);
+                    };
+                    // stop tests of one face (CLSchemeMUSCLHancock.clc:1172-1204); only reached at wet/dry fronts
+                    auto owner_stop = [&](const bool ownIsLeft, const bool isx, const R etaO, const R hO, const int pn, const int on) {
+                        const int sb = isx ? 3 : 7, qb = isx ? 1 : 2;
+                        const R sgn = ownIsLeft ? -half : half;
+                        const R etaN_ = s_p[pn] + sgn * s_p[sb * T::PPLANE + pn];
+                        const R hN_ = (s_p[pn] - t_zb[on]) + sgn * s_p[(sb + 1) * T::PPLANE + pn];
+                        const R zO = etaO - hO, zN_ = etaN_ - hN_;
+                        const R zmax = zO > zN_ ? zO : zN_;
+                        const R hOwn = (etaO - zmax > R(0)) ? (etaO - zmax) : R(0);
+                        const R hNb = (etaN_ - zmax > R(0)) ? (etaN_ - zmax) : R(0);
+                        const R qO = s_p[qb * T::PPLANE + p] + (ownIsLeft ? half : -half) * s_p[(sb + qb + 1) * T::PPLANE + p];
+                        const R qN_ = s_p[qb * T::PPLANE + pn] + sgn * s_p[(sb + qb + 1) * T::PPLANE + pn];
+                        const R unO = hO <= k.eps ? R(0) : qO * fm_rcp(hO), unN = hN_ <= k.eps ? R(0) : qN_ * fm_rcp(hN_);
+                        const R ownQn = isx ? c.qx : c.qy;
+                        const R hL = ownIsLeft ? hOwn : hNb, hR = ownIsLeft ? hNb : hOwn;
+                        const R unL = ownIsLeft ? unO : unN, unR = ownIsLeft ? unN : unO;
+                        if (ownIsLeft) { if (hL <= k.eps && ownQn > R(0)) ++stop; }
+                        else           { if (hR <= k.eps && ownQn < R(0)) ++stop; }
+                        if (hR <= k.eps && unL < R(0)) ++stop;
+                        if (hL <= k.eps && unR > R(0)) ++stop;
                     };
                     owner(true, false, e2 + half * syE, hc2 + half * syH, p + T::PW, o + T::BW, bN, hnN);
                     owner(false, false, e2 - half * syE, hc2 - half * syH, p - T::PW, o - T::BW, bS, hnS);
                     owner(true, true, e2 + half * sxE, hc2 + half * sxH, p + 1, o + 1, bE, hnE);
                     owner(false, true, e2 - half * sxE, hc2 - half * sxH, p - 1, o - 1, bW, hnW);
+                    if (front) {
+                        owner_stop(true, false, e2 + half * syE, hc2 + half * syH, p + T::PW, o + T::BW);
+                        owner_stop(false, false, e2 - half * syE, hc2 - half * syH, p - T::PW, o - T::BW);
+                        owner_stop(true, true, e2 + half * sxE, hc2 + half * sxH, p + 1, o + 1);
+                        owner_stop(false, true, e2 - half * sxE, hc2 - half * sxH, p - 1, o - 1);
+                    }
                     const int fe = j * (T::TX + 1) + i + 1, fw = fe - 1;
                     const int fn = T::NXF + (j + 1) * T::TX + i, fs = fn - T::TX;
                     R dEta = ((s_f[fe] - s_f[fw]) + (s_f[fn] - s_f[fs])) * inv_delta;

@@ -125,9 +125,10 @@ __device__ __forceinline__ Flux3<R> face_core_flux(const Params<R>& k, R etaL, R
     const R ss = sL * sR;
     const R f1 = (sR * FL.m - sL * FR.m + ss * (hR - hL)) * inv;
     const R f2 = (sR * FL.n - sL * FR.n + ss * (qnR - qnL)) * inv;
-    const R mR = hR * (unR - sR), mL = hL * (unL - sL);
-    const R num = sL * mR - sR * mL, den = mR - mL;                       // S_M = num / den, only its sign matters
-    const bool smPos = num * den >= R(0) && den != R(0);                  // NaN (0/0) counts as "not >= 0", like the reference
+    // The contact speed S_M = num / den has num = -f1 (sR - sL) and den = hR (unR - sR) - hL (unL - sL) < 0
+    // whenever sL < unL and unR < sR (true by construction of the wave speeds), so sign(S_M) = sign(f1):
+    // the tangential momentum is upwinded by the direction of the mass flux, no quotient needed.
+    const bool smPos = f1 >= R(0);
     return Flux3<R>{f1, f2, f1 * (smPos ? utL : utR)};
 }
 

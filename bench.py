@@ -42,9 +42,51 @@ WORKLOADS = {
     "dambreak4096-inertial-f32": dict(scheme="inertial", precision="single", cols=4096, rows_per_gpu=4096, scenario="dambreak"),
     "pluvial4096-mh": dict(scheme="muscl-hancock", precision="double", cols=4096, rows_per_gpu=4096, scenario="pluvial"),
     "pluvial4096": dict(scheme="godunov", precision="double", cols=4096, rows_per_gpu=4096, scenario="pluvial"),
-    "pluvial16384": dict(scheme="muscl-hancock", precision="double", cols=16384, rows_per_gpu=16384, scenario="pluvial"),
-    "river32768": dict(scheme="muscl-hancock", precision="double", cols=32768, rows_per_gpu=4096, scenario="valley"),
+    # configs[0] shape (the DEM itself needs an HFA reader): 342 x 195 at 2 m, rain 70 mm/h + losses 12 mm/h
+    "newcastle": dict(scheme="godunov", precision="double", cols=342, rows_per_gpu=195, scenario="pluvial", delta=2.0,
+                      boundaries="rain+loss"),
+    # configs[2]: uniform time-varying rain on a 16384^2 fractal DEM, MUSCL-Hancock fp64
+    "pluvial16384": dict(scheme="muscl-hancock", precision="double", cols=16384, rows_per_gpu=16384, scenario="pluvial",
+                         boundaries="rain-series"),
+    # configs[3]: 16384^2, inertial fp32, gridded radar rain + 1024 point volume sources
+    "radar16384": dict(scheme="inertial", precision="single", cols=16384, rows_per_gpu=16384, scenario="pluvial",
+                       boundaries="radar+sewers"),
+    # configs[4]: 32768 columns x 4096 rows per GPU, MUSCL-Hancock fp64, imposed discharge (west) and level (east)
+    "river32768": dict(scheme="muscl-hancock", precision="double", cols=32768, rows_per_gpu=4096, scenario="valley",
+                       boundaries="river"),
 }
+
+
+def attach_boundaries(sim, w, cols, total_rows):
+    """Boundary sets of the BASELINE configs; cell ids are global."""
+    kind = w.get("boundaries")
+    if not kind:
+        return
+    from hipims_ocl_b200 import config as hc
+    if kind == "rain+loss":
+        sim.add_uniform(hc.UNIFORM_LOSS_RATE, [0.0, 1.0e8], [12.0, 12.0])
+        sim.add_uniform(hc.UNIFORM_RAIN_INTENSITY, [0.0, 3600.0, 7200.0, 10800.0], [70.0, 70.0, 0.0, 0.0])
+    elif kind == "rain-series":
+        sim.add_uniform(hc.UNIFORM_RAIN_INTENSITY, [0.0, 1800.0, 3600.0, 5400.0], [50.0, 100.0, 0.0, 0.0])
+    elif kind == "radar+sewers":
+        rng = np.random.default_rng(7)
+        gr, gc = -(-total_rows // 256), -(-cols // 256)
+        sim.add_gridded(hc.GRIDDED_RAIN_INTENSITY, 300.0, 256.0, 0.0, 0.0, rng.uniform(0.0, 80.0, size=(13, gr, gc)))
+        pts = rng.integers(1, [total_rows - 1, cols - 1], size=(1024, 2))
+        ids = sorted(set(int(y) * cols + int(x) for y, x in pts))
+        sim.add_cell(hc.DEPTH_IGNORE, hc.DISCHARGE_IS_VOLUME, ids, [[0.0, 0.0, 0.0, 0.0], [600.0, 0.0, 2.0, 0.0], [1200.0, 0.0, 0.0, 0.0], [1.0e6, 0.0, 0.0, 0.0]])
+    elif kind == "river":
+        mid, band = total_rows // 2, max(4, total_rows // 64)
+        west = [y * cols + 1 for y in range(mid - band, mid + band)]
+        ts = np.array([[0.0, 0.0, 0.0, 0.0], [600.0, 0.0, 5000.0, 0.0], [1.0e6, 0.0, 5000.0, 0.0]])
+        ts[:, 2] /= len(west)
+        sim.add_cell(hc.DEPTH_IGNORE, hc.DISCHARGE_IS_DISCHARGE, west, ts)
+        east = [y * cols + cols - 2 for y in range(mid - band, mid + band)]
+        t = np.arange(0.0, 44700.0 * 2, 447.0)
+        tide = np.stack([t, 3.0 + 2.0 * np.sin(2 * np.pi * t / 44700.0), 0 * t, 0 * t], axis=1)
+        sim.add_cell(hc.DEPTH_IS_FSL, hc.DISCHARGE_IGNORE, east, tide)
+    else:
+        raise ValueError(kind)
 
 
 def peak_hbm():
@@ -155,8 +197,8 @@ def make_inputs(w, rows, cols, dtype, row_offset=0, total_rows=None):
 
 
 def cfg_for(w, rows, cols):
-    return SchemeConfig(scheme=w["scheme"], precision=w["precision"], rows=rows, cols=cols, delta=1.0, end_time=1.0e7,
-                        friction=True)
+    return SchemeConfig(scheme=w["scheme"], precision=w["precision"], rows=rows, cols=cols, delta=w.get("delta", 1.0),
+                        end_time=1.0e7, friction=True)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -178,6 +220,7 @@ def cpu_rate(w, n, steps, warmup, threads=0):
     bed, st, man = make_inputs(w, n, n, dtype)
     sim = cpu_sim.CpuSim(backend, cfg, threads=threads)
     sim.upload(st, bed, man)
+    attach_boundaries(sim, w, n, n)
     sim.set_target(1.0e7)
     sim.iterate(warmup)
     t0 = time.perf_counter()
@@ -278,6 +321,7 @@ def main():
         ids = [hx.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         sim.attach_comm(ids[0], rank, world)
+    attach_boundaries(sim, w, cols, total_rows)
 
     # pinned host buffers for the end-to-end leg
     t_st = torch.from_numpy(st).pin_memory()

@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <iterator>
 #include <sstream>
 
 namespace model {
@@ -181,6 +182,119 @@ bool CCSVDataset::readFile() {
 }
 
 bool SRaster::read(const std::string& path) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f) return false;
+    char tag[16] = {0};
+    f.read(tag, 15);
+    f.close();
+    return std::string(tag) == "EHFA_HEADER_TAG" ? readHFA(path) : readASCII(path);
+}
+
+// ERDAS IMAGINE HFA: header tag -> Ehfa_File -> tree of Ehfa_Entry nodes; the first Eimg_Layer gives
+// width/height/pixel type/block size, its RasterDMS (Edms_State) child the block table, its Map_Info child
+// the georeferencing.  Compressed blocks: {u32 min, i32 runs, i32 data offset, u8 bits} then run lengths
+// (top two bits of the first byte = number of extra bytes, big-endian) and values (big-endian, offset by min).
+bool SRaster::readHFA(const std::string& path) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f) return false;
+    std::vector<unsigned char> d((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    auto u32 = [&](size_t o) -> uint32_t { return o + 4 <= d.size() ? (uint32_t)d[o] | (uint32_t)d[o + 1] << 8 | (uint32_t)d[o + 2] << 16 | (uint32_t)d[o + 3] << 24 : 0u; };
+    auto u16 = [&](size_t o) -> uint32_t { return o + 2 <= d.size() ? (uint32_t)d[o] | (uint32_t)d[o + 1] << 8 : 0u; };
+    auto f64 = [&](size_t o) { double v = 0; if (o + 8 <= d.size()) memcpy(&v, &d[o], 8); return v; };
+    if (d.size() < 64) return false;
+    const size_t hdr = u32(16), root = u32(hdr + 8);
+    struct Entry { size_t next, child, data, size; std::string name, type; };
+    auto entry = [&](size_t o) {
+        Entry e{u32(o), u32(o + 12), u32(o + 16), u32(o + 20), "", ""};
+        if (o + 120 <= d.size()) { e.name = reinterpret_cast<const char*>(&d[o + 24]); e.type = std::string(reinterpret_cast<const char*>(&d[o + 88]), strnlen(reinterpret_cast<const char*>(&d[o + 88]), 32)); }
+        return e;
+    };
+    size_t layer = 0;
+    for (size_t o = entry(root).child; o && o < d.size(); o = entry(o).next) if (entry(o).type == "Eimg_Layer") { layer = o; break; }
+    if (!layer) return false;
+    const Entry L = entry(layer);
+    const long W = (int32_t)u32(L.data), H = (int32_t)u32(L.data + 4), BWd = (int32_t)u32(L.data + 12), BHt = (int32_t)u32(L.data + 16);
+    const unsigned ptype = u16(L.data + 10);     // u1,u2,u4,u8,s8,u16,s16,u32,s32,f32,f64
+    if (W <= 0 || H <= 0 || BWd <= 0 || BHt <= 0 || ptype < 3 || ptype > 10) return false;
+    const int psize = (ptype == 3 || ptype == 4) ? 1 : (ptype == 5 || ptype == 6) ? 2 : (ptype == 10 ? 8 : 4);
+    size_t dms = 0, mapinfo = 0;
+    for (size_t o = L.child; o && o < d.size(); o = entry(o).next) { const Entry e = entry(o); if (e.type == "Edms_State") dms = e.data; if (e.type == "Eprj_MapInfo") mapinfo = e.data; }
+    if (!dms) return false;
+    const uint32_t nblocks = u32(dms + 14);
+    const size_t table = u32(dms + 18);
+    const long nbx = (W + BWd - 1) / BWd, nby = (H + BHt - 1) / BHt;
+    if ((long)nblocks < nbx * nby) return false;
+    cols = W; rows = H; nodata = -9999.0;
+    values.assign((size_t)W * H, nodata);
+    auto convert = [&](uint32_t bits_lo, const unsigned char* raw) -> double {   // raw: little-endian pixel (uncompressed blocks)
+        (void)bits_lo;
+        switch (ptype) {
+        case 3: return raw[0]; case 4: return (int8_t)raw[0];
+        case 5: return (uint16_t)(raw[0] | raw[1] << 8); case 6: return (int16_t)(raw[0] | raw[1] << 8);
+        case 7: { uint32_t v; memcpy(&v, raw, 4); return v; } case 8: { int32_t v; memcpy(&v, raw, 4); return v; }
+        case 9: { float v; memcpy(&v, raw, 4); return v; } default: { double v; memcpy(&v, raw, 8); return v; }
+        }
+    };
+    std::vector<double> blk((size_t)BWd * BHt);
+    for (long b = 0; b < nbx * nby; ++b) {
+        const size_t rec = table + (size_t)b * 14;
+        const size_t off = u32(rec + 2), size = u32(rec + 6);
+        const unsigned comp = u16(rec + 12);
+        if (off + size > d.size()) return false;
+        const unsigned char* c = &d[off];
+        if (comp == 0) {
+            if (size < blk.size() * psize) return false;
+            for (size_t i = 0; i < blk.size(); ++i) blk[i] = convert(0, c + i * psize);
+        } else {
+            if (psize == 8) return false;                 // compressed f64 is not produced by the tools in use
+            const uint32_t vmin = u32(off); const int32_t runs = (int32_t)u32(off + 4); const uint32_t doff = u32(off + 8); const unsigned nbits = d[off + 12];
+            auto value = [&](const unsigned char* v, size_t i) -> uint32_t {
+                switch (nbits) {
+                case 0: return 0; case 8: return v[i]; case 16: return (uint32_t)v[2 * i] << 8 | v[2 * i + 1];
+                case 32: return (uint32_t)v[4 * i] << 24 | (uint32_t)v[4 * i + 1] << 16 | (uint32_t)v[4 * i + 2] << 8 | v[4 * i + 3];
+                case 1: return (v[i >> 3] >> (i & 7)) & 1; case 2: return (v[i >> 2] >> ((i & 3) * 2)) & 3; case 4: return (v[i >> 1] >> ((i & 1) * 4)) & 15;
+                default: return 0;
+                }
+            };
+            auto store = [&](size_t i, uint32_t raw) {
+                raw += vmin;
+                if (ptype == 9) { float fv; memcpy(&fv, &raw, 4); blk[i] = fv; }
+                else if (ptype == 4) blk[i] = (int8_t)raw; else if (ptype == 6) blk[i] = (int16_t)raw; else if (ptype == 8) blk[i] = (int32_t)raw; else blk[i] = raw;
+            };
+            if (runs == -1) {
+                for (size_t i = 0; i < blk.size(); ++i) store(i, value(c + 13, i));
+            } else {
+                size_t cnt = 13, n = 0;
+                for (int32_t r = 0; r < runs; ++r) {
+                    if (cnt >= size) return false;
+                    const unsigned extra = c[cnt] >> 6;
+                    size_t len = c[cnt] & 0x3f;
+                    for (unsigned j = 0; j < extra; ++j) len = len << 8 | c[cnt + 1 + j];
+                    cnt += 1 + extra;
+                    const uint32_t v = value(c + doff, (size_t)r);
+                    for (size_t j = 0; j < len && n < blk.size(); ++j) store(n++, v);
+                }
+                if (n != blk.size()) return false;
+            }
+        }
+        const long by = b / nbx, bx = b % nbx;
+        for (long y = 0; y < BHt; ++y) for (long x = 0; x < BWd; ++x) {
+            const long gy = by * BHt + y, gx = bx * BWd + x;                    // file rows are north-first
+            if (gy < H && gx < W) values[(size_t)(H - 1 - gy) * W + gx] = blk[(size_t)y * BWd + x];
+        }
+    }
+    cellsize = 1.0; xll = yll = 0.0;
+    if (mapinfo) {          // Eprj_MapInfo: name, upperLeftCenter, lowerRightCenter, pixelSize, units -- each behind {count, ptr}
+        size_t o = mapinfo; o += 8 + u32(o);
+        const double ulx = f64(o + 8); o += 24;
+        const double lry = f64(o + 16); o += 24;
+        cellsize = f64(o + 8);
+        xll = ulx - 0.5 * cellsize; yll = lry - 0.5 * cellsize;
+    }
+    return true;
+}
+
+bool SRaster::readASCII(const std::string& path) {
     std::ifstream f(path);
     if (!f) return false;
     std::string key; double v;
@@ -723,6 +837,16 @@ int hph_model_boundary(void* h, unsigned int i, int* kind, int* def_a, int* def_
     if (auto* g = dynamic_cast<CBoundaryGridded*>(b)) { *kind = 1; *def_a = g->ucValue; *interval = g->dInterval; *length = 0; return 0; }
     return -1;
 }
+// raster reader probe: fills cols/rows/cellsize/xll/yll and returns a malloc'ed south-first array (free with hph_free)
+double* hph_raster_read(const char* path, unsigned long* cols, unsigned long* rows, double* cellsize, double* xll, double* yll) {
+    SRaster r;
+    if (!r.read(path)) return nullptr;
+    *cols = r.cols; *rows = r.rows; *cellsize = r.cellsize; *xll = r.xll; *yll = r.yll;
+    double* out = static_cast<double*>(malloc(r.values.size() * sizeof(double)));
+    memcpy(out, r.values.data(), r.values.size() * sizeof(double));
+    return out;
+}
+void hph_free(void* p) { free(p); }
 int hph_error_count(void) { return static_cast<int>(model::errorLog.size()); }
 const char* hph_error(int i) { return (i >= 0 && i < static_cast<int>(model::errorLog.size())) ? model::errorLog[i].c_str() : ""; }
 double hph_round(double v, int places) { return Util::round(v, static_cast<unsigned char>(places)); }

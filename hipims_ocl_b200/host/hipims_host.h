@@ -67,13 +67,17 @@ class CCSVDataset {
     bool bReady = false;
 };
 
-// ESRI ASCII grid (GDAL-free stand-in for CRasterDataset); rows are stored south-first like the
-// reference's cell arrays (src/Datasets/CRasterDataset.cpp:411 flips on load).
+// GDAL-free stand-in for CRasterDataset: reads ESRI ASCII grids and ERDAS IMAGINE (.img / HFA) single-band
+// rasters (uncompressed and run-length "ESRI GRID" compressed 64x64 blocks -- the reference's test DEM),
+// writes ESRI ASCII grids.  Rows are stored south-first like the reference's cell arrays
+// (src/Datasets/CRasterDataset.cpp:411 flips on load).
 struct SRaster {
     unsigned long cols = 0, rows = 0;
     double xll = 0, yll = 0, cellsize = 1, nodata = -9999;
     std::vector<double> values;
-    bool read(const std::string& path);
+    bool read(const std::string& path);          // by content: "EHFA_HEADER_TAG" -> HFA, else ASCII grid
+    bool readASCII(const std::string& path);
+    bool readHFA(const std::string& path);
     bool write(const std::string& path) const;
 };
 

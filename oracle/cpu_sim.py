@@ -136,9 +136,11 @@ class CpuSim:
             self.prefix = "hpo_f64_" if cfg.precision == "double" else "hpo_f32_"
         elif backend == "ref":
             path = ref_library_path(cfg)
-            if not os.path.exists(path):
-                from . import build_ref
-                build_ref.build_variant(ref_variant(cfg))
+            from . import build_ref
+            if build_ref.reference_available():
+                build_ref.build_variant(ref_variant(cfg))     # no-op when up to date
+            elif not os.path.exists(path):
+                raise RuntimeError("reference library %s missing and /root/reference not available" % path)
             self.lib = _load(path)
             self.prefix = "hpo_ref_"
         else:

@@ -39,7 +39,45 @@ CASES = {
 }
 
 
+def newcastle():
+    """BASELINE.json configs[0]: the reference's own test case (test/newcastle-centre.xml), read through the host
+    mirror's XML/HFA readers, stepped by the reference's kernels: Godunov fp64, friction, rain 70 mm/h + losses
+    12 mm/h, reference launch coverage (Q6: columns 336+ and rows 192+ get no rain)."""
+    import ctypes as C
+    from hipims_ocl_b200 import build as hpbuild, config as hc
+    hpbuild.build_host()
+    lib = C.CDLL(hpbuild.HOST_LIB)
+    lib.hph_model_load.restype = C.c_void_p
+    h = lib.hph_model_load(b"/root/reference/test/newcastle-centre.xml", 1)
+    for fn in ("hph_model_states", "hph_model_bed", "hph_model_manning"):
+        getattr(lib, fn).restype = C.POINTER(C.c_double); getattr(lib, fn).argtypes = [C.c_void_p]
+    rows, cols = 195, 342
+    st = np.ctypeslib.as_array(lib.hph_model_states(h), shape=(rows, cols, 4)).copy()
+    bed = np.ctypeslib.as_array(lib.hph_model_bed(h), shape=(rows, cols)).copy()
+    man = np.ctypeslib.as_array(lib.hph_model_manning(h), shape=(rows, cols)).copy()
+    cfg = make_cfg("godunov", "double", rows, cols, delta=2.0, end_time=7200.0)
+    sim = cpu_sim.CpuSim("ref", cfg)
+    sim.upload(st, bed, man)
+    sim.add_uniform(hc.UNIFORM_LOSS_RATE, [0.0, 1.0e8], [12.0, 12.0])
+    sim.add_uniform(hc.UNIFORM_RAIN_INTENSITY, [0.0, 3600.0, 7200.0, 10800.0], [70.0, 70.0, 0.0, 0.0])
+    sim.set_target(7200.0)
+    outs = {}
+    for it in (100, 600):
+        sim.iterate(it - (0 if it == 100 else 100))
+        outs[it] = (sim.download(), sim.stats())
+    assert np.array_equal(np.rint(bed * 1e4) / 1e4, bed)
+    np.savez_compressed(os.path.join(HERE, "newcastle_centre.npz"), bed_e4=np.rint(bed * 1e4).astype(np.int32),
+                        out_100=outs[100][0], out_600=outs[600][0],
+                        stats_100=np.array([outs[100][1][k] for k in sorted(outs[100][1])]),
+                        stats_600=np.array([outs[600][1][k] for k in sorted(outs[600][1])]),
+                        stats_keys=np.array(sorted(outs[100][1])))
+    print("wrote newcastle_centre.npz (t = %.4f s after 600 iterations, %d wet cells)" % (
+        outs[600][1]["time"], int(((outs[600][0][..., 0] - bed) > 1e-10).sum())))
+
+
 def main():
+    if os.path.exists("/root/reference/test/newcastle-centre.xml"):
+        newcastle()
     for name, (scheme, precision, scen, bdy, rows, cols, iters, extra) in CASES.items():
         cfg = make_cfg(scheme, precision, rows, cols, **extra)
         bed, st, man = scenario(scen, rows, cols, dtype_of(precision))

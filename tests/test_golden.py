@@ -15,7 +15,8 @@ from oracle import cpu_sim
 from tests.helpers import add_standard_boundaries, make_cfg
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-FILES = sorted(glob.glob(os.path.join(HERE, "golden", "*.npz")))
+FILES = sorted(f for f in glob.glob(os.path.join(HERE, "golden", "*.npz")) if "newcastle" not in f)
+NEWCASTLE = os.path.join(HERE, "golden", "newcastle_centre.npz")
 TOL = {"double": 1e-9, "single": 1e-4}
 
 
@@ -77,4 +78,59 @@ def test_cuda_reproduces_reference_golden(path, options):
         assert int(((cur[..., 0] - z["bed"]) > 1e-10).sum()) == int(((want[..., 0] - z["bed"]) > 1e-10).sum())
     assert np.isfinite(cur).all()
     sim.close()
+    ex.close()
+
+
+# ---- BASELINE.json configs[0]: the reference's own test case on its own DEM -----------------------------
+def newcastle_sim(make):
+    from hipims_ocl_b200 import config as hc
+    z = np.load(NEWCASTLE)
+    bed = z["bed_e4"].astype(np.float64) / 1e4       # the DEM after the reference's 4-decimal ingestion
+    rows, cols = bed.shape
+    cfg = make_cfg("godunov", "double", rows, cols, delta=2.0, end_time=7200.0)
+    st = np.zeros((rows, cols, 4))
+    st[..., 0] = bed
+    st[..., 1] = bed
+    sim = make(cfg)
+    sim.upload(st, bed, np.full((rows, cols), 0.03))
+    sim.add_uniform(hc.UNIFORM_LOSS_RATE, [0.0, 1.0e8], [12.0, 12.0])
+    sim.add_uniform(hc.UNIFORM_RAIN_INTENSITY, [0.0, 3600.0, 7200.0, 10800.0], [70.0, 70.0, 0.0, 0.0])
+    sim.set_target(7200.0)
+    return z, bed, sim
+
+
+def test_oracle_reproduces_newcastle_centre():
+    z, bed, sim = newcastle_sim(lambda cfg: cpu_sim.CpuSim("oracle", cfg))
+    keys = [str(k) for k in z["stats_keys"]]
+    sim.iterate(100)
+    np.testing.assert_array_equal(sim.download(), z["out_100"])
+    assert [sim.stats()[k] for k in keys] == list(z["stats_100"])
+    sim.iterate(500)
+    np.testing.assert_array_equal(sim.download(), z["out_600"])
+    assert [sim.stats()[k] for k in keys] == list(z["stats_600"])
+    # reference launch coverage: columns 336..340 never receive rain, only inflow from their neighbours
+    depth = z["out_600"][..., 0] - bed
+    assert depth[1:192, 337:341].mean() < 0.5 * depth[1:192, 300:336].mean()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("options", [hx.OPT_STRICT_FP, 0], ids=["strict", "fast"])
+def test_cuda_reproduces_newcastle_centre(options):
+    ex = hx.Executor(0)
+    z, bed, sim = newcastle_sim(lambda cfg: hx.CudaScheme(ex, cfg, options=options))
+    keys = [str(k) for k in z["stats_keys"]]
+    sim.iterate(100)
+    got, want = sim.download(), z["out_100"]
+    st = dict(zip(keys, z["stats_100"]))
+    assert sim.stats()["batch_successful"] == st["batch_successful"] and abs(sim.stats()["time"] - st["time"]) < 1e-9
+    assert np.abs(got[..., 0] - want[..., 0]).max() <= 1e-9
+    assert int(((got[..., 0] - bed) > 1e-10).sum()) == int(((want[..., 0] - bed) > 1e-10).sum())
+    sim.iterate(500)                     # thin-film drift stays bounded (Parity)
+    got, want = sim.download(), z["out_600"]
+    st = dict(zip(keys, z["stats_600"]))
+    assert sim.stats()["batch_successful"] == st["batch_successful"]
+    assert abs(sim.stats()["time"] - st["time"]) < 1e-6
+    assert np.abs(got[..., 0] - want[..., 0]).max() <= 1e-5
+    vol_g, vol_w = (got[..., 0] - bed).sum(), (want[..., 0] - bed).sum()
+    assert abs(vol_g - vol_w) <= 1e-6 * vol_w
     ex.close()

@@ -200,10 +200,30 @@ def test_bad_configurations_report_through_doError(host, model_dir, tmp_path):
     bad.write_text(text.replace("</simulation>", ""))
     assert not host.hph_model_load(str(bad).encode(), 1)
     assert "Cannot load configuration" in host.hph_error(host.hph_error_count() - 1).decode()
-    ref_cfg = "/root/reference/test/newcastle-centre.xml"
-    if os.path.exists(ref_cfg):      # the reference's own file parses; its HFA raster needs GDAL
-        assert not host.hph_model_load(ref_cfg.encode(), 1)
-        assert "structure raster" in host.hph_error(host.hph_error_count() - 1).decode()
+
+
+REF_CFG = "/root/reference/test/newcastle-centre.xml"
+
+
+@pytest.mark.skipif(not os.path.exists(REF_CFG), reason="reference tree not present")
+def test_reference_newcastle_configuration_loads_unmodified(host):
+    """The reference's own test configuration (executor "OpenCL", ERDAS IMAGINE DEM with run-length
+    compressed blocks) is read as it is: BASELINE.json configs[0]."""
+    h = host.hph_model_load(REF_CFG.encode(), 1)
+    assert h, [host.hph_error(i) for i in range(host.hph_error_count())]
+    i = info(host, h)
+    assert (i["cols"], i["rows"], i["resolution"], i["duration"], i["output_frequency"]) == (342, 195, 2.0, 7200.0, 600.0)
+    assert (i["precision"], i["scheme"], i["boundaries"]) == (1, 0, 2)
+    st, bed, man = arrays(host, h, 195, 342)
+    # the .img carries its own statistics (Esta_Statistics): min 43.4375, max 81.7375, mean 56.5676
+    assert bed.min() == 43.4375 and bed.max() == 81.7375 and abs(bed.mean() - 56.567615) < 1e-4
+    np.testing.assert_array_equal(bed, sc.round4(bed))
+    np.testing.assert_array_equal(st[..., 0], bed)
+    assert (man == 0.03).all()
+    b = boundaries(host, h, 2)
+    assert [x["def_a"] for x in b] == [hc.UNIFORM_LOSS_RATE, hc.UNIFORM_RAIN_INTENSITY]
+    assert b[1]["series"][:4] == [0.0, 70.0, 3600.0, 70.0]
+    host.hph_model_destroy(C.c_void_p(h))
 
 
 @pytest.mark.gpu

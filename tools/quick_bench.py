@@ -19,6 +19,7 @@ for name in names:
     bed, st, man = bench.make_inputs(w, cfg.rows, cfg.cols, dtype)
     sim = hx.CudaScheme(ex, cfg, options=options)
     sim.upload(st, bed, man)
+    bench.attach_boundaries(sim, w, cfg.cols, cfg.rows)
     sim.set_target(1e7)
     sim.iterate(10)
     best = 0.0

@@ -62,12 +62,15 @@ def newcastle():
     sim.add_uniform(hc.UNIFORM_RAIN_INTENSITY, [0.0, 3600.0, 7200.0, 10800.0], [70.0, 70.0, 0.0, 0.0])
     sim.set_target(7200.0)
     outs = {}
-    for it in (100, 600):
-        sim.iterate(it - (0 if it == 100 else 100))
+    done = 0
+    for it in (40, 100, 600):
+        sim.iterate(it - done)
+        done = it
         outs[it] = (sim.download(), sim.stats())
     assert np.array_equal(np.rint(bed * 1e4) / 1e4, bed)
     np.savez_compressed(os.path.join(HERE, "newcastle_centre.npz"), bed_e4=np.rint(bed * 1e4).astype(np.int32),
-                        out_100=outs[100][0], out_600=outs[600][0],
+                        out_40=outs[40][0], out_100=outs[100][0], out_600=outs[600][0],
+                        stats_40=np.array([outs[40][1][k] for k in sorted(outs[40][1])]),
                         stats_100=np.array([outs[100][1][k] for k in sorted(outs[100][1])]),
                         stats_600=np.array([outs[600][1][k] for k in sorted(outs[600][1])]),
                         stats_keys=np.array(sorted(outs[100][1])))

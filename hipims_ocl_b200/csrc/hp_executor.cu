@@ -82,8 +82,9 @@ struct hp_scheme {
     // graphs: [0] one pair of iterations (A->B, B->A), [1] kGraphPairs pairs
     cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};
     int graph_launches[2] = {0, 0};
-    bool use_tma = false;
+    bool use_tma = false, use_march = false;
     hp::TmaMapsPOD maps_a{}, maps_b{};   // descriptors with buffer A / buffer B as the source
+    hp::TmaMaps6POD march_a{}, march_b{};
     hp::Comm* comm = nullptr;
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t ev_edges = nullptr, ev_halo = nullptr;
@@ -146,6 +147,8 @@ int enqueue_iteration(hp_scheme* s, bool alt, int* launched) {
         else a.reduce_mode = alt ? hp::kReduceDst : hp::kReduceSrc;   // Q1: always buffer A
     }
     auto step = [&](const hp::StepArgs& args) {
+        if (s->use_march) return s->K->step_march(static_cast<int>(s->cfg.scheme), rb, args, alt ? &s->march_b : &s->march_a,
+                                                  s->ex->prop.multiProcessorCount, st);
         if (s->use_tma) return s->K->step_tma(static_cast<int>(s->cfg.scheme), rb, args, alt ? &s->maps_b : &s->maps_a,
                                               s->ex->prop.multiProcessorCount, st);
         return s->K->step(static_cast<int>(s->cfg.scheme), rb, args, st);
@@ -203,7 +206,7 @@ int build_graph(hp_scheme* s, int slot, int pairs) {
 // zero-filled device allocation; the fill is ordered on the scheme's own stream (a legacy
 // default-stream cudaMemset is NOT ordered against a non-blocking stream)
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
-int encode_plane_map(void* out128, void* plane, const hp::Grid& g, size_t rb, int halo) {
+int encode_plane_map(void* out128, void* plane, const hp::Grid& g, size_t rb, int box_w, int box_h) {
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -217,7 +220,7 @@ int encode_plane_map(void* out128, void* plane, const hp::Grid& g, size_t rb, in
     }
     const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(g.cols), static_cast<cuuint64_t>(g.rows)};
     const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(g.pitch) * rb};
-    const cuuint32_t box[2] = {static_cast<cuuint32_t>(hp::tma_box_w(static_cast<int>(rb), halo)), static_cast<cuuint32_t>(hp::tma_box_h(halo))};
+    const cuuint32_t box[2] = {static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(box_h)};
     const cuuint32_t estride[2] = {1, 1};
     CUtensorMap tm;
     const CUresult r = encode(&tm, rb == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, plane, gdim, gstride,
@@ -234,11 +237,24 @@ int build_tma_maps(hp_scheme* s) {
     int rc;
     hp::Planes* bufs[2] = {&s->A, &s->B};
     hp::TmaMapsPOD* maps[2] = {&s->maps_a, &s->maps_b};
+    const int rbi = static_cast<int>(s->rb);
+    if (s->use_march) {
+        // marching kernels: single-row boxes of six planes
+        hp::TmaMaps6POD* m6[2] = {&s->march_a, &s->march_b};
+        const int w = hp::march_box_w(rbi, halo);
+        for (int b = 0; b < 2; ++b) {
+            void* planes[6] = {bufs[b]->eta, bufs[b]->qx, bufs[b]->qy, s->bed, bufs[b]->emax, s->manning};
+            for (int p = 0; p < 6; ++p)
+                if ((rc = encode_plane_map(m6[b]->bytes[p], planes[p], s->grid, s->rb, w, 1))) return rc;
+        }
+        return HP_OK;
+    }
+    const int w = hp::tma_box_w(rbi, halo), h = hp::tma_box_h(halo);
     for (int b = 0; b < 2; ++b) {
-        if ((rc = encode_plane_map(maps[b]->bytes[0], bufs[b]->eta, s->grid, s->rb, halo))) return rc;
-        if ((rc = encode_plane_map(maps[b]->bytes[1], bufs[b]->qx, s->grid, s->rb, halo))) return rc;
-        if ((rc = encode_plane_map(maps[b]->bytes[2], bufs[b]->qy, s->grid, s->rb, halo))) return rc;
-        if ((rc = encode_plane_map(maps[b]->bytes[3], s->bed, s->grid, s->rb, halo))) return rc;
+        if ((rc = encode_plane_map(maps[b]->bytes[0], bufs[b]->eta, s->grid, s->rb, w, h))) return rc;
+        if ((rc = encode_plane_map(maps[b]->bytes[1], bufs[b]->qx, s->grid, s->rb, w, h))) return rc;
+        if ((rc = encode_plane_map(maps[b]->bytes[2], bufs[b]->qy, s->grid, s->rb, w, h))) return rc;
+        if ((rc = encode_plane_map(maps[b]->bytes[3], s->bed, s->grid, s->rb, w, h))) return rc;
     }
     return HP_OK;
 }
@@ -444,6 +460,8 @@ int hp_scheme_create(hp_executor* ex, const hp_scheme_config* cfg, hp_scheme** o
         // TMA-staged kernels: the fast flavour's Godunov step (others use the plain-load kernels)
         s->use_tma = s->K->step_tma != nullptr && !(cfg->options & HP_OPT_NO_TMA) &&
                      (cfg->scheme == HP_SCHEME_GODUNOV || cfg->scheme == HP_SCHEME_MUSCL_HANCOCK);
+        s->use_march = s->use_tma && s->K->step_march != nullptr && !(cfg->options & HP_OPT_TILE_KERNELS) &&
+                       cfg->scheme == HP_SCHEME_MUSCL_HANCOCK;
         if (s->use_tma && (rc = build_tma_maps(s))) break;
     } while (0);
     if (rc != HP_OK) { hp_scheme_destroy(s); return rc; }

@@ -402,6 +402,7 @@ template <class R> __global__ void __launch_bounds__(256) copy_plane_rows_kernel
 
 #ifndef HP_FLAVOUR_STRICT
 #include "hp_fast_kernels.cuh"
+#include "hp_march_kernels.cuh"
 #endif
 
 namespace HP_NS {
@@ -417,6 +418,12 @@ static int launch_step_tma(int scheme, int real_bytes, const StepArgs& a, const 
     const TmaMaps& m = *reinterpret_cast<const TmaMaps*>(maps);
     if (scheme == 0) return real_bytes == 8 ? launch_godunov_tma<double>(a, m, sm_count, st) : launch_godunov_tma<float>(a, m, sm_count, st);
     if (scheme == 1) return real_bytes == 8 ? launch_mh_tma<double>(a, m, sm_count, st) : launch_mh_tma<float>(a, m, sm_count, st);
+    return -1;
+}
+static_assert(sizeof(TmaMaps6) == sizeof(hp::TmaMaps6POD), "descriptor block layout");
+static int launch_step_march(int scheme, int real_bytes, const StepArgs& a, const hp::TmaMaps6POD* maps, int sm_count, cudaStream_t st) {
+    const TmaMaps6& m = *reinterpret_cast<const TmaMaps6*>(maps);
+    if (scheme == 1) return real_bytes == 8 ? launch_mh_march<double>(a, m, sm_count, st) : launch_mh_march<float>(a, m, sm_count, st);
     return -1;
 }
 #endif
@@ -509,9 +516,9 @@ static int launch_copy_plane_rows(int real_bytes, const void* dense, void* plane
 
 static const hp::KernelTable g_table = {
 #ifndef HP_FLAVOUR_STRICT
-    launch_step_tma,
+    launch_step_tma, launch_step_march,
 #else
-    nullptr,
+    nullptr, nullptr,
 #endif
     launch_step, launch_reduce_only, launch_advance, launch_update_timestep, launch_bdy_uniform, launch_bdy_gridded,
     launch_bdy_cell, launch_aos_to_soa, launch_soa_to_aos, launch_copy_plane_rows,

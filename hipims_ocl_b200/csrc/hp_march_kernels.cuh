@@ -1,0 +1,359 @@
+// hp_march_kernels.cuh -- "marching" step kernels: one warp owns a strip of 32 columns and walks it
+// row by row, keeping everything that is reused between consecutive rows in registers.
+//
+// Why: the tile kernels (hp_fast_kernels.cuh) are bound by instruction issue, not by HBM
+// (profiles/r01_*): per cell-update only ~36 % of their instructions are fp64 arithmetic, the rest
+// is index arithmetic, shared-memory traffic for predictor / flux planes and CTA barriers between
+// the phases.  Here
+//   * raw rows arrive through TMA (cp.async.bulk.tensor.2d + mbarrier) into a per-warp ring of
+//     four rows x six planes, one row ahead of the arithmetic; every plane is read from HBM once;
+//   * the y-direction never leaves the thread: the predictor of the row below, the flux through the
+//     southern face and its owner terms are carried in registers from the previous row;
+//   * the x-direction is exchanged between neighbouring lanes with warp shuffles: the east-side
+//     face estimate goes one lane up, the solved face (flux, reconstructed bed, depth) comes back
+//     one lane down -- every face is still solved exactly once;
+//   * there is no CTA-level barrier and no shared-memory store in the loop: warps are autonomous,
+//     a CTA is four warps on four adjacent strips so that the halo columns hit in L1/L2;
+//   * work is split into equal runs of (strip group, row) units over a persistent grid that
+//     exactly fills the SMs, so all CTAs finish together (no tail wave).
+// Lanes at the strip edge only feed their neighbours (halo lanes): 28 of 32 lanes update cells
+// for MUSCL-Hancock (halo 2), 30 of 32 for Godunov fp64 (halo 1).
+// The per-cell arithmetic is the one of the tile kernels (same helper functions), so results are
+// identical to them to the last bit where the operation order is the same.
+#pragma once
+
+#include "hp_fast_kernels.cuh"
+
+namespace HP_NS {
+
+struct TmaMaps6 { CUtensorMap eta, qx, qy, zb, emax, n; };
+
+template <class R, int HALO> struct March {
+    static constexpr int NW = hp::kMarchWarps, RR = 4, NP = 6;
+    static constexpr int A16 = 16 / int(sizeof(R));                       // elements per 16 bytes
+    static constexpr int USE = hp::march_use(int(sizeof(R)), HALO);       // cells updated per warp row
+    static constexpr int PADL = ((-HALO) % A16 + A16) % A16;              // box starts 16-byte aligned
+    static constexpr int BW = hp::march_box_w(int(sizeof(R)), HALO);
+    static constexpr int PLANE = (BW * int(sizeof(R)) + 127) / 128 * 128; // bytes between planes of one ring row
+    static constexpr int SLOT = NP * PLANE;                               // one ring row
+    static constexpr int WARP_BYTES = RR * SLOT;
+    static constexpr int SMEM_BYTES = NW * WARP_BYTES + NW * RR * 8;
+    static constexpr int P_ETA = 0, P_QX = 1, P_QY = 2, P_ZB = 3, P_EMAX = 4, P_N = 5;
+    static_assert((USE % A16) == 0, "strip starts must keep the TMA box 16-byte aligned");
+    static_assert(BW >= 32 + PADL && (BW * sizeof(R)) % 16 == 0, "box");
+};
+
+// One face in the normal frame, solved once for both cells: core flux (see face_core_flux), the
+// common reconstructed bed, both reconstructed depths and the stop-counter increments of the two
+// owners (CLSchemeGodunov.clc:83-137 / CLSchemeMUSCLHancock.clc:1172-1204; they can only be
+// non-zero at a wet/dry front).  qOwnL / qOwnR: the owning CELLS' discharge normal to the face.
+template <class R> struct FaceOut { R m, n, t, zmax, hL, hR; int stopL, stopR; };
+
+template <class R>
+__device__ __forceinline__ void face_solve(const Params<R>& k, R etaL, R zL, R unL, R utL, R aL_cached, R etaR, R zR, R unR, R utR,
+                                           R aR_cached, const bool cached, R qOwnL, R qOwnR, FaceOut<R>& o) {
+    const R hg = R(0.5) * k.g;
+    const R zmax = zL > zR ? zL : zR;
+    const R hL = (etaL - zmax > R(0)) ? (etaL - zmax) : R(0);
+    const R hR = (etaR - zmax > R(0)) ? (etaR - zmax) : R(0);
+    o.zmax = zmax; o.hL = hL; o.hR = hR; o.stopL = 0; o.stopR = 0;
+    if (hL <= k.eps || hR <= k.eps) {
+        int both = 0;
+        if (hR <= k.eps && unL < R(0)) ++both;
+        if (hL <= k.eps && unR > R(0)) ++both;
+        o.stopL = both + ((hL <= k.eps && qOwnL > R(0)) ? 1 : 0);
+        o.stopR = both + ((hR <= k.eps && qOwnR < R(0)) ? 1 : 0);
+    }
+    const bool dryL = hL < k.eps, dryR = hR < k.eps;
+    if (dryL && dryR) {
+        const R hm = R(0.5) * (hL + hR);
+        o.m = R(0); o.n = hg * hm * hm; o.t = R(0);
+        return;
+    }
+    if (dryL) { unL = R(0); utL = R(0); }
+    if (dryR) { unR = R(0); utR = R(0); }
+    const R aL = (cached && zmax == zL) ? aL_cached : fm_sqrt(k.g * hL);
+    const R aR = (cached && zmax == zR) ? aR_cached : fm_sqrt(k.g * hR);
+    const R qnL = hL * unL, qnR = hR * unR;
+    const R as = hp_abs(R(0.5) * (aL + aR) + R(0.25) * (unL - unR));
+    const R us = R(0.5) * (unL + unR) + aL - aR;
+    const R sL = dryL ? unR - 2 * aR : fm_min(unL - aL, us - as);
+    const R sR = dryR ? unL + 2 * aL : fm_max(unR + aR, us + as);
+    const R FLn = unL * qnL + hg * hL * hL, FRn = unR * qnR + hg * hR * hR;
+    if (sL >= R(0)) { o.m = qnL; o.n = FLn; o.t = qnL * utL; return; }
+    if (!(sR >= R(0))) { o.m = qnR; o.n = FRn; o.t = qnR * utR; return; }
+    const R inv = fm_rcp(sR - sL);
+    const R ss = sL * sR;
+    const R f1 = (sR * qnL - sL * qnR + ss * (hR - hL)) * inv;
+    const R f2 = (sR * FLn - sL * FRn + ss * (qnR - qnL)) * inv;
+    o.m = f1; o.n = f2; o.t = f1 * (f1 >= R(0) ? utL : utR);
+}
+
+template <class R> __device__ __forceinline__ R shfl_up1(R v) { return __shfl_up_sync(0xffffffffu, v, 1); }
+template <class R> __device__ __forceinline__ R shfl_dn1(R v) { return __shfl_down_sync(0xffffffffu, v, 1); }
+
+// The part of the launch every marching kernel shares: per-warp ring, barriers, work split.
+template <class T> struct MarchCtx {
+    unsigned char* ring;
+    uint32_t ring_u, bar_u, ph;
+    int lane, warp;
+};
+
+// =============================================================================================
+// MUSCL-Hancock, predictor + corrector fused, marching.
+// =============================================================================================
+template <class R>
+__global__ void __launch_bounds__(March<R, 2>::NW * 32, sizeof(R) == 8 ? 4 : 6)
+mh_step_march(const StepArgs a, const __grid_constant__ TmaMaps6 maps) {
+    using T = March<R, 2>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* const ring = smem_raw + warp * T::WARP_BYTES;
+    const uint32_t ring_u = smem_u32(ring);
+    const uint32_t bar_u = smem_u32(smem_raw + T::NW * T::WARP_BYTES) + warp * T::RR * 8;
+    if (lane == 0) {
+#pragma unroll
+        for (int r = 0; r < T::RR; ++r) mbar_init(bar_u + 8 * r, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+
+    const Params<R> k = make_params<R>(a.params);
+    const Grid g = a.grid;
+    const R dt = read_timestep<R>(a.clock);
+    const R inv_delta = fm_rcp(k.delta);
+    const R hg = R(0.5) * k.g, half = R(0.5);
+    const MutView<R> d(a.dst);
+    const bool stepping = dt > R(0);
+
+    const int nrows = a.y1 - a.y0;
+    const int nstrips = (g.cols + T::USE - 1) / T::USE;
+    const int ngroups = (nstrips + T::NW - 1) / T::NW;
+    const long long units = static_cast<long long>(ngroups) * nrows;
+    long long u = units * blockIdx.x / gridDim.x;
+    const long long u1 = units * (blockIdx.x + 1) / gridDim.x;
+
+    // per-lane byte offsets of the own column and its clamped x-neighbours inside a plane row
+    const int lc = (lane + T::PADL) * int(sizeof(R));
+    const int lw = (lane > 0 ? lane - 1 + T::PADL : T::PADL) * int(sizeof(R));
+    const int le = (lane < 31 ? lane + 1 + T::PADL : 31 + T::PADL) * int(sizeof(R));
+    auto ld = [&](int row_off, int plane, int col_off) -> R {
+        return *reinterpret_cast<const R*>(ring + row_off + plane * T::PLANE + col_off);
+    };
+    auto flags_of = [&](R em) -> int { return (em <= R(-9998.0) ? 1 : 0) | (em < k.eps ? 2 : 0); };
+
+    R ws = R(0);
+    uint32_t ph = 0;
+
+    while (u < u1) {
+        const int grp = static_cast<int>(u / nrows);
+        const int ya = a.y0 + static_cast<int>(u - static_cast<long long>(grp) * nrows);
+        const long long gend = static_cast<long long>(grp + 1) * nrows;
+        const int yb = ya + static_cast<int>((u1 < gend ? u1 : gend) - u);
+        u += yb - ya;
+        const int strip = grp * T::NW + warp;
+        if (strip >= nstrips) continue;
+
+        const int X0 = strip * T::USE - 2;               // column of lane 0
+        const int x = X0 + lane;
+        const int rs = ya - 2;                            // first raw row of this run
+        const int J = yb - ya + 2;                        // raw rows 0 .. J+1, predictor rows 1 .. J
+        auto issue_row = [&](int j) {
+            const uint32_t bar = bar_u + 8 * (j & (T::RR - 1));
+            const uint32_t dst = ring_u + (j & (T::RR - 1)) * T::SLOT;
+            mbar_expect_tx(bar, uint32_t(T::NP * T::BW * sizeof(R)));
+            tma_load_2d(dst + T::P_ETA * T::PLANE, &maps.eta, X0 - T::PADL, rs + j, bar);
+            tma_load_2d(dst + T::P_QX * T::PLANE, &maps.qx, X0 - T::PADL, rs + j, bar);
+            tma_load_2d(dst + T::P_QY * T::PLANE, &maps.qy, X0 - T::PADL, rs + j, bar);
+            tma_load_2d(dst + T::P_ZB * T::PLANE, &maps.zb, X0 - T::PADL, rs + j, bar);
+            tma_load_2d(dst + T::P_EMAX * T::PLANE, &maps.emax, X0 - T::PADL, rs + j, bar);
+            tma_load_2d(dst + T::P_N * T::PLANE, &maps.n, X0 - T::PADL, rs + j, bar);
+        };
+        auto wait_row = [&](int j) {
+            const int s = j & (T::RR - 1);
+            mbar_wait(bar_u + 8 * s, (ph >> s) & 1u);
+            ph ^= 1u << s;
+        };
+        // the previous run's rows are all consumed; order its generic reads before the async writes
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < T::RR; ++j) issue_row(j);      // J + 2 >= 5 rows always exist
+        }
+        wait_row(0);
+        wait_row(1);
+
+        // ---- state carried from row to row (registers) -------------------------------------------
+        int f_m2 = 0, f_m1 = flags_of(ld(0 * T::SLOT, T::P_EMAX, lc)), f_c = flags_of(ld(1 * T::SLOT, T::P_EMAX, lc));
+        int f_ew_prev = 0;                                   // bit1 flags of the x-neighbours of the previous row: W | E<<2
+        R pe = R(0), pqx = R(0), pqy = R(0), psxE = R(0), psxH = R(0), psxQx = R(0), psxQy = R(0);
+        R psyE = R(0), psyH = R(0), psyQx = R(0), psyQy = R(0), pzb = R(0);
+        R sM = R(0), sN = R(0), sT = R(0), sZ = R(0), sH = R(0);   // southern face of the previous row
+        int sStop = 0;
+
+        for (int j = 1; j <= J; ++j) {
+            const int y = rs + j, gy = y + g.gy0;
+            const int o_m = ((j - 1) & (T::RR - 1)) * T::SLOT, o_c = (j & (T::RR - 1)) * T::SLOT,
+                      o_p = ((j + 1) & (T::RR - 1)) * T::SLOT;
+            wait_row(j + 1);
+            const int f_p = flags_of(ld(o_p, T::P_EMAX, lc));
+            const int f_w = __shfl_up_sync(0xffffffffu, f_c, 1), f_e = __shfl_down_sync(0xffffffffu, f_c, 1);
+
+            // ---- predictor of row y (CLSchemeMUSCLHancock.clc:301-382) ---------------------------
+            const R eta = ld(o_c, T::P_ETA, lc), qx = ld(o_c, T::P_QX, lc), qy = ld(o_c, T::P_QY, lc), zb = ld(o_c, T::P_ZB, lc);
+            R ce = eta, cqx = qx, cqy = qy;
+            R sxE = R(0), sxH = R(0), sxQx = R(0), sxQy = R(0), syE = R(0), syH = R(0), syQx = R(0), syQy = R(0);
+            {
+                const bool valid = stepping && x >= 1 && x <= g.cols - 2 && gy >= 1 && gy <= g.grows - 2 && y >= 1 && y <= g.rows - 2;
+                const R h = eta - zb;
+                if (valid && !(h < R(1E-5)) && !((f_p | f_e | f_m1 | f_w) & 1)) {
+                    const R etaE = ld(o_c, T::P_ETA, le), etaW = ld(o_c, T::P_ETA, lw), etaN = ld(o_p, T::P_ETA, lc), etaS = ld(o_m, T::P_ETA, lc);
+                    const R hE = etaE - ld(o_c, T::P_ZB, le), hW = etaW - ld(o_c, T::P_ZB, lw);
+                    const R hN = etaN - ld(o_p, T::P_ZB, lc), hS = etaS - ld(o_m, T::P_ZB, lc);
+                    if (!(hW < k.eps || hE < k.eps)) {
+                        sxE = minmod(eta - etaW, etaE - eta); sxH = minmod(h - hW, hE - h);
+                        sxQx = minmod(qx - ld(o_c, T::P_QX, lw), ld(o_c, T::P_QX, le) - qx);
+                        sxQy = minmod(qy - ld(o_c, T::P_QY, lw), ld(o_c, T::P_QY, le) - qy);
+                    }
+                    if (!(hS < k.eps || hN < k.eps)) {
+                        syE = minmod(eta - etaS, etaN - eta); syH = minmod(h - hS, hN - h);
+                        syQx = minmod(qx - ld(o_m, T::P_QX, lc), ld(o_p, T::P_QX, lc) - qx);
+                        syQy = minmod(qy - ld(o_m, T::P_QY, lc), ld(o_p, T::P_QY, lc) - qy);
+                    }
+                    const R hEf = h + half * sxH, hWf = h - half * sxH, hNf = h + half * syH, hSf = h - half * syH;
+                    const R qxE = qx + half * sxQx, qxW = qx - half * sxQx, qyE = qy + half * sxQy, qyW = qy - half * sxQy;
+                    const R qxN = qx + half * syQx, qxS = qx - half * syQx, qyN = qy + half * syQy, qyS = qy - half * syQy;
+                    const R uE = hEf < k.eps ? R(0) : qxE * fm_rcp(hEf), uW = hWf < k.eps ? R(0) : qxW * fm_rcp(hWf);
+                    const R vN = hNf < k.eps ? R(0) : qyN * fm_rcp(hNf), vS = hSf < k.eps ? R(0) : qyS * fm_rcp(hSf);
+                    R dEta = ((qxE - qxW) + (qyN - qyS)) * inv_delta;
+                    R dQx = (uE * qxE - uW * qxW + vN * qxN - vS * qxS + hg * sxE * (hEf + hWf)) * inv_delta;
+                    R dQy = (uE * qyE - uW * qyW + vN * qyN - vS * qyS + hg * syE * (hNf + hSf)) * inv_delta;
+                    dEta = fm_chop(dEta, k.eps); dQx = fm_chop(dQx, k.eps); dQy = fm_chop(dQy, k.eps);
+                    ce = eta - half * dt * dEta; cqx = qx - half * dt * dQx; cqy = qy - half * dt * dQy;
+                }
+            }
+
+            if (stepping && j >= 2) {
+                // ---- face between rows y-1 (left) and y (right); normal = y ----------------------
+                FaceOut<R> fy;
+                {
+                    const R etaL = pe + half * psyE, hfL = (pe - pzb) + half * psyH;
+                    const R qxL = pqx + half * psyQx, qyL = pqy + half * psyQy;
+                    const R etaR = ce - half * syE, hfR = (ce - zb) - half * syH;
+                    const R qxR = cqx - half * syQx, qyR = cqy - half * syQy;
+                    const R rL = hfL <= k.eps ? R(0) : fm_rcp(hfL), rR = hfR <= k.eps ? R(0) : fm_rcp(hfR);
+                    face_solve<R>(k, etaL, etaL - hfL, qyL * rL, qxL * rL, R(0), etaR, etaR - hfR, qyR * rR, qxR * rR, R(0), false,
+                                  ld(o_m, T::P_QY, lc), qy, fy);
+                }
+                if (j >= 3) {
+                    // ---- west face of row y-1: the east-side estimate of lane-1 against the own west side
+                    const R xe_eta = pe + half * psxE, xe_h = (pe - pzb) + half * psxH;
+                    const R xe_r = xe_h <= k.eps ? R(0) : fm_rcp(xe_h);
+                    const R xe_u = (pqx + half * psxQx) * xe_r, xe_v = (pqy + half * psxQy) * xe_r;
+                    const R etaL = shfl_up1(xe_eta), hfL = shfl_up1(xe_h), uL = shfl_up1(xe_u), vL = shfl_up1(xe_v);
+                    const R etaR = pe - half * psxE, hfR = (pe - pzb) - half * psxH;
+                    const R rR = hfR <= k.eps ? R(0) : fm_rcp(hfR);
+                    const R uR = (pqx - half * psxQx) * rR, vR = (pqy - half * psxQy) * rR;
+                    const R c_qx = ld(o_m, T::P_QX, lc);
+                    FaceOut<R> fx;
+                    face_solve<R>(k, etaL, etaL - hfL, uL, vL, R(0), etaR, etaR - hfR, uR, vR, R(0), false, ld(o_m, T::P_QX, lw), c_qx, fx);
+                    // the east face comes back from lane+1
+                    const R eM = shfl_dn1(fx.m), eN = shfl_dn1(fx.n), eT = shfl_dn1(fx.t), eZ = shfl_dn1(fx.zmax), eH = shfl_dn1(fx.hR);
+                    const int eStop = __shfl_down_sync(0xffffffffu, fx.stopL, 1);
+
+                    // ---- corrector of row y-1 (CLSchemeMUSCLHancock.clc:596-800) -----------------
+                    const int yc = y - 1, gyc = gy - 1;
+                    Cell<R> c{ld(o_m, T::P_ETA, lc), ld(o_m, T::P_EMAX, lc), c_qx, ld(o_m, T::P_QY, lc)};
+                    const bool interior = x >= 2 && x <= g.cols - 3 && gyc >= 2 && gyc <= g.grows - 3;   // ring of two is frozen
+                    if (interior && !(c.emax <= R(-9999.0) || c.eta == R(-9999.0))) {
+                        int dry = (c.eta - pzb < k.eps) ? 1 : 0;
+                        dry += (f_c >> 1) + (f_m2 >> 1) + (f_ew_prev & 1) + (f_ew_prev >> 2);
+                        if (dry < 5) {
+                            const R bN = fm_min(fy.zmax, pe + half * psyE), bS = fm_min(sZ, pe - half * psyE);
+                            const R bE = fm_min(eZ, pe + half * psxE), bW = fm_min(fx.zmax, pe - half * psxE);
+                            const int stop = fy.stopL + sStop + fx.stopR + eStop;
+                            R dEta = ((eM - fx.m) + (fy.m - sM)) * inv_delta;
+                            R dQx = ((eN - fx.n) + (fy.t - sT) + hg * (bE - bW) * (eH + fx.hL)) * inv_delta;
+                            R dQy = ((eT - fx.t) + (fy.n - sN) + hg * (bN - bS) * (fy.hR + sH)) * inv_delta;
+                            dEta = fm_chop(dEta, k.eps); dQx = fm_chop(dQx, k.eps); dQy = fm_chop(dQy, k.eps);
+                            if (stop > 0) { c.qx = R(0); c.qy = R(0); }
+                            c.eta = c.eta - dt * dEta; c.qx = c.qx - dt * dQx; c.qy = c.qy - dt * dQy;
+                            const R h_new = c.eta - pzb;
+                            if (k.friction && !(h_new < k.eps)) friction_fast(k, h_new, fm_rcp(h_new), c.qx, c.qy, ld(o_m, T::P_N, lc), dt);
+                            if (h_new < k.eps) c.eta = pzb;
+                            if (c.eta > c.emax && c.emax > R(-9990.0)) c.emax = c.eta;
+                        }
+                    }
+                    if (lane >= 2 && lane < 2 + T::USE && x < g.cols) {
+                        d.store(static_cast<size_t>(yc) * g.pitch + x, c);
+                        if (a.reduce_mode != hp::kReduceNone) {
+                            const R h = c.eta - pzb;
+                            if (h > k.eps10 && c.emax > R(-9999.0)) {
+                                const R cc = fm_sqrt(k.g * h);
+                                R sp = cc;
+                                if (!k.simplified_speed) { const R rh = fm_rcp(h); sp = fm_max(hp_abs(c.qx * rh), hp_abs(c.qy * rh)) + cc; }
+                                ws = sp > ws ? sp : ws;
+                            }
+                        }
+                    }
+                }
+                sM = fy.m; sN = fy.n; sT = fy.t; sZ = fy.zmax; sH = fy.hL; sStop = fy.stopR;
+            } else if (!stepping && j >= 3) {
+                // dt <= 0: the reference's kernels return; the ping-pong copies the state through
+                if (lane >= 2 && lane < 2 + T::USE && x < g.cols) {
+                    Cell<R> c{ld(o_m, T::P_ETA, lc), ld(o_m, T::P_EMAX, lc), ld(o_m, T::P_QX, lc), ld(o_m, T::P_QY, lc)};
+                    d.store(static_cast<size_t>(y - 1) * g.pitch + x, c);
+                    if (a.reduce_mode != hp::kReduceNone) {
+                        const R h = c.eta - pzb;
+                        if (h > k.eps10 && c.emax > R(-9999.0)) {
+                            const R cc = fm_sqrt(k.g * h);
+                            R sp = cc;
+                            if (!k.simplified_speed) { const R rh = fm_rcp(h); sp = fm_max(hp_abs(c.qx * rh), hp_abs(c.qy * rh)) + cc; }
+                            ws = sp > ws ? sp : ws;
+                        }
+                    }
+                }
+            }
+            // rotate
+            pe = ce; pqx = cqx; pqy = cqy; psxE = sxE; psxH = sxH; psxQx = sxQx; psxQy = sxQy;
+            psyE = syE; psyH = syH; psyQx = syQx; psyQy = syQy; pzb = zb;
+            f_ew_prev = (f_w >> 1) | ((f_e >> 1) << 2);
+            f_m2 = f_m1; f_m1 = f_c; f_c = f_p;
+
+            // row j-1 is dead: refill its ring slot with row j-1+RR
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0 && j - 1 + T::RR <= J + 1) issue_row(j - 1 + T::RR);
+        }
+    }
+    block_reduce_finalize<R>(ws, a, k);
+}
+
+template <class K> static int march_grid(const StepArgs& a, int use, int nw, int ctas_per_sm, int sm_count) {
+    const int nrows = a.y1 - a.y0;
+    const int nstrips = (a.grid.cols + use - 1) / use, ngroups = (nstrips + nw - 1) / nw;
+    const long long units = static_cast<long long>(ngroups) * nrows;
+    const int min_rows = nrows < 8 ? nrows : 8;                      // amortise the three start-up rows of a run
+    long long grid = (units + min_rows - 1) / min_rows;
+    const long long cap = static_cast<long long>(ctas_per_sm) * sm_count;
+    if (grid > cap) grid = cap;
+    return static_cast<int>(grid < 1 ? 1 : grid);
+}
+
+template <class R> static int launch_mh_march(const StepArgs& a_in, const TmaMaps6& maps, int sm_count, cudaStream_t st) {
+    using T = March<R, 2>;
+    StepArgs a = a_in;
+    if (a.y1 <= a.y0) return 0;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(mh_step_march<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES);
+        configured = true;
+    }
+    const int grid = march_grid<void>(a, T::USE, T::NW, sizeof(R) == 8 ? 4 : 6, sm_count);
+    a.total_ctas = grid;
+    mh_step_march<R><<<grid, T::NW * 32, T::SMEM_BYTES, st>>>(a, maps);
+    return 1;
+}
+
+}  // namespace HP_NS

@@ -19,6 +19,7 @@ LIB_PATH = os.path.join(HERE, "libhipims_cuda.so")
 OPT_STRICT_FP = 1
 OPT_NO_GRAPH = 2
 OPT_NO_TMA = 4
+OPT_TILE_KERNELS = 8
 
 _SCHEME_ID = {hc.SCHEME_GODUNOV: 0, hc.SCHEME_MUSCL_HANCOCK: 1, hc.SCHEME_INERTIAL: 2}
 

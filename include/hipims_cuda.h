@@ -68,7 +68,9 @@ enum {
     HP_OPT_STRICT_FP   = 1u << 0, /* kernels built without FMA contraction: bit-comparable with the
                                      reference arithmetic evaluated in IEEE order                   */
     HP_OPT_NO_GRAPH    = 1u << 1, /* launch kernels directly instead of replaying CUDA graphs      */
-    HP_OPT_NO_TMA      = 1u << 2  /* use the plain-load kernels instead of the TMA-staged ones     */
+    HP_OPT_NO_TMA      = 1u << 2, /* use the plain-load kernels instead of the TMA-staged ones     */
+    HP_OPT_TILE_KERNELS = 1u << 3 /* use the TMA tile kernels (CTA-wide 2-D tiles) instead of the
+                                     default marching kernels (one warp per column strip)        */
 };
 
 /*

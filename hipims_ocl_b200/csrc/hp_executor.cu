@@ -71,6 +71,10 @@ struct hp_scheme {
     hp::ParamsD params{};
     const hp::KernelTable* K = nullptr;
     size_t rb = 8, plane_bytes = 0;
+    // the ten planes live in ONE allocation, in the order  A.eta A.qx A.qy A.emax | zb n | B.eta B.qx B.qy B.emax,
+    // so that a single 3-D TMA box of six consecutive planes holds everything a step reads (buffer A: planes
+    // 0..5, buffer B: planes 4..9)
+    char* block = nullptr;
     hp::Planes A{}, B{};
     void *bed = nullptr, *manning = nullptr, *clock = nullptr;
     unsigned long long* max_bits = nullptr;
@@ -84,7 +88,7 @@ struct hp_scheme {
     int graph_launches[2] = {0, 0};
     bool use_tma = false, use_march = false;
     hp::TmaMapsPOD maps_a{}, maps_b{};   // descriptors with buffer A / buffer B as the source
-    hp::TmaMaps6POD march_a{}, march_b{};
+    hp::TmaMaps6POD march_map{};         // bytes[0]: 3-D descriptor over the ten-plane block
     hp::Comm* comm = nullptr;
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t ev_edges = nullptr, ev_halo = nullptr;
@@ -147,7 +151,7 @@ int enqueue_iteration(hp_scheme* s, bool alt, int* launched) {
         else a.reduce_mode = alt ? hp::kReduceDst : hp::kReduceSrc;   // Q1: always buffer A
     }
     auto step = [&](const hp::StepArgs& args) {
-        if (s->use_march) return s->K->step_march(static_cast<int>(s->cfg.scheme), rb, args, alt ? &s->march_b : &s->march_a,
+        if (s->use_march) return s->K->step_march(static_cast<int>(s->cfg.scheme), rb, args, &s->march_map, alt ? 1 : 0,
                                                   s->ex->prop.multiProcessorCount, st);
         if (s->use_tma) return s->K->step_tma(static_cast<int>(s->cfg.scheme), rb, args, alt ? &s->maps_b : &s->maps_a,
                                               s->ex->prop.multiProcessorCount, st);
@@ -206,7 +210,8 @@ int build_graph(hp_scheme* s, int slot, int pairs) {
 // zero-filled device allocation; the fill is ordered on the scheme's own stream (a legacy
 // default-stream cudaMemset is NOT ordered against a non-blocking stream)
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
-int encode_plane_map(void* out128, void* plane, const hp::Grid& g, size_t rb, int box_w, int box_h) {
+int encode_plane_map(void* out128, void* plane, const hp::Grid& g, size_t rb, int box_w, int box_h, int planes = 0,
+                     size_t plane_bytes = 0, int box_planes = 0) {
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -218,12 +223,12 @@ int encode_plane_map(void* out128, void* plane, const hp::Grid& g, size_t rb, in
         if (!fn || qres != cudaDriverEntryPointSuccess) return fail(HP_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
         encode = reinterpret_cast<EncodeFn>(fn);
     }
-    const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(g.cols), static_cast<cuuint64_t>(g.rows)};
-    const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(g.pitch) * rb};
-    const cuuint32_t box[2] = {static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(box_h)};
-    const cuuint32_t estride[2] = {1, 1};
+    const cuuint64_t gdim[3] = {static_cast<cuuint64_t>(g.cols), static_cast<cuuint64_t>(g.rows), static_cast<cuuint64_t>(planes)};
+    const cuuint64_t gstride[2] = {static_cast<cuuint64_t>(g.pitch) * rb, static_cast<cuuint64_t>(plane_bytes)};
+    const cuuint32_t box[3] = {static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(box_h), static_cast<cuuint32_t>(box_planes)};
+    const cuuint32_t estride[3] = {1, 1, 1};
     CUtensorMap tm;
-    const CUresult r = encode(&tm, rb == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, plane, gdim, gstride,
+    const CUresult r = encode(&tm, rb == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, planes > 0 ? 3 : 2, plane, gdim, gstride,
                               box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(HP_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
@@ -239,15 +244,8 @@ int build_tma_maps(hp_scheme* s) {
     hp::TmaMapsPOD* maps[2] = {&s->maps_a, &s->maps_b};
     const int rbi = static_cast<int>(s->rb);
     if (s->use_march) {
-        // marching kernels: single-row boxes of six planes
-        hp::TmaMaps6POD* m6[2] = {&s->march_a, &s->march_b};
-        const int w = hp::march_box_w(rbi, halo);
-        for (int b = 0; b < 2; ++b) {
-            void* planes[6] = {bufs[b]->eta, bufs[b]->qx, bufs[b]->qy, s->bed, bufs[b]->emax, s->manning};
-            for (int p = 0; p < 6; ++p)
-                if ((rc = encode_plane_map(m6[b]->bytes[p], planes[p], s->grid, s->rb, w, 1))) return rc;
-        }
-        return HP_OK;
+        // marching kernels: one 3-D descriptor over the ten-plane block; a box is one row of six planes
+        return encode_plane_map(s->march_map.bytes[0], s->block, s->grid, s->rb, hp::march_box_w(rbi, halo), 1, 10, s->plane_bytes, 6);
     }
     const int w = hp::tma_box_w(rbi, halo), h = hp::tma_box_h(halo);
     for (int b = 0; b < 2; ++b) {
@@ -265,15 +263,15 @@ template <class T> int dev_alloc(hp_scheme* s, T** p, size_t bytes) {
     return HP_OK;
 }
 
-int alloc_planes(hp_scheme* s, hp::Planes& p) {
+int alloc_block(hp_scheme* s) {
     int rc;
-    if ((rc = dev_alloc(s, reinterpret_cast<char**>(&p.eta), s->plane_bytes))) return rc;
-    if ((rc = dev_alloc(s, reinterpret_cast<char**>(&p.emax), s->plane_bytes))) return rc;
-    if ((rc = dev_alloc(s, reinterpret_cast<char**>(&p.qx), s->plane_bytes))) return rc;
-    if ((rc = dev_alloc(s, reinterpret_cast<char**>(&p.qy), s->plane_bytes))) return rc;
+    if ((rc = dev_alloc(s, &s->block, 10 * s->plane_bytes))) return rc;
+    auto at = [&](int i) { return static_cast<void*>(s->block + static_cast<size_t>(i) * s->plane_bytes); };
+    s->A = hp::Planes{at(0), at(3), at(1), at(2)};           // Planes is {eta, emax, qx, qy}
+    s->bed = at(4); s->manning = at(5);
+    s->B = hp::Planes{at(6), at(9), at(7), at(8)};
     return HP_OK;
 }
-void free_planes(hp::Planes& p) { cudaFree(p.eta); cudaFree(p.emax); cudaFree(p.qx); cudaFree(p.qy); p = hp::Planes{}; }
 
 int write_clock(hp_scheme* s, double t, double dt, double th, double target) {
     if (s->rb == 8) { auto c = make_clock<double>(t, dt, th, target); HP_CUDA(cudaMemcpyAsync(s->clock, &c, sizeof(c), cudaMemcpyHostToDevice, s->ex->stream)); }
@@ -442,10 +440,7 @@ int hp_scheme_create(hp_executor* ex, const hp_scheme_config* cfg, hp_scheme** o
     s->plane_bytes = static_cast<size_t>(g.rows) * g.pitch * s->rb;
     int rc = HP_OK;
     do {
-        if ((rc = alloc_planes(s, s->A))) break;
-        if ((rc = alloc_planes(s, s->B))) break;
-        if ((rc = dev_alloc(s, reinterpret_cast<char**>(&s->bed), s->plane_bytes))) break;
-        if ((rc = dev_alloc(s, reinterpret_cast<char**>(&s->manning), s->plane_bytes))) break;
+        if ((rc = alloc_block(s))) break;
         if ((rc = dev_alloc(s, reinterpret_cast<char**>(&s->clock), 64))) break;
         if ((rc = dev_alloc(s, &s->max_bits, sizeof(unsigned long long)))) break;
         if ((rc = dev_alloc(s, &s->ticket, sizeof(unsigned int)))) break;
@@ -460,8 +455,9 @@ int hp_scheme_create(hp_executor* ex, const hp_scheme_config* cfg, hp_scheme** o
         // TMA-staged kernels: the fast flavour's Godunov step (others use the plain-load kernels)
         s->use_tma = s->K->step_tma != nullptr && !(cfg->options & HP_OPT_NO_TMA) &&
                      (cfg->scheme == HP_SCHEME_GODUNOV || cfg->scheme == HP_SCHEME_MUSCL_HANCOCK);
-        s->use_march = s->use_tma && s->K->step_march != nullptr && !(cfg->options & HP_OPT_TILE_KERNELS) &&
-                       cfg->scheme == HP_SCHEME_MUSCL_HANCOCK;
+        s->use_march = s->use_tma && s->K->step_march != nullptr &&
+                       ((cfg->scheme == HP_SCHEME_MUSCL_HANCOCK && !(cfg->options & HP_OPT_TILE_KERNELS)) ||
+                        (cfg->scheme == HP_SCHEME_GODUNOV && (cfg->options & HP_OPT_MARCH_GODUNOV)));
         if (s->use_tma && (rc = build_tma_maps(s))) break;
     } while (0);
     if (rc != HP_OK) { hp_scheme_destroy(s); return rc; }
@@ -478,8 +474,7 @@ void hp_scheme_destroy(hp_scheme* s) {
     if (s->comm_stream) cudaStreamDestroy(s->comm_stream);
     if (s->ev_edges) cudaEventDestroy(s->ev_edges);
     if (s->ev_halo) cudaEventDestroy(s->ev_halo);
-    free_planes(s->A); free_planes(s->B);
-    cudaFree(s->bed); cudaFree(s->manning); cudaFree(s->clock); cudaFree(s->max_bits); cudaFree(s->ticket); cudaFree(s->staging);
+    cudaFree(s->block); cudaFree(s->clock); cudaFree(s->max_bits); cudaFree(s->ticket); cudaFree(s->staging);
     for (auto& b : s->bdys) { cudaFree(b.series); cudaFree(b.relations); }
     delete s;
 }

@@ -420,10 +420,11 @@ static int launch_step_tma(int scheme, int real_bytes, const StepArgs& a, const 
     if (scheme == 1) return real_bytes == 8 ? launch_mh_tma<double>(a, m, sm_count, st) : launch_mh_tma<float>(a, m, sm_count, st);
     return -1;
 }
-static_assert(sizeof(TmaMaps6) == sizeof(hp::TmaMaps6POD), "descriptor block layout");
-static int launch_step_march(int scheme, int real_bytes, const StepArgs& a, const hp::TmaMaps6POD* maps, int sm_count, cudaStream_t st) {
-    const TmaMaps6& m = *reinterpret_cast<const TmaMaps6*>(maps);
-    if (scheme == 1) return real_bytes == 8 ? launch_mh_march<double>(a, m, sm_count, st) : launch_mh_march<float>(a, m, sm_count, st);
+static_assert(sizeof(TmaBlockMap) == sizeof(hp::TmaMaps6POD), "descriptor block layout");
+static int launch_step_march(int scheme, int real_bytes, const StepArgs& a, const hp::TmaMaps6POD* maps, int alt, int sm_count, cudaStream_t st) {
+    const TmaBlockMap& m = *reinterpret_cast<const TmaBlockMap*>(maps);
+    if (scheme == 0) return real_bytes == 8 ? launch_godunov_march<double>(a, m, alt, sm_count, st) : launch_godunov_march<float>(a, m, alt, sm_count, st);
+    if (scheme == 1) return real_bytes == 8 ? launch_mh_march<double>(a, m, alt, sm_count, st) : launch_mh_march<float>(a, m, alt, sm_count, st);
     return -1;
 }
 #endif

@@ -80,8 +80,10 @@ constexpr int tma_box_w(int real_bytes, int halo) { return tma_tile_x(halo) + 2 
 constexpr int tma_box_h(int halo) { return kTmaTileY + 2 * halo; }
 
 // Marching kernels (hp_march_kernels.cuh): one warp per 32-column strip, rows streamed through a
-// per-warp TMA ring of single rows x six planes (eta, qx, qy, zb, eta_max, n).
-struct alignas(64) TmaMaps6POD { unsigned char bytes[6][128]; };
+// per-warp TMA ring of single rows x six planes; bytes[0] is a 3-D descriptor {cols, rows, 10 planes} over the
+// scheme's plane block (A.eta A.qx A.qy A.emax | zb n | B.eta B.qx B.qy B.emax), box = {march_box_w, 1, 6}:
+// plane coordinate 0 reads buffer A + zb + n, plane coordinate 4 reads zb + n + buffer B.
+struct alignas(64) TmaMaps6POD { unsigned char bytes[1][128]; };
 constexpr int kMarchWarps = 4;                      // warps (= adjacent strips) per CTA
 constexpr int march_use(int real_bytes, int halo) { return (halo == 2 || real_bytes == 4) ? 28 : 30; }   // cells updated per warp row
 constexpr int march_box_w(int real_bytes, int halo) {
@@ -94,7 +96,7 @@ struct KernelTable {
     // TMA-staged step (fast flavour only, NULL otherwise); returns -1 if the scheme has no such kernel
     int (*step_tma)(int scheme, int real_bytes, const StepArgs& a, const TmaMapsPOD* maps, int sm_count, cudaStream_t st);
     // marching step (fast flavour only, NULL otherwise); returns -1 if the scheme has no such kernel
-    int (*step_march)(int scheme, int real_bytes, const StepArgs& a, const TmaMaps6POD* maps, int sm_count, cudaStream_t st);
+    int (*step_march)(int scheme, int real_bytes, const StepArgs& a, const TmaMaps6POD* maps, int alt, int sm_count, cudaStream_t st);
     // returns the number of kernels launched
     int (*step)(int scheme, int real_bytes, const StepArgs& a, cudaStream_t st);
     int (*reduce_only)(int real_bytes, const StepArgs& a, cudaStream_t st);       // tst_Reduce

@@ -5,7 +5,7 @@
 // (profiles/r01_*): per cell-update only ~36 % of their instructions are fp64 arithmetic, the rest
 // is index arithmetic, shared-memory traffic for predictor / flux planes and CTA barriers between
 // the phases.  Here
-//   * raw rows arrive through TMA (cp.async.bulk.tensor.2d + mbarrier) into a per-warp ring of
+//   * raw rows arrive through TMA (cp.async.bulk.tensor.3d + mbarrier, ONE box = one row of six planes) into a per-warp ring of
 //     four rows x six planes, one row ahead of the arithmetic; every plane is read from HBM once;
 //   * the y-direction never leaves the thread: the predictor of the row below, the flux through the
 //     southern face and its owner terms are carried in registers from the previous row;
@@ -26,19 +26,29 @@
 
 namespace HP_NS {
 
-struct TmaMaps6 { CUtensorMap eta, qx, qy, zb, emax, n; };
+struct TmaBlockMap { CUtensorMap block; };
 
-template <class R, int HALO> struct March {
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int x, int y, int p, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(p), "r"(bar) : "memory");
+}
+
+// Ring geometry.  ALT = false: the step reads buffer A (block planes 0..5 = eta qx qy emax zb n);
+// ALT = true: buffer B (block planes 4..9 = zb n eta qx qy emax).
+template <class R, int HALO, bool ALT> struct March {
     static constexpr int NW = hp::kMarchWarps, RR = 4, NP = 6;
     static constexpr int A16 = 16 / int(sizeof(R));                       // elements per 16 bytes
     static constexpr int USE = hp::march_use(int(sizeof(R)), HALO);       // cells updated per warp row
     static constexpr int PADL = ((-HALO) % A16 + A16) % A16;              // box starts 16-byte aligned
     static constexpr int BW = hp::march_box_w(int(sizeof(R)), HALO);
-    static constexpr int PLANE = (BW * int(sizeof(R)) + 127) / 128 * 128; // bytes between planes of one ring row
-    static constexpr int SLOT = NP * PLANE;                               // one ring row
+    static constexpr int PLANE = BW * int(sizeof(R));                     // bytes between planes of one ring row
+    static constexpr int ROW_TX = NP * PLANE;                             // bytes one TMA box delivers
+    static constexpr int SLOT = (ROW_TX + 127) / 128 * 128;               // one ring row
     static constexpr int WARP_BYTES = RR * SLOT;
     static constexpr int SMEM_BYTES = NW * WARP_BYTES + NW * RR * 8;
-    static constexpr int P_ETA = 0, P_QX = 1, P_QY = 2, P_ZB = 3, P_EMAX = 4, P_N = 5;
+    static constexpr int P0 = ALT ? 4 : 0;                                // first block plane of the box
+    static constexpr int P_ETA = ALT ? 2 : 0, P_QX = ALT ? 3 : 1, P_QY = ALT ? 4 : 2, P_EMAX = ALT ? 5 : 3, P_ZB = ALT ? 0 : 4,
+                         P_N = ALT ? 1 : 5;
     static_assert((USE % A16) == 0, "strip starts must keep the TMA box 16-byte aligned");
     static_assert(BW >= 32 + PADL && (BW * sizeof(R)) % 16 == 0, "box");
 };
@@ -92,20 +102,13 @@ __device__ __forceinline__ void face_solve(const Params<R>& k, R etaL, R zL, R u
 template <class R> __device__ __forceinline__ R shfl_up1(R v) { return __shfl_up_sync(0xffffffffu, v, 1); }
 template <class R> __device__ __forceinline__ R shfl_dn1(R v) { return __shfl_down_sync(0xffffffffu, v, 1); }
 
-// The part of the launch every marching kernel shares: per-warp ring, barriers, work split.
-template <class T> struct MarchCtx {
-    unsigned char* ring;
-    uint32_t ring_u, bar_u, ph;
-    int lane, warp;
-};
-
 // =============================================================================================
 // MUSCL-Hancock, predictor + corrector fused, marching.
 // =============================================================================================
-template <class R>
-__global__ void __launch_bounds__(March<R, 2>::NW * 32, sizeof(R) == 8 ? 4 : 6)
-mh_step_march(const StepArgs a, const __grid_constant__ TmaMaps6 maps) {
-    using T = March<R, 2>;
+template <class R, bool ALT>
+__global__ void __launch_bounds__(hp::kMarchWarps * 32, sizeof(R) == 8 ? 4 : 6)
+mh_step_march(const StepArgs a, const __grid_constant__ TmaBlockMap maps) {
+    using T = March<R, 2, ALT>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* const ring = smem_raw + warp * T::WARP_BYTES;
@@ -160,14 +163,8 @@ mh_step_march(const StepArgs a, const __grid_constant__ TmaMaps6 maps) {
         const int J = yb - ya + 2;                        // raw rows 0 .. J+1, predictor rows 1 .. J
         auto issue_row = [&](int j) {
             const uint32_t bar = bar_u + 8 * (j & (T::RR - 1));
-            const uint32_t dst = ring_u + (j & (T::RR - 1)) * T::SLOT;
-            mbar_expect_tx(bar, uint32_t(T::NP * T::BW * sizeof(R)));
-            tma_load_2d(dst + T::P_ETA * T::PLANE, &maps.eta, X0 - T::PADL, rs + j, bar);
-            tma_load_2d(dst + T::P_QX * T::PLANE, &maps.qx, X0 - T::PADL, rs + j, bar);
-            tma_load_2d(dst + T::P_QY * T::PLANE, &maps.qy, X0 - T::PADL, rs + j, bar);
-            tma_load_2d(dst + T::P_ZB * T::PLANE, &maps.zb, X0 - T::PADL, rs + j, bar);
-            tma_load_2d(dst + T::P_EMAX * T::PLANE, &maps.emax, X0 - T::PADL, rs + j, bar);
-            tma_load_2d(dst + T::P_N * T::PLANE, &maps.n, X0 - T::PADL, rs + j, bar);
+            mbar_expect_tx(bar, uint32_t(T::ROW_TX));
+            tma_load_3d(ring_u + (j & (T::RR - 1)) * T::SLOT, &maps.block, X0 - T::PADL, rs + j, T::P0, bar);
         };
         auto wait_row = [&](int j) {
             const int s = j & (T::RR - 1);
@@ -330,7 +327,203 @@ mh_step_march(const StepArgs a, const __grid_constant__ TmaMaps6 maps) {
     block_reduce_finalize<R>(ws, a, k);
 }
 
-template <class K> static int march_grid(const StepArgs& a, int use, int nw, int ctas_per_sm, int sm_count) {
+// =============================================================================================
+// First-order Godunov, marching.  Carried per lane: the cell below (level, bed, velocities, celerity)
+// and its southern face.  Cells whose stencil is dry stay unwritten, exactly like
+// godunov_step_tma.
+// =============================================================================================
+template <class R> struct GodCell { R eta, zb, u, v, c; };
+
+#ifndef HP_MARCH_GOD_CTAS64
+#define HP_MARCH_GOD_CTAS64 5
+#endif
+#ifndef HP_MARCH_GOD_CTAS32
+#define HP_MARCH_GOD_CTAS32 8
+#endif
+template <class R, bool ALT>
+__global__ void __launch_bounds__(hp::kMarchWarps * 32, sizeof(R) == 8 ? HP_MARCH_GOD_CTAS64 : HP_MARCH_GOD_CTAS32)
+godunov_step_march(const StepArgs a, const __grid_constant__ TmaBlockMap maps) {
+    using T = March<R, 1, ALT>;
+    constexpr unsigned FULL = 0xffffffffu;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* const ring = smem_raw + warp * T::WARP_BYTES;
+    const uint32_t ring_u = smem_u32(ring);
+    const uint32_t bar_u = smem_u32(smem_raw + T::NW * T::WARP_BYTES) + warp * T::RR * 8;
+    if (lane == 0) {
+#pragma unroll
+        for (int r = 0; r < T::RR; ++r) mbar_init(bar_u + 8 * r, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+
+    const Params<R> k = make_params<R>(a.params);
+    const Grid g = a.grid;
+    const R dt = read_timestep<R>(a.clock);
+    const R inv_delta = fm_rcp(k.delta);
+    const R hg = R(0.5) * k.g;
+    const MutView<R> d(a.dst);
+    const bool stepping = dt > R(0);
+
+    const int nrows = a.y1 - a.y0;
+    const int nstrips = (g.cols + T::USE - 1) / T::USE;
+    const int ngroups = (nstrips + T::NW - 1) / T::NW;
+    const long long units = static_cast<long long>(ngroups) * nrows;
+    long long u = units * blockIdx.x / gridDim.x;
+    const long long u1 = units * (blockIdx.x + 1) / gridDim.x;
+
+    const int lc = (lane + T::PADL) * int(sizeof(R));
+    const int lw = (lane > 0 ? lane - 1 + T::PADL : T::PADL) * int(sizeof(R));
+    auto ld = [&](int row_off, int plane, int col_off) -> R {
+        return *reinterpret_cast<const R*>(ring + row_off + plane * T::PLANE + col_off);
+    };
+    const bool lane_owns = lane >= 1 && lane < 1 + T::USE;
+
+    R ws = R(0);
+    uint32_t ph = 0;
+
+    while (u < u1) {
+        const int grp = static_cast<int>(u / nrows);
+        const int ya = a.y0 + static_cast<int>(u - static_cast<long long>(grp) * nrows);
+        const long long gend = static_cast<long long>(grp + 1) * nrows;
+        const int yb = ya + static_cast<int>((u1 < gend ? u1 : gend) - u);
+        u += yb - ya;
+        const int strip = grp * T::NW + warp;
+        if (strip >= nstrips) continue;
+
+        const int X0 = strip * T::USE - 1;               // column of lane 0
+        const int x = X0 + lane;
+        const int rs = ya - 1;                            // first raw row of this run
+        const int NR = yb - ya + 2;                       // raw rows 0 .. NR-1; rows 1 .. NR-2 are updated
+        const bool x_interior = x >= 1 && x <= g.cols - 2;
+        const bool x_store = lane_owns && x < g.cols;
+        auto issue_row = [&](int j) {
+            const uint32_t bar = bar_u + 8 * (j & (T::RR - 1));
+            mbar_expect_tx(bar, uint32_t(T::ROW_TX));
+            tma_load_3d(ring_u + (j & (T::RR - 1)) * T::SLOT, &maps.block, X0 - T::PADL, rs + j, T::P0, bar);
+        };
+        auto wait_row = [&](int j) {
+            const int s = j & (T::RR - 1);
+            mbar_wait(bar_u + 8 * s, (ph >> s) & 1u);
+            ph ^= 1u << s;
+        };
+        auto derive = [&](int row_off, GodCell<R>& o, R& qx, R& qy) {      // phase B of the tile kernel
+            o.eta = ld(row_off, T::P_ETA, lc); o.zb = ld(row_off, T::P_ZB, lc);
+            qx = ld(row_off, T::P_QX, lc); qy = ld(row_off, T::P_QY, lc);
+            const R h = o.eta - o.zb;
+            const R rh = !(h < k.eps) ? fm_rcp(h) : R(0);
+            o.u = qx * rh; o.v = qy * rh;
+            o.c = fm_sqrt(k.g * (h > R(0) ? h : R(0)));
+        };
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < T::RR; ++j) if (j < NR) issue_row(j);
+        }
+        wait_row(0);
+
+        GodCell<R> P;
+        R p_qx, p_qy;
+        derive(0, P, p_qx, p_qy);
+        R sM = R(0), sN = R(0), sT = R(0), sZ = R(0), sH = R(0);   // southern face of row j-1
+        int sStop = 0;
+        bool dry_s = true;                                          // dryness of the cell below row j-1
+
+        for (int j = 1; j < NR; ++j) {
+            const int y = rs + j;
+            const int o_m = ((j - 1) & (T::RR - 1)) * T::SLOT, o_c = (j & (T::RR - 1)) * T::SLOT;
+            wait_row(j);
+            GodCell<R> C;
+            R c_qx, c_qy;
+            derive(o_c, C, c_qx, c_qy);
+            const bool dry_p = P.eta - P.zb < k.eps, dry_c = C.eta - C.zb < k.eps;
+
+            FaceOut<R> fy;
+            if (stepping) face_solve<R>(k, P.eta, P.zb, P.v, P.u, P.c, C.eta, C.zb, C.v, C.u, C.c, true, p_qy, c_qy, fy);
+            else { fy.m = fy.n = fy.t = fy.zmax = fy.hL = fy.hR = R(0); fy.stopL = fy.stopR = 0; }
+
+            if (j >= 2) {
+                const int yc = y - 1, gyc = yc + g.gy0;
+                // west face of row y-1: the cell of lane-1 against the own cell
+                const R wU = shfl_up1(P.u), wV = shfl_up1(P.v), wC = shfl_up1(P.c);
+                const unsigned drym = __ballot_sync(FULL, dry_p);
+                FaceOut<R> fx;
+                if (stepping) face_solve<R>(k, ld(o_m, T::P_ETA, lw), ld(o_m, T::P_ZB, lw), wU, wV, wC, P.eta, P.zb, P.u, P.v, P.c, true,
+                                            ld(o_m, T::P_QX, lw), p_qx, fx);
+                else { fx.m = fx.n = fx.t = fx.zmax = fx.hL = fx.hR = R(0); fx.stopL = fx.stopR = 0; }
+                const R eM = shfl_dn1(fx.m), eN = shfl_dn1(fx.n), eT = shfl_dn1(fx.t), eZ = shfl_dn1(fx.zmax), eH = shfl_dn1(fx.hR);
+                const int eStop = __shfl_down_sync(FULL, fx.stopL, 1);
+
+                Cell<R> c{P.eta, ld(o_m, T::P_EMAX, lc), p_qx, p_qy};
+                const R zb = P.zb;
+                if (a.reduce_mode == hp::kReduceSrc && x_store) {
+                    const R h = c.eta - zb;
+                    if (h > k.eps10 && c.emax > R(-9999.0)) {
+                        const R sp = k.simplified_speed ? P.c : fm_max(hp_abs(P.u), hp_abs(P.v)) + P.c;
+                        ws = sp > ws ? sp : ws;
+                    }
+                }
+                bool wrote = false;
+                R rh_new = R(0);
+                bool have_new = false;
+                if (x_interior && gyc >= 1 && gyc <= g.grows - 2) {                  // frozen outer ring
+                    if (!stepping) {
+                        wrote = true;                                                   // CLSchemeGodunov.clc:201-206
+                    } else if (c.emax <= R(-9999.0) || c.eta == R(-9999.0)) {
+                        wrote = true;                                                   // disabled cell: copied through
+                    } else {
+                        const bool dry_e = (drym >> ((lane + 1) & 31)) & 1u, dry_w = (drym >> ((lane + 31) & 31)) & 1u;
+                        const bool all_dry = dry_p && dry_c && dry_s && dry_e && dry_w; // CLSchemeGodunov.clc:248-255
+                        if (!all_dry) {
+                            const R bN = fm_min(fy.zmax, c.eta), bS = fm_min(sZ, c.eta), bE = fm_min(eZ, c.eta), bW = fm_min(fx.zmax, c.eta);
+                            const int stop = fy.stopL + sStop + fx.stopR + eStop;
+                            R dEta = ((eM - fx.m) + (fy.m - sM)) * inv_delta;
+                            R dQx = ((eN - fx.n) + (fy.t - sT) + hg * (bE - bW) * (eH + fx.hL)) * inv_delta;
+                            R dQy = ((eT - fx.t) + (fy.n - sN) + hg * (bN - bS) * (fy.hR + sH)) * inv_delta;
+                            dEta = fm_chop(dEta, k.eps); dQx = fm_chop(dQx, k.eps); dQy = fm_chop(dQy, k.eps);
+                            if (stop > 0) { c.qx = R(0); c.qy = R(0); }
+                            c.eta = c.eta - dt * dEta; c.qx = c.qx - dt * dQx; c.qy = c.qy - dt * dQy;
+                            const R h_new = c.eta - zb;
+                            if (!(h_new < k.eps)) { rh_new = fm_rcp(h_new); have_new = true; }
+                            if (k.friction) friction_fast(k, h_new, rh_new, c.qx, c.qy, ld(o_m, T::P_N, lc), dt);
+                            if (c.eta > c.emax && c.emax > R(-9990.0)) c.emax = c.eta;
+                            if (h_new < k.eps) c.eta = zb;
+                            wrote = true;
+                        }
+                    }
+                }
+                if (x_store) {
+                    const size_t id = static_cast<size_t>(yc) * g.pitch + x;
+                    if (wrote) d.store(id, c);
+                    if (a.reduce_mode == hp::kReduceDst) {
+                        if (!wrote) { c.eta = d.eta[id]; c.emax = d.emax[id]; c.qx = d.qx[id]; c.qy = d.qy[id]; have_new = false; }
+                        const R h = c.eta - zb;
+                        if (h > k.eps10 && c.emax > R(-9999.0)) {
+                            const R cc = fm_sqrt(k.g * h);
+                            R sp = cc;
+                            if (!k.simplified_speed) {
+                                const R rh = have_new ? rh_new : fm_rcp(h);
+                                sp = fm_max(hp_abs(c.qx * rh), hp_abs(c.qy * rh)) + cc;
+                            }
+                            ws = sp > ws ? sp : ws;
+                        }
+                    }
+                }
+            }
+            sM = fy.m; sN = fy.n; sT = fy.t; sZ = fy.zmax; sH = fy.hL; sStop = fy.stopR;
+            dry_s = dry_p;
+            P = C; p_qx = c_qx; p_qy = c_qy;
+
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0 && j - 1 + T::RR < NR) issue_row(j - 1 + T::RR);
+        }
+    }
+    block_reduce_finalize<R>(ws, a, k);
+}
+
+static int march_grid(const StepArgs& a, int use, int nw, int ctas_per_sm, int sm_count) {
     const int nrows = a.y1 - a.y0;
     const int nstrips = (a.grid.cols + use - 1) / use, ngroups = (nstrips + nw - 1) / nw;
     const long long units = static_cast<long long>(ngroups) * nrows;
@@ -341,18 +534,37 @@ template <class K> static int march_grid(const StepArgs& a, int use, int nw, int
     return static_cast<int>(grid < 1 ? 1 : grid);
 }
 
-template <class R> static int launch_mh_march(const StepArgs& a_in, const TmaMaps6& maps, int sm_count, cudaStream_t st) {
-    using T = March<R, 2>;
+template <class R> static int launch_mh_march(const StepArgs& a_in, const TmaBlockMap& maps, int alt, int sm_count, cudaStream_t st) {
+    using T = March<R, 2, false>;
     StepArgs a = a_in;
     if (a.y1 <= a.y0) return 0;
     static bool configured = false;
     if (!configured) {
-        cudaFuncSetAttribute(mh_step_march<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES);
+        cudaFuncSetAttribute(mh_step_march<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES);
+        cudaFuncSetAttribute(mh_step_march<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES);
         configured = true;
     }
-    const int grid = march_grid<void>(a, T::USE, T::NW, sizeof(R) == 8 ? 4 : 6, sm_count);
+    const int grid = march_grid(a, T::USE, T::NW, sizeof(R) == 8 ? 4 : 6, sm_count);
     a.total_ctas = grid;
-    mh_step_march<R><<<grid, T::NW * 32, T::SMEM_BYTES, st>>>(a, maps);
+    if (alt) mh_step_march<R, true><<<grid, T::NW * 32, T::SMEM_BYTES, st>>>(a, maps);
+    else mh_step_march<R, false><<<grid, T::NW * 32, T::SMEM_BYTES, st>>>(a, maps);
+    return 1;
+}
+
+template <class R> static int launch_godunov_march(const StepArgs& a_in, const TmaBlockMap& maps, int alt, int sm_count, cudaStream_t st) {
+    using T = March<R, 1, false>;
+    StepArgs a = a_in;
+    if (a.y1 <= a.y0) return 0;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(godunov_step_march<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES);
+        cudaFuncSetAttribute(godunov_step_march<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES);
+        configured = true;
+    }
+    const int grid = march_grid(a, T::USE, T::NW, sizeof(R) == 8 ? HP_MARCH_GOD_CTAS64 : HP_MARCH_GOD_CTAS32, sm_count);
+    a.total_ctas = grid;
+    if (alt) godunov_step_march<R, true><<<grid, T::NW * 32, T::SMEM_BYTES, st>>>(a, maps);
+    else godunov_step_march<R, false><<<grid, T::NW * 32, T::SMEM_BYTES, st>>>(a, maps);
     return 1;
 }
 

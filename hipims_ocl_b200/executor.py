@@ -14,12 +14,14 @@ import numpy as np
 from . import config as hc
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libhipims_cuda.so")
+# HIPIMS_CUDA_LIB: development aid (tools/build_variant.py) -- another build of the same CUDA library, never a fallback
+LIB_PATH = os.environ.get("HIPIMS_CUDA_LIB") or os.path.join(HERE, "libhipims_cuda.so")
 
 OPT_STRICT_FP = 1
 OPT_NO_GRAPH = 2
 OPT_NO_TMA = 4
 OPT_TILE_KERNELS = 8
+OPT_MARCH_GODUNOV = 16
 
 _SCHEME_ID = {hc.SCHEME_GODUNOV: 0, hc.SCHEME_MUSCL_HANCOCK: 1, hc.SCHEME_INERTIAL: 2}
 

@@ -69,8 +69,10 @@ enum {
                                      reference arithmetic evaluated in IEEE order                   */
     HP_OPT_NO_GRAPH    = 1u << 1, /* launch kernels directly instead of replaying CUDA graphs      */
     HP_OPT_NO_TMA      = 1u << 2, /* use the plain-load kernels instead of the TMA-staged ones     */
-    HP_OPT_TILE_KERNELS = 1u << 3 /* use the TMA tile kernels (CTA-wide 2-D tiles) instead of the
-                                     default marching kernels (one warp per column strip)        */
+    HP_OPT_TILE_KERNELS = 1u << 3, /* MUSCL-Hancock: use the TMA tile kernel (CTA-wide 2-D tiles) instead of
+                                      the default marching kernel (one warp per column strip)      */
+    HP_OPT_MARCH_GODUNOV = 1u << 4 /* Godunov: use the marching kernel instead of the default TMA tile
+                                      kernel (equal on wet domains, slower on mostly dry ones)     */
 };
 
 /*

@@ -121,7 +121,12 @@ TOLERANCE_CASES = [
 ]
 
 
-@pytest.mark.parametrize("options", [hx.OPT_STRICT_FP, 0, hx.OPT_NO_GRAPH], ids=["strict", "fast", "fast-nograph"])
+# "fast" runs the default kernels (Godunov: TMA tiles, MUSCL-Hancock: marching warps), "fast-other" the other
+# kernel of each scheme (Godunov marching, MUSCL-Hancock tiles)
+OTHER_KERNELS = hx.OPT_TILE_KERNELS | hx.OPT_MARCH_GODUNOV
+
+
+@pytest.mark.parametrize("options", [hx.OPT_STRICT_FP, 0, hx.OPT_NO_GRAPH, OTHER_KERNELS], ids=["strict", "fast", "fast-nograph", "fast-other"])
 @pytest.mark.parametrize("scheme,precision,scen,bdy,n,iters,extra", TOLERANCE_CASES)
 def test_parity_within_tolerance(ex, options, scheme, precision, scen, bdy, n, iters, extra):
     cfg = make_cfg(scheme, precision, n, n, **extra)
@@ -132,7 +137,7 @@ def test_parity_within_tolerance(ex, options, scheme, precision, scen, bdy, n, i
 SINGLE_STEP = [(s, p) for s in ("godunov", "muscl-hancock", "inertial") for p in ("double", "single")]
 
 
-@pytest.mark.parametrize("options", [hx.OPT_STRICT_FP, 0], ids=["strict", "fast"])
+@pytest.mark.parametrize("options", [hx.OPT_STRICT_FP, 0, OTHER_KERNELS], ids=["strict", "fast", "fast-other"])
 @pytest.mark.parametrize("scheme,precision", SINGLE_STEP)
 def test_single_iteration_on_adversarial_input(ex, options, scheme, precision):
     """One iteration from identical adversarial states (rough bed, wet/dry patches, disabled cells,

@@ -22,6 +22,13 @@ DISCHARGE_IGNORE, DISCHARGE_IS_DISCHARGE, DISCHARGE_IS_VELOCITY, DISCHARGE_IS_VO
 UNIFORM_RAIN_INTENSITY, UNIFORM_LOSS_RATE = 0, 1
 GRIDDED_RAIN_INTENSITY, GRIDDED_MASS_FLUX = 0, 2
 
+# Output raster values: model::rasterDatasets::dataValues (src/Datasets/CRasterDataset.h:33-46), keyed by the
+# names CDomain::getDataValueCode accepts in <dataTarget value="..."> (src/Domain/CDomain.cpp:464-500)
+RASTER_DEPTH, RASTER_FSL, RASTER_VELOCITY_X, RASTER_VELOCITY_Y, RASTER_DISCHARGE_X, RASTER_DISCHARGE_Y = 1, 2, 3, 4, 5, 6
+RASTER_MAX_DEPTH, RASTER_MAX_FSL, RASTER_FROUDE = 9, 10, 11
+RASTER_VALUES = {"depth": 1, "fsl": 2, "velocityx": 3, "velocityy": 4, "dischargex": 5, "dischargey": 6, "maxdepth": 9,
+                 "maxfsl": 10, "froude": 11}
+
 
 @dataclass
 class SchemeConfig:

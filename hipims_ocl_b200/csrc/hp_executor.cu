@@ -566,6 +566,27 @@ int hp_scheme_write_rows(hp_scheme* s, uint64_t first_row, uint64_t row_count, c
     return rows_to_device(s, states, static_cast<int>(first_row), static_cast<int>(row_count), false);
 }
 
+int hp_scheme_derive_raster(hp_scheme* s, uint32_t value, double nodata, double* out) {
+    if (!s || !out) return fail(HP_ERR_INVALID, "null argument");
+    if (value > 11u) return fail(HP_ERR_INVALID, "unknown raster value code %u", value);
+    HP_CUDA(cudaSetDevice(s->ex->device));
+    const hp::Grid& g = s->grid;
+    const hp::KernelTable& K = hp::strict_kernels();              // rounded as written, like the reference's host loop
+    const size_t row_bytes = static_cast<size_t>(g.cols) * sizeof(double);
+    const int chunk = static_cast<int>(s->staging_bytes / row_bytes) > 0 ? static_cast<int>(s->staging_bytes / row_bytes) : 1;
+    const int own = g.own_y1 - g.own_y0;
+    for (int done = 0; done < own; done += chunk) {               // from the northern edge of the owned rows downwards
+        const int n = own - done < chunk ? own - done : chunk;
+        s->launches += K.derive_raster(static_cast<int>(s->rb), src_planes(s, s->use_alt), s->bed, static_cast<double*>(s->staging), g,
+                                       g.own_y1 - done, n, static_cast<int>(value), s->cfg.delta, nodata, s->ex->stream);
+        HP_CUDA(cudaMemcpyAsync(out + static_cast<size_t>(done) * g.cols, s->staging, static_cast<size_t>(n) * row_bytes,
+                                cudaMemcpyDeviceToHost, s->ex->stream));
+    }
+    HP_CUDA(cudaStreamSynchronize(s->ex->stream));
+    HP_CUDA(cudaGetLastError());
+    return HP_OK;
+}
+
 int hp_scheme_set_target_time(hp_scheme* s, double target) {
     if (!s) return fail(HP_ERR_INVALID, "scheme is null");
     return write_clock_field(s, 3, target);

@@ -398,6 +398,45 @@ template <class R> __global__ void __launch_bounds__(256) copy_plane_rows_kernel
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Output rasters: the per-cell derivation of CRasterDataset::domainToRaster
+// (src/Datasets/CRasterDataset.cpp:180-267), in double like the reference's host loop, written
+// in raster order (north row first, :270-280).  Value codes: src/Datasets/CRasterDataset.h:33-46.
+// The executor always takes this kernel from the strict flavour (no FMA contraction), so the result
+// is bit-identical to the host arithmetic of the reference.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double derive_output(int value, double eta, double emax, double qx, double qy, double bed, double res,
+                                                double nodata) {
+    const double depth = eta - bed;
+    switch (value) {
+    case 10: return (emax < bed + 1E-8 || bed > 9999.0) ? nodata : emax;                        // kMaxFSL :187-196
+    case 2: return (eta < bed + 1E-8 || bed > 9999.0) ? nodata : eta;                           // kFreeSurfaceLevel :197-206
+    case 9: { const double d = fmax(0.0, emax - bed); return (d < 1E-8 || d <= -9990.0 || d >= 9999.0) ? nodata : d; }   // kMaxDepth :207-213
+    case 1: { const double d = fmax(0.0, depth); return d < 1E-8 ? nodata : d; }                // kDepth :214-220
+    case 5: return qx * res;                                                                    // kDischargeX :221-226
+    case 6: return qy * res;                                                                    // kDischargeY :227-232
+    case 3: return depth > 1E-8 ? qx / depth : nodata;                                          // kVelocityX :233-242
+    case 4: return depth > 1E-8 ? qy / depth : nodata;                                          // kVelocityY :243-252
+    case 11: { const double u = qx / depth, v = qy / depth;                                     // kFroudeNumber :253-266
+               return depth > 1E-8 ? sqrt(u * u + v * v) / sqrt(9.81 * depth) : nodata; }
+    default: return nodata;                                                                     // :183 (row pre-filled with -9999)
+    }
+}
+
+template <class R> __global__ void __launch_bounds__(256) derive_raster_kernel(Planes p, const R* __restrict__ bed, double* __restrict__ out,
+                                                                                Grid g, int row_end, int nrows, int value, double res,
+                                                                                double nodata) {
+    const View<R> s(p);
+    const long long n = static_cast<long long>(nrows) * g.cols;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int r = static_cast<int>(i / g.cols), x = static_cast<int>(i % g.cols);      // r = 0 is the northernmost row
+        const size_t id = static_cast<size_t>(row_end - 1 - r) * g.pitch + x;
+        out[i] = derive_output(value, static_cast<double>(s.eta[id]), static_cast<double>(s.emax[id]), static_cast<double>(s.qx[id]),
+                               static_cast<double>(s.qy[id]), static_cast<double>(bed[id]), res, nodata);
+    }
+}
+
 }  // namespace HP_NS
 
 #ifndef HP_FLAVOUR_STRICT
@@ -515,6 +554,14 @@ static int launch_copy_plane_rows(int real_bytes, const void* dense, void* plane
     return 1;
 }
 
+static int launch_derive_raster(int real_bytes, Planes src, const void* bed, double* out, Grid g, int row_end, int nrows, int value,
+                                double resolution, double nodata, cudaStream_t st) {
+    const int grid = stride_grid(static_cast<long long>(nrows) * g.cols, 256, 8);
+    if (real_bytes == 8) derive_raster_kernel<double><<<grid, 256, 0, st>>>(src, static_cast<const double*>(bed), out, g, row_end, nrows, value, resolution, nodata);
+    else derive_raster_kernel<float><<<grid, 256, 0, st>>>(src, static_cast<const float*>(bed), out, g, row_end, nrows, value, resolution, nodata);
+    return 1;
+}
+
 static const hp::KernelTable g_table = {
 #ifndef HP_FLAVOUR_STRICT
     launch_step_tma, launch_step_march,
@@ -522,7 +569,7 @@ static const hp::KernelTable g_table = {
     nullptr, nullptr,
 #endif
     launch_step, launch_reduce_only, launch_advance, launch_update_timestep, launch_bdy_uniform, launch_bdy_gridded,
-    launch_bdy_cell, launch_aos_to_soa, launch_soa_to_aos, launch_copy_plane_rows,
+    launch_bdy_cell, launch_aos_to_soa, launch_soa_to_aos, launch_copy_plane_rows, launch_derive_raster,
 };
 
 }  // namespace HP_NS

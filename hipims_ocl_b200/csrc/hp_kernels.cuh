@@ -109,6 +109,10 @@ struct KernelTable {
     int (*aos_to_soa)(int real_bytes, const void* aos, Planes dst, Grid g, int row0, int nrows, cudaStream_t st);
     int (*soa_to_aos)(int real_bytes, Planes src, void* aos, Grid g, int row0, int nrows, cudaStream_t st);
     int (*copy_plane_rows)(int real_bytes, const void* dense, void* plane, Grid g, int row0, int nrows, cudaStream_t st);
+    // output rasters (CRasterDataset::domainToRaster): `nrows` local rows ending below row `row_end`, written
+    // NORTH row first into `out` (nrows x cols doubles)
+    int (*derive_raster)(int real_bytes, Planes src, const void* bed, double* out, Grid g, int row_end, int nrows, int value,
+                         double resolution, double nodata, cudaStream_t st);
 };
 
 const KernelTable& strict_kernels();

@@ -83,6 +83,7 @@ ABI = {
     "hp_scheme_download_cells": (C.c_int, [_VP, _VP]),
     "hp_scheme_download_both": (C.c_int, [_VP, _VP, _VP]),
     "hp_scheme_read_rows": (C.c_int, [_VP, C.c_uint64, C.c_uint64, _VP]),
+    "hp_scheme_derive_raster": (C.c_int, [_VP, C.c_uint32, C.c_double, _VP]),
     "hp_scheme_write_rows": (C.c_int, [_VP, C.c_uint64, C.c_uint64, _VP]),
     "hp_scheme_set_target_time": (C.c_int, [_VP, C.c_double]),
     "hp_scheme_force_timestep": (C.c_int, [_VP, C.c_double]),
@@ -179,6 +180,7 @@ class CudaScheme:
         self.ex, self.cfg, self.lib = executor, cfg, executor.lib
         self.dtype = np.float64 if cfg.precision == "double" else np.float32
         self.rows, self.cols = cfg.rows, cfg.cols
+        self.halo_south, self.halo_north = halo_south, halo_north
         c = HpSchemeConfig(struct_size=C.sizeof(HpSchemeConfig), scheme=_SCHEME_ID[cfg.scheme],
                            real_bytes=cfg.real_bytes, quirks=cfg.quirks, options=options,
                            dynamic_timestep=int(cfg.dynamic), friction=int(cfg.friction), cols=cfg.cols, rows=cfg.rows,
@@ -231,6 +233,13 @@ class CudaScheme:
     def read_rows(self, first_row, count):
         out = np.empty((count, self.cols, 4), dtype=self.dtype)
         _check(self.lib.hp_scheme_read_rows(self.h, first_row, count, _ptr(out)))
+        return out
+
+    def derive_raster(self, value, nodata=-9999.0):
+        """One output raster (hp.RASTER_* code or the reference's XML name) of the owned rows, NORTH row first, float64."""
+        code = hc.RASTER_VALUES[value] if isinstance(value, str) else int(value)
+        out = np.empty((self.rows - self.halo_south - self.halo_north, self.cols), dtype=np.float64)
+        _check(self.lib.hp_scheme_derive_raster(self.h, code, float(nodata), _ptr(out)))
         return out
 
     def write_rows(self, first_row, states):

@@ -618,20 +618,133 @@ double CDomainCartesian::deriveOutput(unsigned char code, const double* st, doub
     }
 }
 
-bool CDomainCartesian::writeOutputs(double dTime) {
+bool CDomainCartesian::writeOutputs(double dTime, CScheme* pScheme) {       // src/Domain/Cartesian/CDomainCartesian.cpp:738-767
     bool ok = true;
+    std::vector<double> values;
     for (const auto& o : outputs) {
         const unsigned char code = getDataValueCode(o.sValue);
-        SRaster r; r.cols = ulCols; r.rows = ulRows; r.cellsize = dCellResolution; r.xll = dRealOffsetX; r.yll = dRealOffsetY; r.nodata = -9999.0;
-        r.values.resize(getCellCount());
-        for (unsigned long i = 0; i < getCellCount(); ++i) r.values[i] = deriveOutput(code, &dCellStates[4 * i], dBedElevations[i], dCellResolution, -9999.0);
+        if (!(pScheme && pScheme->deriveRaster(code, values))) {
+            values.resize(getCellCount());
+            for (unsigned long y = 0; y < ulRows; ++y)
+                for (unsigned long x = 0; x < ulCols; ++x) {
+                    const unsigned long i = getCellID(x, y);
+                    values[(ulRows - 1 - y) * ulCols + x] = deriveOutput(code, &dCellStates[4 * i], dBedElevations[i], dCellResolution, -9999.0);
+                }
+        }
         std::string file = o.sTarget; const size_t pos = file.find("%t");
         char tbuf[64]; snprintf(tbuf, sizeof(tbuf), "%g", std::floor(dTime * 100.0) / 100.0);   // "%t" -> floor(t*100)/100
         if (pos != std::string::npos) file.replace(pos, 2, tbuf);
-        const size_t dot = file.find_last_of('.');
-        if (o.sFormat != "AAIGrid") file = (dot == std::string::npos ? file : file.substr(0, dot)) + ".asc";   // GDAL drivers are not available
-        ok = r.write(sTargetDir + file) && ok;
+        ok = CRasterDataset::writeRaster(o.sFormat, sTargetDir + file, ulCols, ulRows, dRealOffsetX, dRealOffsetY, dCellResolution, values.data()) && ok;
     }
+    return ok;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Raster writers
+// ---------------------------------------------------------------------------------------------
+namespace {
+template <class T> void put(std::vector<unsigned char>& b, T v) { const unsigned char* p = reinterpret_cast<const unsigned char*>(&v); b.insert(b.end(), p, p + sizeof(T)); }
+
+// Uncompressed single-band Float64 GeoTIFF, little endian, one strip per row; classic TIFF below 4 GB, BigTIFF above
+// (what GDAL's GTiff driver produces with its defaults and BIGTIFF=IF_NEEDED).
+bool writeGeoTIFF(const std::string& path, unsigned long cols, unsigned long rows, double ulx, double uly, double res, const double* data) {
+    const uint64_t row_bytes = static_cast<uint64_t>(cols) * 8, image_bytes = row_bytes * rows;
+    const bool big = image_bytes + 65536 + 16ull * rows >= 0xFFFFFFF0ull;
+    struct Entry { uint16_t tag, type; uint64_t count; std::vector<unsigned char> payload; };
+    std::vector<Entry> ifd;
+    auto add_short = [&](uint16_t tag, uint16_t v) { Entry e{tag, 3, 1, {}}; put<uint16_t>(e.payload, v); ifd.push_back(e); };
+    auto add_long = [&](uint16_t tag, uint64_t v) { Entry e{tag, static_cast<uint16_t>(big ? 16 : 4), 1, {}}; if (big) put<uint64_t>(e.payload, v); else put<uint32_t>(e.payload, static_cast<uint32_t>(v)); ifd.push_back(e); };
+    auto add_doubles = [&](uint16_t tag, std::initializer_list<double> v) { Entry e{tag, 12, v.size(), {}}; for (double d : v) put<double>(e.payload, d); ifd.push_back(e); };
+    auto add_shorts = [&](uint16_t tag, std::initializer_list<uint16_t> v) { Entry e{tag, 3, v.size(), {}}; for (uint16_t d : v) put<uint16_t>(e.payload, d); ifd.push_back(e); };
+    auto add_ascii = [&](uint16_t tag, const std::string& t) { Entry e{tag, 2, t.size() + 1, {}}; e.payload.assign(t.begin(), t.end()); e.payload.push_back(0); ifd.push_back(e); };
+    const uint64_t header = big ? 16 : 8;
+    const uint64_t data_off = header;                                   // pixel data first, IFD after it
+    add_long(256, cols); add_long(257, rows); add_short(258, 64); add_short(259, 1); add_short(262, 1);
+    { Entry e{273, static_cast<uint16_t>(big ? 16 : 4), rows, {}};
+      for (unsigned long r = 0; r < rows; ++r) { if (big) put<uint64_t>(e.payload, data_off + r * row_bytes); else put<uint32_t>(e.payload, static_cast<uint32_t>(data_off + r * row_bytes)); }
+      ifd.push_back(e); }
+    add_short(277, 1); add_long(278, 1);
+    { Entry e{279, static_cast<uint16_t>(big ? 16 : 4), rows, {}};
+      for (unsigned long r = 0; r < rows; ++r) { if (big) put<uint64_t>(e.payload, row_bytes); else put<uint32_t>(e.payload, static_cast<uint32_t>(row_bytes)); }
+      ifd.push_back(e); }
+    add_short(284, 1); add_short(339, 3);
+    add_doubles(33550, {res, res, 0.0});                                // ModelPixelScaleTag
+    add_doubles(33922, {0.0, 0.0, 0.0, ulx, uly, 0.0});                 // ModelTiepointTag: pixel (0,0) = upper-left corner
+    add_shorts(34735, {1, 1, 0, 1, 1025, 0, 1, 1});                     // GeoKeyDirectory: GTRasterTypeGeoKey = RasterPixelIsArea
+    add_ascii(42113, "-9999");                                          // GDAL_NODATA
+    FILE* f = fopen(path.c_str(), "wb");
+    if (!f) return false;
+    std::vector<unsigned char> head;
+    head.push_back('I'); head.push_back('I');
+    const uint64_t ifd_off = (data_off + image_bytes + 7) / 8 * 8;
+    if (big) { put<uint16_t>(head, 43); put<uint16_t>(head, 8); put<uint16_t>(head, 0); put<uint64_t>(head, ifd_off); }
+    else { put<uint16_t>(head, 42); put<uint32_t>(head, static_cast<uint32_t>(ifd_off)); }
+    bool ok = fwrite(head.data(), 1, head.size(), f) == head.size();
+    ok = ok && fwrite(data, 1, image_bytes, f) == image_bytes;
+    for (uint64_t p = data_off + image_bytes; p < ifd_off && ok; ++p) ok = fputc(0, f) != EOF;
+    // IFD: entries sorted by tag (they are added in ascending order), out-of-line payloads behind the table
+    const uint64_t entry_size = big ? 20 : 12, inline_cap = big ? 8 : 4;
+    const uint64_t table_bytes = (big ? 8 : 2) + entry_size * ifd.size() + (big ? 8 : 4);
+    uint64_t extra_off = ifd_off + table_bytes;
+    std::vector<unsigned char> table, extra;
+    if (big) put<uint64_t>(table, ifd.size()); else put<uint16_t>(table, static_cast<uint16_t>(ifd.size()));
+    for (auto& e : ifd) {
+        put<uint16_t>(table, e.tag); put<uint16_t>(table, e.type);
+        if (big) put<uint64_t>(table, e.count); else put<uint32_t>(table, static_cast<uint32_t>(e.count));
+        if (e.payload.size() <= inline_cap) {
+            std::vector<unsigned char> v = e.payload; v.resize(inline_cap, 0);
+            table.insert(table.end(), v.begin(), v.end());
+        } else {
+            if (big) put<uint64_t>(table, extra_off + extra.size()); else put<uint32_t>(table, static_cast<uint32_t>(extra_off + extra.size()));
+            extra.insert(extra.end(), e.payload.begin(), e.payload.end());
+            while (extra.size() % 8) extra.push_back(0);
+        }
+    }
+    if (big) put<uint64_t>(table, 0); else put<uint32_t>(table, 0);     // no further IFD
+    ok = ok && fwrite(table.data(), 1, table.size(), f) == table.size();
+    ok = ok && (extra.empty() || fwrite(extra.data(), 1, extra.size(), f) == extra.size());
+    return fclose(f) == 0 && ok;
+}
+
+bool writeENVI(const std::string& path, unsigned long cols, unsigned long rows, double ulx, double uly, double res, const double* data) {
+    FILE* f = fopen(path.c_str(), "wb");
+    if (!f) return false;
+    const size_t n = static_cast<size_t>(cols) * rows;
+    bool ok = fwrite(data, sizeof(double), n, f) == n;
+    ok = fclose(f) == 0 && ok;
+    const size_t dot = path.find_last_of('.'), slash = path.find_last_of('/');
+    const std::string hdr = ((dot == std::string::npos || (slash != std::string::npos && dot < slash)) ? path : path.substr(0, dot)) + ".hdr";
+    f = fopen(hdr.c_str(), "w");
+    if (!f) return false;
+    fprintf(f, "ENVI\ndescription = {%s}\nsamples = %lu\nlines   = %lu\nbands   = 1\nheader offset = 0\nfile type = ENVI Standard\n"
+               "data type = 5\ninterleave = bsq\nbyte order = 0\nmap info = {Arbitrary, 1, 1, %.10g, %.10g, %.10g, %.10g}\n"
+               "data ignore value = -9999\nband names = {Band 1}\n", path.c_str(), cols, rows, ulx, uly, res, res);
+    return fclose(f) == 0 && ok;
+}
+}  // namespace
+
+bool CRasterDataset::writeRaster(const std::string& sFormat, const std::string& sFilename, unsigned long cols, unsigned long rows, double offX,
+                                 double offY, double res, const double* northFirst, std::string* pWritten) {
+    const double ulx = offX, uly = offY + res * rows;                   // top-left instead of bottom-left, CRasterDataset.cpp:166
+    std::string file = sFilename;
+    bool ok;
+    if (sFormat == "AAIGrid") {
+        SRaster r; r.cols = cols; r.rows = rows; r.cellsize = res; r.xll = offX; r.yll = offY; r.nodata = -9999.0;
+        r.values.resize(static_cast<size_t>(cols) * rows);
+        for (unsigned long y = 0; y < rows; ++y) std::copy(northFirst + (rows - 1 - y) * cols, northFirst + (rows - y) * cols, r.values.begin() + y * cols);
+        ok = r.write(file);
+    } else if (sFormat == "ENVI") {
+        ok = writeENVI(file, cols, rows, ulx, uly, res, northFirst);
+    } else {
+        if (sFormat != "GTiff") {
+            model::doError("GDAL format driver '" + sFormat + "' is not available in this build: writing GeoTIFF instead.", model::errorCodes::kLevelWarning);
+            const size_t dot = file.find_last_of('.'), slash = file.find_last_of('/');
+            file = ((dot == std::string::npos || (slash != std::string::npos && dot < slash)) ? file : file.substr(0, dot)) + ".tif";
+        }
+        ok = writeGeoTIFF(file, cols, rows, ulx, uly, res, northFirst);
+    }
+    if (!ok) model::doError("Could not create output raster file.", model::errorCodes::kLevelWarning);     // CRasterDataset.cpp:155-161
+    if (pWritten) *pWritten = file;
     return ok;
 }
 
@@ -730,6 +843,12 @@ void CScheme::readDomainAll() {
         HP_CHECK(hp_scheme_download_cells(pScheme, pDomain->dCellStates.data()), "download");
     }
 }
+bool CScheme::deriveRaster(unsigned char ucValue, std::vector<double>& northFirst) {
+    if (!pScheme) return false;
+    northFirst.resize(pDomain->getCellCount());
+    if (hp_scheme_derive_raster(pScheme, ucValue, -9999.0, northFirst.data()) < 0) { model::doError(hp_last_error(), model::errorCodes::kLevelWarning); return false; }
+    return true;
+}
 void CScheme::forceTimestep(double dt) { if (pScheme) HP_CHECK(hp_scheme_force_timestep(pScheme, dt), "force timestep"); }
 void CScheme::cleanupSimulation() { if (pScheme) { hp_scheme_destroy(pScheme); pScheme = nullptr; } }
 
@@ -787,10 +906,10 @@ bool CModel::runModel() {
     while (!model::forceAbort && pScheme->getCurrentTime() < dSimulationTime - 1E-5) {
         const double target = std::min(nextOutput, dSimulationTime);
         while (!model::forceAbort && pScheme->getCurrentTime() < target - 1E-5) pScheme->runSimulation(target, 0.0);
-        pScheme->readDomainAll();
-        pDomain->writeOutputs(pScheme->getCurrentTime());
+        pDomain->writeOutputs(pScheme->getCurrentTime(), pScheme.get());      // derived on the device; no full-state read-back
         nextOutput += dOutputFrequency > 0.0 ? dOutputFrequency : dSimulationTime;
     }
+    pScheme->readDomainAll();                                              // final state back in the CDomain arrays
     return !model::forceAbort;
 }
 
@@ -850,6 +969,13 @@ void hph_free(void* p) { free(p); }
 int hph_error_count(void) { return static_cast<int>(model::errorLog.size()); }
 const char* hph_error(int i) { return (i >= 0 && i < static_cast<int>(model::errorLog.size())) ? model::errorLog[i].c_str() : ""; }
 double hph_round(double v, int places) { return Util::round(v, static_cast<unsigned char>(places)); }
+int hph_write_raster(const char* format, const char* path, unsigned long cols, unsigned long rows, double off_x, double off_y, double res,
+                     const double* north_first, char* written, size_t written_len) {
+    std::string out;
+    const bool ok = CRasterDataset::writeRaster(format, path, cols, rows, off_x, off_y, res, north_first, &out);
+    if (written && written_len) { strncpy(written, out.c_str(), written_len - 1); written[written_len - 1] = 0; }
+    return ok ? 0 : -1;
+}
 double hph_derive_output(const char* value, const double* state4, double bed, double resolution) {
     return CDomainCartesian::deriveOutput(CDomainCartesian::getDataValueCode(value), state4, bed, resolution, -9999.0);
 }

@@ -81,6 +81,18 @@ struct SRaster {
     bool write(const std::string& path) const;
 };
 
+// GDAL-free stand-in for the writing half of CRasterDataset (src/Datasets/CRasterDataset.cpp:101-287): one
+// Float64 band, no-data -9999, geotransform {xll, res, 0, yll + res * rows, 0, -res} (:163-170).  `format` keeps
+// GDAL's driver codes: "GTiff" (uncompressed GeoTIFF, BigTIFF above 4 GB), "ENVI" (raw little-endian + .hdr),
+// "AAIGrid" (ESRI ASCII).  Other codes (e.g. "HFA") are reported through doError(kLevelWarning) like a driver
+// that cannot create files (:129-146) and written as GeoTIFF next to the requested name.
+class CRasterDataset {
+  public:
+    // `northFirst`: rows x cols values, row 0 = northern edge (raster order)
+    static bool writeRaster(const std::string& sFormat, const std::string& sFilename, unsigned long ulCols, unsigned long ulRows,
+                            double dOffsetX, double dOffsetY, double dResolution, const double* northFirst, std::string* pWritten = nullptr);
+};
+
 namespace Util {
 double round(double value, unsigned char places);   // src/util.cpp:79-93 (negatives go towards -inf)
 std::string toLowercase(const char* s);
@@ -179,7 +191,9 @@ class CDomainCartesian {
     void handleInputData(unsigned long ulCellID, double dValue, unsigned char ucValue, unsigned char ucRounding);
     static unsigned char getDataValueCode(const std::string& sLower);
     double getVolume() const;
-    bool writeOutputs(double dTime);                       // derives depth / velocity / fsl / maxdepth / ... rasters
+    // derives depth / velocity / fsl / maxdepth / ... rasters: on the device through pScheme when given (one
+    // 8-byte value per cell crosses PCIe instead of the whole state), else from the host arrays
+    bool writeOutputs(double dTime, CScheme* pScheme = nullptr);
     static double deriveOutput(unsigned char ucValue, const double* state, double bed, double resolution, double nodata);
     CBoundaryMap* getBoundaries() { return &boundaryMap; }
     // host cell arrays, reference layout (src/Domain/CDomain.h:28-33); always double on the host side
@@ -209,6 +223,7 @@ class CScheme {
     void readKeyStatistics();
     void readDomainAll();                              // device -> CDomain host arrays
     void saveCurrentState() { readDomainAll(); }
+    bool deriveRaster(unsigned char ucValue, std::vector<double>& northFirst);   // hp_scheme_derive_raster
     void forceTimestep(double dTimestep);
     void cleanupSimulation();
     bool isReady() const { return pScheme != nullptr; }

@@ -199,6 +199,16 @@ int  hp_scheme_download_both(hp_scheme* s, void* states_a, void* states_b);
 /* COCLBuffer::queueReadPartial / queueWritePartial on whole rows of the next source buffer, as
  * CDomainLink::pullFromBuffer / pushToBuffer use them (src/Domain/Links/CDomainLink.cpp:168-197,
  * 252-270).  `first_row` is local to this scheme. */
+/* Output rasters.  Replaces the full-state read-back + host loop of CRasterDataset::domainToRaster
+ * (src/Datasets/CRasterDataset.cpp:180-280; called from CDomainCartesian::writeOutputs,
+ * src/Domain/Cartesian/CDomainCartesian.cpp:738-767): derives one output value per cell on the device, in
+ * double and with the reference's no-data rules, and writes the OWNED rows in raster order -- NORTH row first,
+ * (rows - halos) x cols doubles -- to `out`.  `value` is a model::rasterDatasets::dataValues code
+ * (src/Datasets/CRasterDataset.h:33-46): HP_RASTER_*.  Synchronous. */
+enum { HP_RASTER_DEPTH = 1, HP_RASTER_FSL = 2, HP_RASTER_VELOCITY_X = 3, HP_RASTER_VELOCITY_Y = 4, HP_RASTER_DISCHARGE_X = 5,
+       HP_RASTER_DISCHARGE_Y = 6, HP_RASTER_MAX_DEPTH = 9, HP_RASTER_MAX_FSL = 10, HP_RASTER_FROUDE = 11 };
+int  hp_scheme_derive_raster(hp_scheme* s, uint32_t value, double nodata, double* out);
+
 int  hp_scheme_read_rows(hp_scheme* s, uint64_t first_row, uint64_t row_count, void* states);
 int  hp_scheme_write_rows(hp_scheme* s, uint64_t first_row, uint64_t row_count, const void* states);
 

@@ -36,8 +36,8 @@ XML = """<?xml version="1.0"?>
 					<dataSource type="constant" value="depth" source="0.0" />
 					<dataSource type="constant" value="manningCoefficient" source="0.030" />
 					<dataSource type="raster" value="structure,dem" source="dem.asc" />
-					<dataTarget type="raster" value="depth" format="HFA" target="depth_%t.img" />
-					<dataTarget type="raster" value="velocityX" format="HFA" target="velX_%t.img" />
+					<dataTarget type="raster" value="depth" format="GTiff" target="depth_%t.tif" />
+					<dataTarget type="raster" value="velocityX" format="ENVI" target="velX_%t.bil" />
 					<dataTarget type="raster" value="fsl" format="AAIGrid" target="fsl_%t.asc" />
 					<dataTarget type="raster" value="maxdepth" format="HFA" target="maxdepth_%t.img" />
 				</data>
@@ -77,6 +77,52 @@ def read_asc(path):
             hdr[k.lower()] = float(v)
         data = np.loadtxt(f)
     return data[::-1], hdr
+
+
+def read_tiff(path):
+    """Minimal reader for what CRasterDataset::writeRaster("GTiff") produces: little-endian classic TIFF or BigTIFF,
+    uncompressed strips.  Returns (array, tags)."""
+    import struct
+    raw = open(path, "rb").read()
+    assert raw[:2] == b"II"
+    magic = struct.unpack_from("<H", raw, 2)[0]
+    big = magic == 43
+    assert magic in (42, 43)
+    if big:
+        assert struct.unpack_from("<HH", raw, 4) == (8, 0)
+        off = struct.unpack_from("<Q", raw, 8)[0]
+        n = struct.unpack_from("<Q", raw, off)[0]; off += 8; esz = 20
+    else:
+        off = struct.unpack_from("<I", raw, 4)[0]
+        n = struct.unpack_from("<H", raw, off)[0]; off += 2; esz = 12
+    sizes = {2: 1, 3: 2, 4: 4, 12: 8, 16: 8}
+    fmts = {2: "c", 3: "H", 4: "I", 12: "d", 16: "Q"}
+    tags, last = {}, 0
+    for i in range(n):
+        tag, typ = struct.unpack_from("<HH", raw, off + i * esz)
+        assert tag > last; last = tag                                   # ascending, as the TIFF specification requires
+        cnt = struct.unpack_from("<Q" if big else "<I", raw, off + i * esz + 4)[0]
+        voff = off + i * esz + (12 if big else 8)
+        if cnt * sizes[typ] > (8 if big else 4):
+            voff = struct.unpack_from("<Q" if big else "<I", raw, voff)[0]
+        vals = struct.unpack_from("<%d%s" % (cnt, fmts[typ]), raw, voff)
+        tags[tag] = b"".join(vals).rstrip(b"\0").decode() if typ == 2 else list(vals)
+    cols, rows = tags[256][0], tags[257][0]
+    assert tags[258] == [64] and tags[259] == [1] and tags[277] == [1] and tags[339] == [3] and tags[278] == [1]
+    data = np.empty((rows, cols))
+    for r, (o, c) in enumerate(zip(tags[273], tags[279])):
+        assert c == cols * 8
+        data[r] = np.frombuffer(raw, dtype="<f8", count=cols, offset=o)
+    return data, tags
+
+
+def read_envi(path):
+    hdr = {}
+    for line in open(os.path.splitext(path)[0] + ".hdr").read().splitlines()[1:]:
+        k, _, v = line.partition("=")
+        hdr[k.strip()] = v.strip()
+    assert hdr["data type"] == "5" and hdr["byte order"] == "0" and hdr["interleave"] == "bsq" and hdr["bands"] == "1"
+    return np.fromfile(path, dtype="<f8").reshape(int(hdr["lines"]), int(hdr["samples"])), hdr
 
 
 @pytest.fixture()
@@ -151,6 +197,42 @@ def test_rounding_matches_reference_util_round(host):
     assert host.hph_round(-1.23451, 4) == -1.2346 and host.hph_round(-0.00001, 4) == -0.0001
     for v in (3.14159265, -2.000049, 0.00005, 17.99995):
         assert host.hph_round(v, 4) == float(sc.round4(v))
+
+
+def test_raster_writers_round_trip(host, tmp_path):
+    """GeoTIFF / ENVI / ESRI ASCII written by the GDAL-free CRasterDataset stand-in: values bit-exact, georeferencing
+    as src/Datasets/CRasterDataset.cpp:163-176 sets it (top-left origin, negative y resolution, no-data -9999)."""
+    host.hph_write_raster.argtypes = [C.c_char_p, C.c_char_p, C.c_ulong, C.c_ulong, C.c_double, C.c_double, C.c_double,
+                                      C.POINTER(C.c_double), C.c_char_p, C.c_size_t]
+    rng = np.random.default_rng(3)
+    rows, cols, res, xll, yll = 37, 53, 2.0, 424520.0, 565146.0
+    a = rng.normal(size=(rows, cols))
+    a[rng.random((rows, cols)) < 0.3] = -9999.0
+    ptr = a.ctypes.data_as(C.POINTER(C.c_double))
+    written = C.create_string_buffer(512)
+    for fmt, name in (("GTiff", "a.tif"), ("ENVI", "b.bil"), ("AAIGrid", "c.asc"), ("HFA", "d.img")):
+        before = host.hph_error_count()
+        assert host.hph_write_raster(fmt.encode(), str(tmp_path / name).encode(), cols, rows, xll, yll, res, ptr, written, 512) == 0
+        path = written.value.decode()
+        if fmt == "HFA":                                     # no such driver here: warned, GeoTIFF written instead
+            assert path.endswith("d.tif") and host.hph_error_count() == before + 1
+            assert b"not available" in host.hph_error(before)
+        else:
+            assert path.endswith(name) and host.hph_error_count() == before
+        if path.endswith(".tif"):
+            got, tags = read_tiff(path)
+            assert tags[33550] == [res, res, 0.0] and tags[33922] == [0.0, 0.0, 0.0, xll, yll + res * rows, 0.0]
+            assert tags[42113] == "-9999" and tags[34735][:4] == [1, 1, 0, 1]
+        elif path.endswith(".bil"):
+            got, hdr = read_envi(path)
+            assert hdr["map info"] == "{Arbitrary, 1, 1, %.10g, %.10g, %.10g, %.10g}" % (xll, yll + res * rows, res, res)
+            assert hdr["data ignore value"] == "-9999"
+        else:
+            south_first, hdr = read_asc(path)
+            got = south_first[::-1]
+            assert hdr["xllcorner"] == xll and hdr["yllcorner"] == yll and hdr["cellsize"] == res
+        np.testing.assert_array_equal(got, a)
+    assert host.hph_write_raster(b"GTiff", str(tmp_path / "no" / "dir.tif").encode(), cols, rows, xll, yll, res, ptr, written, 512) == -1
 
 
 def test_output_value_derivation(host):
@@ -261,10 +343,19 @@ def test_model_run_matches_oracle_driven_the_same_way(host, model_dir, scheme, n
     assert np.abs(st1[..., 2:] - want[..., 2:]).max() <= 1e-7
     # rasters: derived exactly as CRasterDataset::domainToRaster does, written north-first, every 10 s
     out = os.path.join(os.path.dirname(cfg), "output")
-    assert sorted(os.listdir(out)) == sorted("%s_%d.asc" % (v, k) for v in ("depth", "velX", "fsl", "maxdepth") for k in (10, 20, 30))
-    depth, hdr = read_asc(os.path.join(out, "depth_30.asc"))
-    expect = np.maximum(st1[..., 0] - bed, 0.0)
-    expect = np.where(expect < 1e-8, -9999.0, expect)
-    np.testing.assert_allclose(depth, expect, rtol=0, atol=1e-15)
+    # (derived on the device by hp_scheme_derive_raster; maxdepth asks for the HFA driver and falls back to GeoTIFF)
+    from oracle import raster_oracle as ro
+    out = os.path.join(os.path.dirname(cfg), "output")
+    names = ["depth_%d.tif", "velX_%d.bil", "velX_%d.hdr", "fsl_%d.asc", "maxdepth_%d.tif"]
+    assert sorted(os.listdir(out)) == sorted(n % k for n in names for k in (10, 20, 30))
+    depth, tags = read_tiff(os.path.join(out, "depth_30.tif"))
+    np.testing.assert_array_equal(depth, ro.derive_raster(ro.DEPTH, st1, bed, 2.0))
+    assert tags[33550][:2] == [2.0, 2.0] and tags[42113] == "-9999"
+    velx, _ = read_envi(os.path.join(out, "velX_30.bil"))
+    np.testing.assert_array_equal(velx, ro.derive_raster(ro.VELOCITY_X, st1, bed, 2.0))
+    fsl, hdr = read_asc(os.path.join(out, "fsl_30.asc"))
+    np.testing.assert_array_equal(fsl[::-1], ro.derive_raster(ro.FSL, st1, bed, 2.0))
     assert hdr["cellsize"] == 2.0 and hdr["nodata_value"] == -9999.0
+    maxd, _ = read_tiff(os.path.join(out, "maxdepth_30.tif"))
+    np.testing.assert_array_equal(maxd, ro.derive_raster(ro.MAX_DEPTH, st1, bed, 2.0))
     host.hph_model_destroy(C.c_void_p(h))

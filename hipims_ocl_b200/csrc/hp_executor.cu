@@ -630,7 +630,9 @@ int hp_scheme_iterate(hp_scheme* s, uint32_t iterations) {
     if (!s) return fail(HP_ERR_INVALID, "scheme is null");
     HP_CUDA(cudaSetDevice(s->ex->device));
     uint32_t left = iterations;
-    const bool use_graph = !(s->cfg.options & HP_OPT_NO_GRAPH) && s->comm == nullptr;
+    // with a communicator the halo send/recv, the all-reduce and the fork/join onto the communication stream are
+    // captured too (NCCL records its kernels into the graph), so a strip costs one graph launch per 16 iterations
+    const bool use_graph = !(s->cfg.options & HP_OPT_NO_GRAPH);
     int rc = HP_OK;
     auto direct = [&]() {
         int launched = 0;

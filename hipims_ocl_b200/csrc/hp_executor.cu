@@ -453,10 +453,10 @@ int hp_scheme_create(hp_executor* ex, const hp_scheme_config* cfg, hp_scheme** o
         if ((rc = dev_alloc(s, reinterpret_cast<char**>(&s->staging), s->staging_bytes))) break;
         if ((rc = write_clock(s, 0.0, cfg->initial_timestep, 0.0, 0.0))) break;
         // TMA-staged kernels: the fast flavour's Godunov step (others use the plain-load kernels)
-        s->use_tma = s->K->step_tma != nullptr && !(cfg->options & HP_OPT_NO_TMA) &&
-                     (cfg->scheme == HP_SCHEME_GODUNOV || cfg->scheme == HP_SCHEME_MUSCL_HANCOCK);
+        s->use_tma = s->K->step_tma != nullptr && !(cfg->options & HP_OPT_NO_TMA);
         s->use_march = s->use_tma && s->K->step_march != nullptr &&
-                       ((cfg->scheme == HP_SCHEME_MUSCL_HANCOCK && !(cfg->options & HP_OPT_TILE_KERNELS)) ||
+                       (cfg->scheme == HP_SCHEME_INERTIAL ||
+                        (cfg->scheme == HP_SCHEME_MUSCL_HANCOCK && !(cfg->options & HP_OPT_TILE_KERNELS)) ||
                         (cfg->scheme == HP_SCHEME_GODUNOV && (cfg->options & HP_OPT_MARCH_GODUNOV)));
         if (s->use_tma && (rc = build_tma_maps(s))) break;
     } while (0);

@@ -464,6 +464,7 @@ static int launch_step_march(int scheme, int real_bytes, const StepArgs& a, cons
     const TmaBlockMap& m = *reinterpret_cast<const TmaBlockMap*>(maps);
     if (scheme == 0) return real_bytes == 8 ? launch_godunov_march<double>(a, m, alt, sm_count, st) : launch_godunov_march<float>(a, m, alt, sm_count, st);
     if (scheme == 1) return real_bytes == 8 ? launch_mh_march<double>(a, m, alt, sm_count, st) : launch_mh_march<float>(a, m, alt, sm_count, st);
+    if (scheme == 2) return real_bytes == 8 ? launch_inertial_march<double>(a, m, alt, sm_count, st) : launch_inertial_march<float>(a, m, alt, sm_count, st);
     return -1;
 }
 #endif

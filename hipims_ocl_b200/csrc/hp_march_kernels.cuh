@@ -523,6 +523,194 @@ godunov_step_march(const StepArgs a, const __grid_constant__ TmaBlockMap maps) {
     block_reduce_finalize<R>(ws, a, k);
 }
 
+// =============================================================================================
+// Partial inertial scheme, marching.  A face's discharge is stored at its northern / eastern cell
+// (CLSchemeInertial.clc:141-152) and both cells of a face evaluate the same flux -- except for the
+// Manning coefficient, which each takes from ITSELF (:107-110).  So a face is evaluated once up to
+// the friction denominator, which is then applied per owner (once more only where n differs).
+// =============================================================================================
+template <class R> struct InFace { R num, A, qmax; bool wet; };
+
+// calculateInertialFlux (CLSchemeInertial.clc:335-378) without the owner's Manning coefficient:
+// q(n) = clamp((prev - g dt h S) / (1 + g dt n^2 |prev| / h^(7/3)), +-0.8 h sqrt(g h)), 0 if h < eps
+template <class R>
+__device__ __forceinline__ InFace<R> inertial_face(const Params<R>& k, R gdt, R prev, R etaUp, R zUp, R etaDown, R zDown, R inv_delta) {
+    InFace<R> f;
+    const R h = fm_max(etaDown, etaUp) - fm_max(zUp, zDown);
+    f.wet = !(h < k.eps);
+    f.num = R(0); f.A = R(0); f.qmax = R(0);
+    if (f.wet) {
+        const R rh = fm_rcp(h);
+        f.num = prev - gdt * h * ((etaDown - etaUp) * inv_delta);
+        f.A = gdt * hp_abs(prev) * rh * rh * fm_rcbrt(h);
+        f.qmax = R(0.8) * h * fm_sqrt(k.g * h);
+    }
+    return f;
+}
+template <class R> __device__ __forceinline__ R inertial_q(const InFace<R>& f, R n) {
+    if (!f.wet) return R(0);
+    const R q = f.num * fm_rcp(R(1.0) + f.A * (n * n));
+    return q > f.qmax ? f.qmax : (q < -f.qmax ? -f.qmax : q);
+}
+
+#ifndef HP_MARCH_INE_CTAS64
+#define HP_MARCH_INE_CTAS64 6
+#endif
+template <class R, bool ALT>
+__global__ void __launch_bounds__(hp::kMarchWarps * 32, sizeof(R) == 8 ? HP_MARCH_INE_CTAS64 : 8)
+inertial_step_march(const StepArgs a, const __grid_constant__ TmaBlockMap maps) {
+    using T = March<R, 1, ALT>;
+    constexpr unsigned FULL = 0xffffffffu;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* const ring = smem_raw + warp * T::WARP_BYTES;
+    const uint32_t ring_u = smem_u32(ring);
+    const uint32_t bar_u = smem_u32(smem_raw + T::NW * T::WARP_BYTES) + warp * T::RR * 8;
+    if (lane == 0) {
+#pragma unroll
+        for (int r = 0; r < T::RR; ++r) mbar_init(bar_u + 8 * r, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+
+    const Params<R> k = make_params<R>(a.params);
+    const Grid g = a.grid;
+    const R dt = read_timestep<R>(a.clock);
+    const R inv_delta = fm_rcp(k.delta);
+    const R gdt = k.g * dt;
+    const MutView<R> d(a.dst);
+    const bool stepping = dt > R(0);
+
+    const int nrows = a.y1 - a.y0;
+    const int nstrips = (g.cols + T::USE - 1) / T::USE;
+    const int ngroups = (nstrips + T::NW - 1) / T::NW;
+    const long long units = static_cast<long long>(ngroups) * nrows;
+    long long u = units * blockIdx.x / gridDim.x;
+    const long long u1 = units * (blockIdx.x + 1) / gridDim.x;
+
+    const int lc = (lane + T::PADL) * int(sizeof(R));
+    const int lw = (lane > 0 ? lane - 1 + T::PADL : T::PADL) * int(sizeof(R));
+    auto ld = [&](int row_off, int plane, int col_off) -> R {
+        return *reinterpret_cast<const R*>(ring + row_off + plane * T::PLANE + col_off);
+    };
+    const bool lane_owns = lane >= 1 && lane < 1 + T::USE;
+
+    R ws = R(0);
+    uint32_t ph = 0;
+
+    while (u < u1) {
+        const int grp = static_cast<int>(u / nrows);
+        const int ya = a.y0 + static_cast<int>(u - static_cast<long long>(grp) * nrows);
+        const long long gend = static_cast<long long>(grp + 1) * nrows;
+        const int yb = ya + static_cast<int>((u1 < gend ? u1 : gend) - u);
+        u += yb - ya;
+        const int strip = grp * T::NW + warp;
+        if (strip >= nstrips) continue;
+
+        const int X0 = strip * T::USE - 1;               // column of lane 0
+        const int x = X0 + lane;
+        const int rs = ya - 1;                            // first raw row of this run
+        const int NR = yb - ya + 2;                       // raw rows 0 .. NR-1; rows 1 .. NR-2 are updated
+        const bool x_interior = x >= 1 && x <= g.cols - 2;
+        const bool x_store = lane_owns && x < g.cols;
+        auto issue_row = [&](int j) {
+            const uint32_t bar = bar_u + 8 * (j & (T::RR - 1));
+            mbar_expect_tx(bar, uint32_t(T::ROW_TX));
+            tma_load_3d(ring_u + (j & (T::RR - 1)) * T::SLOT, &maps.block, X0 - T::PADL, rs + j, T::P0, bar);
+        };
+        auto wait_row = [&](int j) {
+            const int s = j & (T::RR - 1);
+            mbar_wait(bar_u + 8 * s, (ph >> s) & 1u);
+            ph ^= 1u << s;
+        };
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < T::RR; ++j) if (j < NR) issue_row(j);
+        }
+        wait_row(0);
+
+        R p_eta = ld(0, T::P_ETA, lc), p_zb = ld(0, T::P_ZB, lc);       // the cell below the face being formed
+        R p_n = ld(0, T::P_N, lc);
+        R qS = R(0);                                                      // flux through the southern face of row j-1, own n
+        bool dry_s = true;
+
+        for (int j = 1; j < NR; ++j) {
+            const int y = rs + j;
+            const int o_m = ((j - 1) & (T::RR - 1)) * T::SLOT, o_c = (j & (T::RR - 1)) * T::SLOT;
+            wait_row(j);
+            const R c_eta = ld(o_c, T::P_ETA, lc), c_zb = ld(o_c, T::P_ZB, lc), c_qy = ld(o_c, T::P_QY, lc), c_n = ld(o_c, T::P_N, lc);
+            const bool dry_p = p_eta - p_zb < k.eps, dry_c = c_eta - c_zb < k.eps;
+            // face between rows y-1 (down) and y (up); its discharge is stored in row y
+            InFace<R> fy{R(0), R(0), R(0), false};
+            if (stepping) fy = inertial_face<R>(k, gdt, c_qy, c_eta, c_zb, p_eta, p_zb, inv_delta);
+            const R qN = inertial_q(fy, p_n);                              // as the cell below sees it (CLSchemeInertial.clc:107)
+            const R qS_next = (c_n == p_n) ? qN : inertial_q(fy, c_n);     // as the cell above sees it (:109)
+
+            if (j >= 2) {
+                const int yc = y - 1, gyc = yc + g.gy0;
+                const R p_qx = ld(o_m, T::P_QX, lc), p_qy = ld(o_m, T::P_QY, lc);
+                // west face of row y-1: own cell is "up", the cell of lane-1 "down"; the discharge is the own qx
+                const R w_n = ld(o_m, T::P_N, lw);
+                InFace<R> fx{R(0), R(0), R(0), false};
+                if (stepping) fx = inertial_face<R>(k, gdt, p_qx, p_eta, p_zb, ld(o_m, T::P_ETA, lw), ld(o_m, T::P_ZB, lw), inv_delta);
+                const R qW = inertial_q(fx, p_n);                          // :110
+                const R qE_for_west = (w_n == p_n) ? qW : inertial_q(fx, w_n);   // the same face as lane-1's eastern one (:108)
+                const R qE = shfl_dn1(qE_for_west);
+                const unsigned drym = __ballot_sync(FULL, dry_p);
+
+                Cell<R> c{p_eta, ld(o_m, T::P_EMAX, lc), p_qx, p_qy};
+                if (a.reduce_mode == hp::kReduceSrc && x_store) {
+                    const R h = c.eta - p_zb;
+                    if (h > k.eps10 && c.emax > R(-9999.0)) {
+                        const R cc = fm_sqrt(k.g * h);
+                        R sp = cc;
+                        if (!k.simplified_speed) { const R rh = fm_rcp(h); sp = fm_max(hp_abs(c.qx * rh), hp_abs(c.qy * rh)) + cc; }
+                        ws = sp > ws ? sp : ws;
+                    }
+                }
+                bool wrote = false;
+                if (x_interior && gyc >= 1 && gyc <= g.grows - 2 && stepping) {         // dt <= 0 returns first (:60-61)
+                    if (c.emax <= R(-9999.0) || c.eta == R(-9999.0)) {
+                        wrote = true;                                                   // disabled cell: copied through
+                    } else {
+                        const bool dry_e = (drym >> ((lane + 1) & 31)) & 1u, dry_w = (drym >> ((lane + 31) & 31)) & 1u;
+                        if (!(dry_p && dry_c && dry_s && dry_e && dry_w)) {             // :92-99
+                            c.qx = qW; c.qy = qS;                                       // :141-142
+                            c.eta = c.eta + dt * ((qE - qW + qN - qS) * inv_delta);     // :145-152
+                            if (c.eta > c.emax) c.emax = c.eta;
+                            if (c.eta - p_zb < k.eps) c.eta = p_zb;
+                            wrote = true;
+                        }
+                    }
+                }
+                if (x_store) {
+                    const size_t id = static_cast<size_t>(yc) * g.pitch + x;
+                    if (wrote) d.store(id, c);
+                    if (a.reduce_mode == hp::kReduceDst) {
+                        if (!wrote) { c.eta = d.eta[id]; c.emax = d.emax[id]; c.qx = d.qx[id]; c.qy = d.qy[id]; }
+                        const R h = c.eta - p_zb;
+                        if (h > k.eps10 && c.emax > R(-9999.0)) {
+                            const R cc = fm_sqrt(k.g * h);
+                            R sp = cc;
+                            if (!k.simplified_speed) { const R rh = fm_rcp(h); sp = fm_max(hp_abs(c.qx * rh), hp_abs(c.qy * rh)) + cc; }
+                            ws = sp > ws ? sp : ws;
+                        }
+                    }
+                }
+            }
+            qS = qS_next; dry_s = dry_p;
+            p_eta = c_eta; p_zb = c_zb; p_n = c_n;
+
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0 && j - 1 + T::RR < NR) issue_row(j - 1 + T::RR);
+        }
+    }
+    block_reduce_finalize<R>(ws, a, k);
+}
+
 static int march_grid(const StepArgs& a, int use, int nw, int ctas_per_sm, int sm_count) {
     const int nrows = a.y1 - a.y0;
     const int nstrips = (a.grid.cols + use - 1) / use, ngroups = (nstrips + nw - 1) / nw;
@@ -565,6 +753,23 @@ template <class R> static int launch_godunov_march(const StepArgs& a_in, const T
     a.total_ctas = grid;
     if (alt) godunov_step_march<R, true><<<grid, T::NW * 32, T::SMEM_BYTES, st>>>(a, maps);
     else godunov_step_march<R, false><<<grid, T::NW * 32, T::SMEM_BYTES, st>>>(a, maps);
+    return 1;
+}
+
+template <class R> static int launch_inertial_march(const StepArgs& a_in, const TmaBlockMap& maps, int alt, int sm_count, cudaStream_t st) {
+    using T = March<R, 1, false>;
+    StepArgs a = a_in;
+    if (a.y1 <= a.y0) return 0;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(inertial_step_march<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES);
+        cudaFuncSetAttribute(inertial_step_march<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES);
+        configured = true;
+    }
+    const int grid = march_grid(a, T::USE, T::NW, sizeof(R) == 8 ? HP_MARCH_INE_CTAS64 : 8, sm_count);
+    a.total_ctas = grid;
+    if (alt) inertial_step_march<R, true><<<grid, T::NW * 32, T::SMEM_BYTES, st>>>(a, maps);
+    else inertial_step_march<R, false><<<grid, T::NW * 32, T::SMEM_BYTES, st>>>(a, maps);
     return 1;
 }
 

@@ -76,12 +76,15 @@ def attach_boundaries(sim, w, cols, total_rows):
         ids = sorted(set(int(y) * cols + int(x) for y, x in pts))
         sim.add_cell(hc.DEPTH_IGNORE, hc.DISCHARGE_IS_VOLUME, ids, [[0.0, 0.0, 0.0, 0.0], [600.0, 0.0, 2.0, 0.0], [1200.0, 0.0, 0.0, 0.0], [1.0e6, 0.0, 0.0, 0.0]])
     elif kind == "river":
-        mid, band = total_rows // 2, max(4, total_rows // 64)
-        west = [y * cols + 1 for y in range(mid - band, mid + band)]
+        # one river per 4096-row strip (see make_inputs): every strip carries the same forcing
+        period = w["rows_per_gpu"]
+        band = max(4, period // 64)
+        mids = [k * period + period // 2 for k in range(max(1, total_rows // period))]
+        west = [y * cols + 1 for mid in mids for y in range(mid - band, mid + band)]
         ts = np.array([[0.0, 0.0, 0.0, 0.0], [600.0, 0.0, 5000.0, 0.0], [1.0e6, 0.0, 5000.0, 0.0]])
         ts[:, 2] /= len(west)
         sim.add_cell(hc.DEPTH_IGNORE, hc.DISCHARGE_IS_DISCHARGE, west, ts)
-        east = [y * cols + cols - 2 for y in range(mid - band, mid + band)]
+        east = [y * cols + cols - 2 for mid in mids for y in range(mid - band, mid + band)]
         t = np.arange(0.0, 44700.0 * 2, 447.0)
         tide = np.stack([t, 3.0 + 2.0 * np.sin(2 * np.pi * t / 44700.0), 0 * t, 0 * t], axis=1)
         sim.add_cell(hc.DEPTH_IS_FSL, hc.DISCHARGE_IGNORE, east, tide)
@@ -194,7 +197,11 @@ def make_inputs(w, rows, cols, dtype, row_offset=0, total_rows=None):
     if w["scenario"] == "valley":
         y = (np.arange(row_offset, row_offset + rows, dtype=np.float64))[:, None]
         x = np.arange(cols, dtype=np.float64)[None, :]
-        mid, width = total_rows / 2.0, max(8.0, total_rows / 16.0)
+        # the valley repeats every rows_per_gpu rows (one west->east river per strip), so that the weak-scaling runs
+        # give every rank the same wet/dry mix as the single-GPU strip instead of one wet rank and seven dry ones
+        period = float(w["rows_per_gpu"])
+        y = np.mod(y, period)
+        mid, width = period / 2.0, max(8.0, period / 16.0)
         rng = np.random.default_rng(20260819 + row_offset)
         bed = 0.001 * (cols - x) + 20.0 * (1.0 - np.exp(-(((y - mid) / width) ** 2))) + 1.0
         bed = sc.round4(bed + 0.5 * rng.uniform(-1.0, 1.0, size=(rows, cols)))

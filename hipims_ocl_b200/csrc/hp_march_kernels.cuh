@@ -63,9 +63,9 @@ template <class R>
 __device__ __forceinline__ void face_solve(const Params<R>& k, R etaL, R zL, R unL, R utL, R aL_cached, R etaR, R zR, R unR, R utR,
                                            R aR_cached, const bool cached, R qOwnL, R qOwnR, FaceOut<R>& o) {
     const R hg = R(0.5) * k.g;
-    const R zmax = zL > zR ? zL : zR;
-    const R hL = (etaL - zmax > R(0)) ? (etaL - zmax) : R(0);
-    const R hR = (etaR - zmax > R(0)) ? (etaR - zmax) : R(0);
+    const R zmax = fm_max(zL, zR);
+    const R hL = fm_posdiff(etaL, zmax);
+    const R hR = fm_posdiff(etaR, zmax);
     o.zmax = zmax; o.hL = hL; o.hR = hR; o.stopL = 0; o.stopR = 0;
     if (hL <= k.eps || hR <= k.eps) {
         int both = 0;
@@ -290,7 +290,7 @@ mh_step_march(const StepArgs a, const __grid_constant__ TmaBlockMap maps) {
                                 const R cc = fm_sqrt(k.g * h);
                                 R sp = cc;
                                 if (!k.simplified_speed) { const R rh = fm_rcp(h); sp = fm_max(hp_abs(c.qx * rh), hp_abs(c.qy * rh)) + cc; }
-                                ws = sp > ws ? sp : ws;
+                                ws = fm_max(sp, ws);
                             }
                         }
                     }
@@ -307,7 +307,7 @@ mh_step_march(const StepArgs a, const __grid_constant__ TmaBlockMap maps) {
                             const R cc = fm_sqrt(k.g * h);
                             R sp = cc;
                             if (!k.simplified_speed) { const R rh = fm_rcp(h); sp = fm_max(hp_abs(c.qx * rh), hp_abs(c.qy * rh)) + cc; }
-                            ws = sp > ws ? sp : ws;
+                            ws = fm_max(sp, ws);
                         }
                     }
                 }
@@ -413,7 +413,7 @@ godunov_step_march(const StepArgs a, const __grid_constant__ TmaBlockMap maps) {
             const R h = o.eta - o.zb;
             const R rh = !(h < k.eps) ? fm_rcp(h) : R(0);
             o.u = qx * rh; o.v = qy * rh;
-            o.c = fm_sqrt(k.g * (h > R(0) ? h : R(0)));
+            o.c = fm_sqrt(k.g * fm_pos(h));
         };
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
@@ -461,7 +461,7 @@ godunov_step_march(const StepArgs a, const __grid_constant__ TmaBlockMap maps) {
                     const R h = c.eta - zb;
                     if (h > k.eps10 && c.emax > R(-9999.0)) {
                         const R sp = k.simplified_speed ? P.c : fm_max(hp_abs(P.u), hp_abs(P.v)) + P.c;
-                        ws = sp > ws ? sp : ws;
+                        ws = fm_max(sp, ws);
                     }
                 }
                 bool wrote = false;
@@ -506,7 +506,7 @@ godunov_step_march(const StepArgs a, const __grid_constant__ TmaBlockMap maps) {
                                 const R rh = have_new ? rh_new : fm_rcp(h);
                                 sp = fm_max(hp_abs(c.qx * rh), hp_abs(c.qy * rh)) + cc;
                             }
-                            ws = sp > ws ? sp : ws;
+                            ws = fm_max(sp, ws);
                         }
                     }
                 }
@@ -667,7 +667,7 @@ inertial_step_march(const StepArgs a, const __grid_constant__ TmaBlockMap maps) 
                         const R cc = fm_sqrt(k.g * h);
                         R sp = cc;
                         if (!k.simplified_speed) { const R rh = fm_rcp(h); sp = fm_max(hp_abs(c.qx * rh), hp_abs(c.qy * rh)) + cc; }
-                        ws = sp > ws ? sp : ws;
+                        ws = fm_max(sp, ws);
                     }
                 }
                 bool wrote = false;
@@ -695,7 +695,7 @@ inertial_step_march(const StepArgs a, const __grid_constant__ TmaBlockMap maps) 
                             const R cc = fm_sqrt(k.g * h);
                             R sp = cc;
                             if (!k.simplified_speed) { const R rh = fm_rcp(h); sp = fm_max(hp_abs(c.qx * rh), hp_abs(c.qy * rh)) + cc; }
-                            ws = sp > ws ? sp : ws;
+                            ws = fm_max(sp, ws);
                         }
                     }
                 }

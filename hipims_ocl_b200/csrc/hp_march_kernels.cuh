@@ -327,6 +327,16 @@ mh_step_march(const StepArgs a, const __grid_constant__ TmaBlockMap maps) {
     block_reduce_finalize<R>(ws, a, k);
 }
 
+// Cells the step leaves unwritten (frozen ring, all-dry stencil) still enter the CFL reduction with the value the
+// destination buffer holds.  That read is a dependent global load in the middle of a row; issue a
+// prefetch for it one row ahead wherever the cell is likely to stay unwritten.
+template <class R> __device__ __forceinline__ void prefetch_dst(const MutView<R>& d, size_t id) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(d.eta + id));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(d.emax + id));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(d.qx + id));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(d.qy + id));
+}
+
 // =============================================================================================
 // First-order Godunov, marching.  Carried per lane: the cell below (level, bed, velocities, celerity)
 // and its southern face.  Cells whose stencil is dry stay unwritten, exactly like
@@ -335,10 +345,10 @@ mh_step_march(const StepArgs a, const __grid_constant__ TmaBlockMap maps) {
 template <class R> struct GodCell { R eta, zb, u, v, c; };
 
 #ifndef HP_MARCH_GOD_CTAS64
-#define HP_MARCH_GOD_CTAS64 5
+#define HP_MARCH_GOD_CTAS64 4
 #endif
 #ifndef HP_MARCH_GOD_CTAS32
-#define HP_MARCH_GOD_CTAS32 8
+#define HP_MARCH_GOD_CTAS32 6
 #endif
 template <class R, bool ALT>
 __global__ void __launch_bounds__(hp::kMarchWarps * 32, sizeof(R) == 8 ? HP_MARCH_GOD_CTAS64 : HP_MARCH_GOD_CTAS32)
@@ -438,6 +448,10 @@ godunov_step_march(const StepArgs a, const __grid_constant__ TmaBlockMap maps) {
             R c_qx, c_qy;
             derive(o_c, C, c_qx, c_qy);
             const bool dry_p = P.eta - P.zb < k.eps, dry_c = C.eta - C.zb < k.eps;
+            if (a.reduce_mode == hp::kReduceDst && x_store && j + 1 < NR) {      // row y is updated in the next trip
+                const int gy = y + g.gy0;
+                if (!x_interior || gy < 1 || gy > g.grows - 2 || (dry_c && dry_p)) prefetch_dst(d, static_cast<size_t>(y) * g.pitch + x);
+            }
 
             FaceOut<R> fy;
             if (stepping) face_solve<R>(k, P.eta, P.zb, P.v, P.u, P.c, C.eta, C.zb, C.v, C.u, C.c, true, p_qy, c_qy, fy);
@@ -642,6 +656,10 @@ inertial_step_march(const StepArgs a, const __grid_constant__ TmaBlockMap maps) 
             wait_row(j);
             const R c_eta = ld(o_c, T::P_ETA, lc), c_zb = ld(o_c, T::P_ZB, lc), c_qy = ld(o_c, T::P_QY, lc), c_n = ld(o_c, T::P_N, lc);
             const bool dry_p = p_eta - p_zb < k.eps, dry_c = c_eta - c_zb < k.eps;
+            if (a.reduce_mode == hp::kReduceDst && x_store && j + 1 < NR) {      // row y is updated in the next trip
+                const int gy = y + g.gy0;
+                if (!x_interior || gy < 1 || gy > g.grows - 2 || !stepping || (dry_c && dry_p)) prefetch_dst(d, static_cast<size_t>(y) * g.pitch + x);
+            }
             // face between rows y-1 (down) and y (up); its discharge is stored in row y
             InFace<R> fy{R(0), R(0), R(0), false};
             if (stepping) fy = inertial_face<R>(k, gdt, c_qy, c_eta, c_zb, p_eta, p_zb, inv_delta);

@@ -245,7 +245,7 @@ int build_tma_maps(hp_scheme* s) {
     const int rbi = static_cast<int>(s->rb);
     if (s->use_march) {
         // marching kernels: one 3-D descriptor over the ten-plane block; a box is one row of six planes
-        return encode_plane_map(s->march_map.bytes[0], s->block, s->grid, s->rb, hp::march_box_w(rbi, halo), 1, 10, s->plane_bytes, 6);
+        return encode_plane_map(s->march_map.bytes[0], s->block, s->grid, s->rb, hp::march_box_w(rbi, 1), 1, 10, s->plane_bytes, 6);
     }
     const int w = hp::tma_box_w(rbi, halo), h = hp::tma_box_h(halo);
     for (int b = 0; b < 2; ++b) {

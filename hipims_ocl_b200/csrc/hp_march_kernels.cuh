@@ -16,8 +16,9 @@
 //     a CTA is four warps on four adjacent strips so that the halo columns hit in L1/L2;
 //   * work is split into equal runs of (strip group, row) units over a persistent grid that
 //     exactly fills the SMs, so all CTAs finish together (no tail wave).
-// Lanes at the strip edge only feed their neighbours (halo lanes): 28 of 32 lanes update cells
-// for MUSCL-Hancock (halo 2), 30 of 32 for Godunov fp64 (halo 1).
+// The lane at either strip edge only feeds its neighbour (halo lanes): 30 of 32 lanes update cells in fp64,
+// 28 in fp32 (the TMA box must start on a 16-byte boundary).  MUSCL-Hancock needs raw values two columns out;
+// those come straight from the box, which is wider than the warp.
 // The per-cell arithmetic is the one of the tile kernels (same helper functions), so results are
 // identical to them to the last bit where the operation order is the same.
 #pragma once
@@ -108,7 +109,9 @@ template <class R> __device__ __forceinline__ R shfl_dn1(R v) { return __shfl_do
 template <class R, bool ALT>
 __global__ void __launch_bounds__(hp::kMarchWarps * 32, sizeof(R) == 8 ? 4 : 6)
 mh_step_march(const StepArgs a, const __grid_constant__ TmaBlockMap maps) {
-    using T = March<R, 2, ALT>;
+    // lane halo of ONE column per side: the raw values two columns out come from the TMA box, which is two columns
+    // wider than the warp (geometry of HALO = 1); only predictor values need a lane.  30 of 32 lanes update cells.
+    using T = March<R, 1, ALT>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* const ring = smem_raw + warp * T::WARP_BYTES;
@@ -138,8 +141,8 @@ mh_step_march(const StepArgs a, const __grid_constant__ TmaBlockMap maps) {
 
     // per-lane byte offsets of the own column and its clamped x-neighbours inside a plane row
     const int lc = (lane + T::PADL) * int(sizeof(R));
-    const int lw = (lane > 0 ? lane - 1 + T::PADL : T::PADL) * int(sizeof(R));
-    const int le = (lane < 31 ? lane + 1 + T::PADL : 31 + T::PADL) * int(sizeof(R));
+    const int lw = (lane - 1 + T::PADL) * int(sizeof(R)), le = (lane + 1 + T::PADL) * int(sizeof(R));   // PADL >= 1, BW >= 33 + PADL
+    static_assert(T::PADL >= 1 && T::BW >= 33 + T::PADL, "the box must hold one raw column beyond either edge lane");
     auto ld = [&](int row_off, int plane, int col_off) -> R {
         return *reinterpret_cast<const R*>(ring + row_off + plane * T::PLANE + col_off);
     };
@@ -157,7 +160,7 @@ mh_step_march(const StepArgs a, const __grid_constant__ TmaBlockMap maps) {
         const int strip = grp * T::NW + warp;
         if (strip >= nstrips) continue;
 
-        const int X0 = strip * T::USE - 2;               // column of lane 0
+        const int X0 = strip * T::USE - 1;               // column of lane 0
         const int x = X0 + lane;
         const int rs = ya - 2;                            // first raw row of this run
         const int J = yb - ya + 2;                        // raw rows 0 .. J+1, predictor rows 1 .. J
@@ -195,7 +198,9 @@ mh_step_march(const StepArgs a, const __grid_constant__ TmaBlockMap maps) {
                       o_p = ((j + 1) & (T::RR - 1)) * T::SLOT;
             wait_row(j + 1);
             const int f_p = flags_of(ld(o_p, T::P_EMAX, lc));
-            const int f_w = __shfl_up_sync(0xffffffffu, f_c, 1), f_e = __shfl_down_sync(0xffffffffu, f_c, 1);
+            int f_w = __shfl_up_sync(0xffffffffu, f_c, 1), f_e = __shfl_down_sync(0xffffffffu, f_c, 1);
+            if (lane == 0) f_w = flags_of(ld(o_c, T::P_EMAX, lw));          // the columns beyond the edge lanes have no lane
+            if (lane == 31) f_e = flags_of(ld(o_c, T::P_EMAX, le));
 
             // ---- predictor of row y (CLSchemeMUSCLHancock.clc:301-382) ---------------------------
             const R eta = ld(o_c, T::P_ETA, lc), qx = ld(o_c, T::P_QX, lc), qy = ld(o_c, T::P_QY, lc), zb = ld(o_c, T::P_ZB, lc);
@@ -282,7 +287,7 @@ mh_step_march(const StepArgs a, const __grid_constant__ TmaBlockMap maps) {
                             if (c.eta > c.emax && c.emax > R(-9990.0)) c.emax = c.eta;
                         }
                     }
-                    if (lane >= 2 && lane < 2 + T::USE && x < g.cols) {
+                    if (lane >= 1 && lane < 1 + T::USE && x < g.cols) {
                         d.store(static_cast<size_t>(yc) * g.pitch + x, c);
                         if (a.reduce_mode != hp::kReduceNone) {
                             const R h = c.eta - pzb;
@@ -298,7 +303,7 @@ mh_step_march(const StepArgs a, const __grid_constant__ TmaBlockMap maps) {
                 sM = fy.m; sN = fy.n; sT = fy.t; sZ = fy.zmax; sH = fy.hL; sStop = fy.stopR;
             } else if (!stepping && j >= 3) {
                 // dt <= 0: the reference's kernels return; the ping-pong copies the state through
-                if (lane >= 2 && lane < 2 + T::USE && x < g.cols) {
+                if (lane >= 1 && lane < 1 + T::USE && x < g.cols) {
                     Cell<R> c{ld(o_m, T::P_ETA, lc), ld(o_m, T::P_EMAX, lc), ld(o_m, T::P_QX, lc), ld(o_m, T::P_QY, lc)};
                     d.store(static_cast<size_t>(y - 1) * g.pitch + x, c);
                     if (a.reduce_mode != hp::kReduceNone) {
@@ -741,7 +746,7 @@ static int march_grid(const StepArgs& a, int use, int nw, int ctas_per_sm, int s
 }
 
 template <class R> static int launch_mh_march(const StepArgs& a_in, const TmaBlockMap& maps, int alt, int sm_count, cudaStream_t st) {
-    using T = March<R, 2, false>;
+    using T = March<R, 1, false>;
     StepArgs a = a_in;
     if (a.y1 <= a.y0) return 0;
     static bool configured = false;

@@ -52,6 +52,7 @@ struct StepArgs {
     int reduce_mode;          // ReduceMode
     int finalize;             // 1: last CTA runs the time controller (single device)
     unsigned int total_ctas;  // CTAs that will arrive on `ticket` before the finaliser runs
+    int march_runs;           // marching kernels: runs of (strip group, row) units per CTA, interleaved across the grid
 };
 
 struct BdyUniformArgs {

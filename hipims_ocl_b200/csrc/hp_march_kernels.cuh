@@ -15,7 +15,8 @@
 //   * there is no CTA-level barrier and no shared-memory store in the loop: warps are autonomous,
 //     a CTA is four warps on four adjacent strips so that the halo columns hit in L1/L2;
 //   * work is split into equal runs of (strip group, row) units over a persistent grid that
-//     exactly fills the SMs, so all CTAs finish together (no tail wave).
+//     exactly fills the SMs; each CTA takes several runs spread round-robin over the domain, so all
+//     CTAs finish together (no tail wave) even where wet and dry regions cost differently.
 // The lane at either strip edge only feeds its neighbour (halo lanes): 30 of 32 lanes update cells in fp64,
 // 28 in fp32 (the TMA box must start on a 16-byte boundary).  MUSCL-Hancock needs raw values two columns out;
 // those come straight from the box, which is wider than the warp.
@@ -36,8 +37,11 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
 
 // Ring geometry.  ALT = false: the step reads buffer A (block planes 0..5 = eta qx qy emax zb n);
 // ALT = true: buffer B (block planes 4..9 = zb n eta qx qy emax).
+#ifndef HP_MARCH_RR
+#define HP_MARCH_RR 4
+#endif
 template <class R, int HALO, bool ALT> struct March {
-    static constexpr int NW = hp::kMarchWarps, RR = 4, NP = 6;
+    static constexpr int NW = hp::kMarchWarps, RR = HP_MARCH_RR, NP = 6;      // RR: ring rows (power of two)
     static constexpr int A16 = 16 / int(sizeof(R));                       // elements per 16 bytes
     static constexpr int USE = hp::march_use(int(sizeof(R)), HALO);       // cells updated per warp row
     static constexpr int PADL = ((-HALO) % A16 + A16) % A16;              // box starts 16-byte aligned
@@ -136,8 +140,11 @@ mh_step_march(const StepArgs a, const __grid_constant__ TmaBlockMap maps) {
     const int nstrips = (g.cols + T::USE - 1) / T::USE;
     const int ngroups = (nstrips + T::NW - 1) / T::NW;
     const long long units = static_cast<long long>(ngroups) * nrows;
-    long long u = units * blockIdx.x / gridDim.x;
-    const long long u1 = units * (blockIdx.x + 1) / gridDim.x;
+    // A CTA works on `march_runs` equal runs of units, taken round-robin from the whole domain (run r belongs to CTA
+    // r mod grid): every CTA gets the same amount of work AND a sample of the domain, so wet and dry regions even out.
+    const long long total_runs = static_cast<long long>(gridDim.x) * a.march_runs;
+    int run = 0;
+    long long u = units * blockIdx.x / total_runs, u1 = units * (blockIdx.x + 1) / total_runs;
 
     // per-lane byte offsets of the own column and its clamped x-neighbours inside a plane row
     const int lc = (lane + T::PADL) * int(sizeof(R));
@@ -151,7 +158,13 @@ mh_step_march(const StepArgs a, const __grid_constant__ TmaBlockMap maps) {
     R ws = R(0);
     uint32_t ph = 0;
 
-    while (u < u1) {
+    for (;;) {
+        if (u >= u1) {
+            if (++run >= a.march_runs) break;
+            const long long r = static_cast<long long>(run) * gridDim.x + blockIdx.x;
+            u = units * r / total_runs; u1 = units * (r + 1) / total_runs;
+            continue;
+        }
         const int grp = static_cast<int>(u / nrows);
         const int ya = a.y0 + static_cast<int>(u - static_cast<long long>(grp) * nrows);
         const long long gend = static_cast<long long>(grp + 1) * nrows;
@@ -179,7 +192,7 @@ mh_step_march(const StepArgs a, const __grid_constant__ TmaBlockMap maps) {
         __syncwarp();
         if (lane == 0) {
 #pragma unroll
-            for (int j = 0; j < T::RR; ++j) issue_row(j);      // J + 2 >= 5 rows always exist
+            for (int j = 0; j < T::RR; ++j) if (j <= J + 1) issue_row(j);
         }
         wait_row(0);
         wait_row(1);
@@ -191,6 +204,15 @@ mh_step_march(const StepArgs a, const __grid_constant__ TmaBlockMap maps) {
         R psyE = R(0), psyH = R(0), psyQx = R(0), psyQy = R(0), pzb = R(0);
         R sM = R(0), sN = R(0), sT = R(0), sZ = R(0), sH = R(0);   // southern face of the previous row
         int sStop = 0;
+        // Rows in which every lane is EXACTLY dry and at rest (eta == zb, q == 0, eta_max not below eta) -- most of a
+        // flood model's domain.  Such a cell falls back to first order with zero slopes, a face between two of them
+        // carries no flux at all, and a cell whose whole stencil is like that cannot change: the row is copied through
+        // (identical to what the full arithmetic produces, at a fraction of its instructions).
+        // Rows in which every lane is EXACTLY dry and at rest (eta == zb, q == 0, eta_max not below eta) -- most of a
+        // flood model's domain.  Such a cell falls back to first order with zero slopes, a face between two of them
+        // carries no flux at all, and a cell whose whole stencil is like that cannot change: the row is copied through
+        // (identical to what the full arithmetic produces, at a fraction of its instructions).
+        bool dr_m2 = false, dr_m1 = false, dr_c = false;       // rows j-2, j-1, j (warp-uniform)
 
         for (int j = 1; j <= J; ++j) {
             const int y = rs + j, gy = y + g.gy0;
@@ -204,91 +226,120 @@ mh_step_march(const StepArgs a, const __grid_constant__ TmaBlockMap maps) {
 
             // ---- predictor of row y (CLSchemeMUSCLHancock.clc:301-382) ---------------------------
             const R eta = ld(o_c, T::P_ETA, lc), qx = ld(o_c, T::P_QX, lc), qy = ld(o_c, T::P_QY, lc), zb = ld(o_c, T::P_ZB, lc);
+            // (tested on every fourth row, and on every row while the rows below are dry: wet regions pay almost nothing)
+            dr_c = false;
+            if (stepping && (dr_m1 || (j & 3) == 0))
+                dr_c = __all_sync(0xffffffffu, eta == zb && qx == R(0) && qy == R(0) && !(eta > ld(o_c, T::P_EMAX, lc)));
             R ce = eta, cqx = qx, cqy = qy;
             R sxE = R(0), sxH = R(0), sxQx = R(0), sxQy = R(0), syE = R(0), syH = R(0), syQx = R(0), syQy = R(0);
-            {
-                const bool valid = stepping && x >= 1 && x <= g.cols - 2 && gy >= 1 && gy <= g.grows - 2 && y >= 1 && y <= g.rows - 2;
-                const R h = eta - zb;
-                if (valid && !(h < R(1E-5)) && !((f_p | f_e | f_m1 | f_w) & 1)) {
-                    const R etaE = ld(o_c, T::P_ETA, le), etaW = ld(o_c, T::P_ETA, lw), etaN = ld(o_p, T::P_ETA, lc), etaS = ld(o_m, T::P_ETA, lc);
-                    const R hE = etaE - ld(o_c, T::P_ZB, le), hW = etaW - ld(o_c, T::P_ZB, lw);
-                    const R hN = etaN - ld(o_p, T::P_ZB, lc), hS = etaS - ld(o_m, T::P_ZB, lc);
-                    if (!(hW < k.eps || hE < k.eps)) {
-                        sxE = minmod(eta - etaW, etaE - eta); sxH = minmod(h - hW, hE - h);
-                        sxQx = minmod(qx - ld(o_c, T::P_QX, lw), ld(o_c, T::P_QX, le) - qx);
-                        sxQy = minmod(qy - ld(o_c, T::P_QY, lw), ld(o_c, T::P_QY, le) - qy);
-                    }
-                    if (!(hS < k.eps || hN < k.eps)) {
-                        syE = minmod(eta - etaS, etaN - eta); syH = minmod(h - hS, hN - h);
-                        syQx = minmod(qx - ld(o_m, T::P_QX, lc), ld(o_p, T::P_QX, lc) - qx);
-                        syQy = minmod(qy - ld(o_m, T::P_QY, lc), ld(o_p, T::P_QY, lc) - qy);
-                    }
-                    const R hEf = h + half * sxH, hWf = h - half * sxH, hNf = h + half * syH, hSf = h - half * syH;
-                    const R qxE = qx + half * sxQx, qxW = qx - half * sxQx, qyE = qy + half * sxQy, qyW = qy - half * sxQy;
-                    const R qxN = qx + half * syQx, qxS = qx - half * syQx, qyN = qy + half * syQy, qyS = qy - half * syQy;
-                    const R uE = hEf < k.eps ? R(0) : qxE * fm_rcp(hEf), uW = hWf < k.eps ? R(0) : qxW * fm_rcp(hWf);
-                    const R vN = hNf < k.eps ? R(0) : qyN * fm_rcp(hNf), vS = hSf < k.eps ? R(0) : qyS * fm_rcp(hSf);
-                    R dEta = ((qxE - qxW) + (qyN - qyS)) * inv_delta;
-                    R dQx = (uE * qxE - uW * qxW + vN * qxN - vS * qxS + hg * sxE * (hEf + hWf)) * inv_delta;
-                    R dQy = (uE * qyE - uW * qyW + vN * qyN - vS * qyS + hg * syE * (hNf + hSf)) * inv_delta;
-                    dEta = fm_chop(dEta, k.eps); dQx = fm_chop(dQx, k.eps); dQy = fm_chop(dQy, k.eps);
-                    ce = eta - half * dt * dEta; cqx = qx - half * dt * dQx; cqy = qy - half * dt * dQy;
-                }
-            }
-
-            if (stepping && j >= 2) {
-                // ---- face between rows y-1 (left) and y (right); normal = y ----------------------
-                FaceOut<R> fy;
+            if (dr_m2 && dr_m1 && dr_c) {
+                // rows y-2, y-1, y exactly dry in every lane (so j >= 3): predictor = the raw state with zero slopes, the face
+                // (y-1 | y) carries nothing, the cell (x, y-1) cannot change
+                if (lane >= 1 && lane < 1 + T::USE && x < g.cols)
+                    d.store(static_cast<size_t>(y - 1) * g.pitch + x,
+                            Cell<R>{ld(o_m, T::P_ETA, lc), ld(o_m, T::P_EMAX, lc), ld(o_m, T::P_QX, lc), ld(o_m, T::P_QY, lc)});
+                sM = R(0); sN = R(0); sT = R(0); sZ = fm_max(pe, ce); sH = R(0); sStop = 0;
+            } else {
                 {
-                    const R etaL = pe + half * psyE, hfL = (pe - pzb) + half * psyH;
-                    const R qxL = pqx + half * psyQx, qyL = pqy + half * psyQy;
-                    const R etaR = ce - half * syE, hfR = (ce - zb) - half * syH;
-                    const R qxR = cqx - half * syQx, qyR = cqy - half * syQy;
-                    const R rL = hfL <= k.eps ? R(0) : fm_rcp(hfL), rR = hfR <= k.eps ? R(0) : fm_rcp(hfR);
-                    face_solve<R>(k, etaL, etaL - hfL, qyL * rL, qxL * rL, R(0), etaR, etaR - hfR, qyR * rR, qxR * rR, R(0), false,
-                                  ld(o_m, T::P_QY, lc), qy, fy);
+                    const bool valid = stepping && x >= 1 && x <= g.cols - 2 && gy >= 1 && gy <= g.grows - 2 && y >= 1 && y <= g.rows - 2;
+                    const R h = eta - zb;
+                    if (valid && !(h < R(1E-5)) && !((f_p | f_e | f_m1 | f_w) & 1)) {
+                        const R etaE = ld(o_c, T::P_ETA, le), etaW = ld(o_c, T::P_ETA, lw), etaN = ld(o_p, T::P_ETA, lc), etaS = ld(o_m, T::P_ETA, lc);
+                        const R hE = etaE - ld(o_c, T::P_ZB, le), hW = etaW - ld(o_c, T::P_ZB, lw);
+                        const R hN = etaN - ld(o_p, T::P_ZB, lc), hS = etaS - ld(o_m, T::P_ZB, lc);
+                        if (!(hW < k.eps || hE < k.eps)) {
+                            sxE = minmod(eta - etaW, etaE - eta); sxH = minmod(h - hW, hE - h);
+                            sxQx = minmod(qx - ld(o_c, T::P_QX, lw), ld(o_c, T::P_QX, le) - qx);
+                            sxQy = minmod(qy - ld(o_c, T::P_QY, lw), ld(o_c, T::P_QY, le) - qy);
+                        }
+                        if (!(hS < k.eps || hN < k.eps)) {
+                            syE = minmod(eta - etaS, etaN - eta); syH = minmod(h - hS, hN - h);
+                            syQx = minmod(qx - ld(o_m, T::P_QX, lc), ld(o_p, T::P_QX, lc) - qx);
+                            syQy = minmod(qy - ld(o_m, T::P_QY, lc), ld(o_p, T::P_QY, lc) - qy);
+                        }
+                        const R hEf = h + half * sxH, hWf = h - half * sxH, hNf = h + half * syH, hSf = h - half * syH;
+                        const R qxE = qx + half * sxQx, qxW = qx - half * sxQx, qyE = qy + half * sxQy, qyW = qy - half * sxQy;
+                        const R qxN = qx + half * syQx, qxS = qx - half * syQx, qyN = qy + half * syQy, qyS = qy - half * syQy;
+                        const R uE = hEf < k.eps ? R(0) : qxE * fm_rcp(hEf), uW = hWf < k.eps ? R(0) : qxW * fm_rcp(hWf);
+                        const R vN = hNf < k.eps ? R(0) : qyN * fm_rcp(hNf), vS = hSf < k.eps ? R(0) : qyS * fm_rcp(hSf);
+                        R dEta = ((qxE - qxW) + (qyN - qyS)) * inv_delta;
+                        R dQx = (uE * qxE - uW * qxW + vN * qxN - vS * qxS + hg * sxE * (hEf + hWf)) * inv_delta;
+                        R dQy = (uE * qyE - uW * qyW + vN * qyN - vS * qyS + hg * syE * (hNf + hSf)) * inv_delta;
+                        dEta = fm_chop(dEta, k.eps); dQx = fm_chop(dQx, k.eps); dQy = fm_chop(dQy, k.eps);
+                        ce = eta - half * dt * dEta; cqx = qx - half * dt * dQx; cqy = qy - half * dt * dQy;
+                    }
                 }
-                if (j >= 3) {
-                    // ---- west face of row y-1: the east-side estimate of lane-1 against the own west side
-                    const R xe_eta = pe + half * psxE, xe_h = (pe - pzb) + half * psxH;
-                    const R xe_r = xe_h <= k.eps ? R(0) : fm_rcp(xe_h);
-                    const R xe_u = (pqx + half * psxQx) * xe_r, xe_v = (pqy + half * psxQy) * xe_r;
-                    const R etaL = shfl_up1(xe_eta), hfL = shfl_up1(xe_h), uL = shfl_up1(xe_u), vL = shfl_up1(xe_v);
-                    const R etaR = pe - half * psxE, hfR = (pe - pzb) - half * psxH;
-                    const R rR = hfR <= k.eps ? R(0) : fm_rcp(hfR);
-                    const R uR = (pqx - half * psxQx) * rR, vR = (pqy - half * psxQy) * rR;
-                    const R c_qx = ld(o_m, T::P_QX, lc);
-                    FaceOut<R> fx;
-                    face_solve<R>(k, etaL, etaL - hfL, uL, vL, R(0), etaR, etaR - hfR, uR, vR, R(0), false, ld(o_m, T::P_QX, lw), c_qx, fx);
-                    // the east face comes back from lane+1
-                    const R eM = shfl_dn1(fx.m), eN = shfl_dn1(fx.n), eT = shfl_dn1(fx.t), eZ = shfl_dn1(fx.zmax), eH = shfl_dn1(fx.hR);
-                    const int eStop = __shfl_down_sync(0xffffffffu, fx.stopL, 1);
 
-                    // ---- corrector of row y-1 (CLSchemeMUSCLHancock.clc:596-800) -----------------
-                    const int yc = y - 1, gyc = gy - 1;
-                    Cell<R> c{ld(o_m, T::P_ETA, lc), ld(o_m, T::P_EMAX, lc), c_qx, ld(o_m, T::P_QY, lc)};
-                    const bool interior = x >= 2 && x <= g.cols - 3 && gyc >= 2 && gyc <= g.grows - 3;   // ring of two is frozen
-                    if (interior && !(c.emax <= R(-9999.0) || c.eta == R(-9999.0))) {
-                        int dry = (c.eta - pzb < k.eps) ? 1 : 0;
-                        dry += (f_c >> 1) + (f_m2 >> 1) + (f_ew_prev & 1) + (f_ew_prev >> 2);
-                        if (dry < 5) {
-                            const R bN = fm_min(fy.zmax, pe + half * psyE), bS = fm_min(sZ, pe - half * psyE);
-                            const R bE = fm_min(eZ, pe + half * psxE), bW = fm_min(fx.zmax, pe - half * psxE);
-                            const int stop = fy.stopL + sStop + fx.stopR + eStop;
-                            R dEta = ((eM - fx.m) + (fy.m - sM)) * inv_delta;
-                            R dQx = ((eN - fx.n) + (fy.t - sT) + hg * (bE - bW) * (eH + fx.hL)) * inv_delta;
-                            R dQy = ((eT - fx.t) + (fy.n - sN) + hg * (bN - bS) * (fy.hR + sH)) * inv_delta;
-                            dEta = fm_chop(dEta, k.eps); dQx = fm_chop(dQx, k.eps); dQy = fm_chop(dQy, k.eps);
-                            if (stop > 0) { c.qx = R(0); c.qy = R(0); }
-                            c.eta = c.eta - dt * dEta; c.qx = c.qx - dt * dQx; c.qy = c.qy - dt * dQy;
-                            const R h_new = c.eta - pzb;
-                            if (k.friction && !(h_new < k.eps)) friction_fast(k, h_new, fm_rcp(h_new), c.qx, c.qy, ld(o_m, T::P_N, lc), dt);
-                            if (h_new < k.eps) c.eta = pzb;
-                            if (c.eta > c.emax && c.emax > R(-9990.0)) c.emax = c.eta;
+                if (stepping && j >= 2) {
+                    // ---- face between rows y-1 (left) and y (right); normal = y ----------------------
+                    FaceOut<R> fy;
+                    {
+                        const R etaL = pe + half * psyE, hfL = (pe - pzb) + half * psyH;
+                        const R qxL = pqx + half * psyQx, qyL = pqy + half * psyQy;
+                        const R etaR = ce - half * syE, hfR = (ce - zb) - half * syH;
+                        const R qxR = cqx - half * syQx, qyR = cqy - half * syQy;
+                        const R rL = hfL <= k.eps ? R(0) : fm_rcp(hfL), rR = hfR <= k.eps ? R(0) : fm_rcp(hfR);
+                        face_solve<R>(k, etaL, etaL - hfL, qyL * rL, qxL * rL, R(0), etaR, etaR - hfR, qyR * rR, qxR * rR, R(0), false,
+                                      ld(o_m, T::P_QY, lc), qy, fy);
+                    }
+                    if (j >= 3) {
+                        // ---- west face of row y-1: the east-side estimate of lane-1 against the own west side
+                        const R xe_eta = pe + half * psxE, xe_h = (pe - pzb) + half * psxH;
+                        const R xe_r = xe_h <= k.eps ? R(0) : fm_rcp(xe_h);
+                        const R xe_u = (pqx + half * psxQx) * xe_r, xe_v = (pqy + half * psxQy) * xe_r;
+                        const R etaL = shfl_up1(xe_eta), hfL = shfl_up1(xe_h), uL = shfl_up1(xe_u), vL = shfl_up1(xe_v);
+                        const R etaR = pe - half * psxE, hfR = (pe - pzb) - half * psxH;
+                        const R rR = hfR <= k.eps ? R(0) : fm_rcp(hfR);
+                        const R uR = (pqx - half * psxQx) * rR, vR = (pqy - half * psxQy) * rR;
+                        const R c_qx = ld(o_m, T::P_QX, lc);
+                        FaceOut<R> fx;
+                        face_solve<R>(k, etaL, etaL - hfL, uL, vL, R(0), etaR, etaR - hfR, uR, vR, R(0), false, ld(o_m, T::P_QX, lw), c_qx, fx);
+                        // the east face comes back from lane+1
+                        const R eM = shfl_dn1(fx.m), eN = shfl_dn1(fx.n), eT = shfl_dn1(fx.t), eZ = shfl_dn1(fx.zmax), eH = shfl_dn1(fx.hR);
+                        const int eStop = __shfl_down_sync(0xffffffffu, fx.stopL, 1);
+
+                        // ---- corrector of row y-1 (CLSchemeMUSCLHancock.clc:596-800) -----------------
+                        const int yc = y - 1, gyc = gy - 1;
+                        Cell<R> c{ld(o_m, T::P_ETA, lc), ld(o_m, T::P_EMAX, lc), c_qx, ld(o_m, T::P_QY, lc)};
+                        const bool interior = x >= 2 && x <= g.cols - 3 && gyc >= 2 && gyc <= g.grows - 3;   // ring of two is frozen
+                        if (interior && !(c.emax <= R(-9999.0) || c.eta == R(-9999.0))) {
+                            int dry = (c.eta - pzb < k.eps) ? 1 : 0;
+                            dry += (f_c >> 1) + (f_m2 >> 1) + (f_ew_prev & 1) + (f_ew_prev >> 2);
+                            if (dry < 5) {
+                                const R bN = fm_min(fy.zmax, pe + half * psyE), bS = fm_min(sZ, pe - half * psyE);
+                                const R bE = fm_min(eZ, pe + half * psxE), bW = fm_min(fx.zmax, pe - half * psxE);
+                                const int stop = fy.stopL + sStop + fx.stopR + eStop;
+                                R dEta = ((eM - fx.m) + (fy.m - sM)) * inv_delta;
+                                R dQx = ((eN - fx.n) + (fy.t - sT) + hg * (bE - bW) * (eH + fx.hL)) * inv_delta;
+                                R dQy = ((eT - fx.t) + (fy.n - sN) + hg * (bN - bS) * (fy.hR + sH)) * inv_delta;
+                                dEta = fm_chop(dEta, k.eps); dQx = fm_chop(dQx, k.eps); dQy = fm_chop(dQy, k.eps);
+                                if (stop > 0) { c.qx = R(0); c.qy = R(0); }
+                                c.eta = c.eta - dt * dEta; c.qx = c.qx - dt * dQx; c.qy = c.qy - dt * dQy;
+                                const R h_new = c.eta - pzb;
+                                if (k.friction && !(h_new < k.eps)) friction_fast(k, h_new, fm_rcp(h_new), c.qx, c.qy, ld(o_m, T::P_N, lc), dt);
+                                if (h_new < k.eps) c.eta = pzb;
+                                if (c.eta > c.emax && c.emax > R(-9990.0)) c.emax = c.eta;
+                            }
+                        }
+                        if (lane >= 1 && lane < 1 + T::USE && x < g.cols) {
+                            d.store(static_cast<size_t>(yc) * g.pitch + x, c);
+                            if (a.reduce_mode != hp::kReduceNone) {
+                                const R h = c.eta - pzb;
+                                if (h > k.eps10 && c.emax > R(-9999.0)) {
+                                    const R cc = fm_sqrt(k.g * h);
+                                    R sp = cc;
+                                    if (!k.simplified_speed) { const R rh = fm_rcp(h); sp = fm_max(hp_abs(c.qx * rh), hp_abs(c.qy * rh)) + cc; }
+                                    ws = fm_max(sp, ws);
+                                }
+                            }
                         }
                     }
+                    sM = fy.m; sN = fy.n; sT = fy.t; sZ = fy.zmax; sH = fy.hL; sStop = fy.stopR;
+                } else if (!stepping && j >= 3) {
+                    // dt <= 0: the reference's kernels return; the ping-pong copies the state through
                     if (lane >= 1 && lane < 1 + T::USE && x < g.cols) {
-                        d.store(static_cast<size_t>(yc) * g.pitch + x, c);
+                        Cell<R> c{ld(o_m, T::P_ETA, lc), ld(o_m, T::P_EMAX, lc), ld(o_m, T::P_QX, lc), ld(o_m, T::P_QY, lc)};
+                        d.store(static_cast<size_t>(y - 1) * g.pitch + x, c);
                         if (a.reduce_mode != hp::kReduceNone) {
                             const R h = c.eta - pzb;
                             if (h > k.eps10 && c.emax > R(-9999.0)) {
@@ -300,28 +351,13 @@ mh_step_march(const StepArgs a, const __grid_constant__ TmaBlockMap maps) {
                         }
                     }
                 }
-                sM = fy.m; sN = fy.n; sT = fy.t; sZ = fy.zmax; sH = fy.hL; sStop = fy.stopR;
-            } else if (!stepping && j >= 3) {
-                // dt <= 0: the reference's kernels return; the ping-pong copies the state through
-                if (lane >= 1 && lane < 1 + T::USE && x < g.cols) {
-                    Cell<R> c{ld(o_m, T::P_ETA, lc), ld(o_m, T::P_EMAX, lc), ld(o_m, T::P_QX, lc), ld(o_m, T::P_QY, lc)};
-                    d.store(static_cast<size_t>(y - 1) * g.pitch + x, c);
-                    if (a.reduce_mode != hp::kReduceNone) {
-                        const R h = c.eta - pzb;
-                        if (h > k.eps10 && c.emax > R(-9999.0)) {
-                            const R cc = fm_sqrt(k.g * h);
-                            R sp = cc;
-                            if (!k.simplified_speed) { const R rh = fm_rcp(h); sp = fm_max(hp_abs(c.qx * rh), hp_abs(c.qy * rh)) + cc; }
-                            ws = fm_max(sp, ws);
-                        }
-                    }
-                }
             }
             // rotate
             pe = ce; pqx = cqx; pqy = cqy; psxE = sxE; psxH = sxH; psxQx = sxQx; psxQy = sxQy;
             psyE = syE; psyH = syH; psyQx = syQx; psyQy = syQy; pzb = zb;
             f_ew_prev = (f_w >> 1) | ((f_e >> 1) << 2);
             f_m2 = f_m1; f_m1 = f_c; f_c = f_p;
+            dr_m2 = dr_m1; dr_m1 = dr_c;
 
             // row j-1 is dead: refill its ring slot with row j-1+RR
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -384,8 +420,11 @@ godunov_step_march(const StepArgs a, const __grid_constant__ TmaBlockMap maps) {
     const int nstrips = (g.cols + T::USE - 1) / T::USE;
     const int ngroups = (nstrips + T::NW - 1) / T::NW;
     const long long units = static_cast<long long>(ngroups) * nrows;
-    long long u = units * blockIdx.x / gridDim.x;
-    const long long u1 = units * (blockIdx.x + 1) / gridDim.x;
+    // A CTA works on `march_runs` equal runs of units, taken round-robin from the whole domain (run r belongs to CTA
+    // r mod grid): every CTA gets the same amount of work AND a sample of the domain, so wet and dry regions even out.
+    const long long total_runs = static_cast<long long>(gridDim.x) * a.march_runs;
+    int run = 0;
+    long long u = units * blockIdx.x / total_runs, u1 = units * (blockIdx.x + 1) / total_runs;
 
     const int lc = (lane + T::PADL) * int(sizeof(R));
     const int lw = (lane > 0 ? lane - 1 + T::PADL : T::PADL) * int(sizeof(R));
@@ -397,7 +436,13 @@ godunov_step_march(const StepArgs a, const __grid_constant__ TmaBlockMap maps) {
     R ws = R(0);
     uint32_t ph = 0;
 
-    while (u < u1) {
+    for (;;) {
+        if (u >= u1) {
+            if (++run >= a.march_runs) break;
+            const long long r = static_cast<long long>(run) * gridDim.x + blockIdx.x;
+            u = units * r / total_runs; u1 = units * (r + 1) / total_runs;
+            continue;
+        }
         const int grp = static_cast<int>(u / nrows);
         const int ya = a.y0 + static_cast<int>(u - static_cast<long long>(grp) * nrows);
         const long long gend = static_cast<long long>(grp + 1) * nrows;
@@ -604,8 +649,11 @@ inertial_step_march(const StepArgs a, const __grid_constant__ TmaBlockMap maps) 
     const int nstrips = (g.cols + T::USE - 1) / T::USE;
     const int ngroups = (nstrips + T::NW - 1) / T::NW;
     const long long units = static_cast<long long>(ngroups) * nrows;
-    long long u = units * blockIdx.x / gridDim.x;
-    const long long u1 = units * (blockIdx.x + 1) / gridDim.x;
+    // A CTA works on `march_runs` equal runs of units, taken round-robin from the whole domain (run r belongs to CTA
+    // r mod grid): every CTA gets the same amount of work AND a sample of the domain, so wet and dry regions even out.
+    const long long total_runs = static_cast<long long>(gridDim.x) * a.march_runs;
+    int run = 0;
+    long long u = units * blockIdx.x / total_runs, u1 = units * (blockIdx.x + 1) / total_runs;
 
     const int lc = (lane + T::PADL) * int(sizeof(R));
     const int lw = (lane > 0 ? lane - 1 + T::PADL : T::PADL) * int(sizeof(R));
@@ -617,7 +665,13 @@ inertial_step_march(const StepArgs a, const __grid_constant__ TmaBlockMap maps) 
     R ws = R(0);
     uint32_t ph = 0;
 
-    while (u < u1) {
+    for (;;) {
+        if (u >= u1) {
+            if (++run >= a.march_runs) break;
+            const long long r = static_cast<long long>(run) * gridDim.x + blockIdx.x;
+            u = units * r / total_runs; u1 = units * (r + 1) / total_runs;
+            continue;
+        }
         const int grp = static_cast<int>(u / nrows);
         const int ya = a.y0 + static_cast<int>(u - static_cast<long long>(grp) * nrows);
         const long long gend = static_cast<long long>(grp + 1) * nrows;
@@ -734,6 +788,14 @@ inertial_step_march(const StepArgs a, const __grid_constant__ TmaBlockMap maps) 
     block_reduce_finalize<R>(ws, a, k);
 }
 
+// runs per CTA: pieces of at least 64 rows (a run pays two or three start-up rows), at most 32
+static int march_runs(const StepArgs& a, int use, int nw, int grid) {
+    const int nrows = a.y1 - a.y0;
+    const int nstrips = (a.grid.cols + use - 1) / use, ngroups = (nstrips + nw - 1) / nw;
+    const long long per_cta = static_cast<long long>(ngroups) * nrows / grid;
+    const long long k = per_cta / 64;
+    return static_cast<int>(k < 1 ? 1 : (k > 32 ? 32 : k));
+}
 static int march_grid(const StepArgs& a, int use, int nw, int ctas_per_sm, int sm_count) {
     const int nrows = a.y1 - a.y0;
     const int nstrips = (a.grid.cols + use - 1) / use, ngroups = (nstrips + nw - 1) / nw;
@@ -756,7 +818,7 @@ template <class R> static int launch_mh_march(const StepArgs& a_in, const TmaBlo
         configured = true;
     }
     const int grid = march_grid(a, T::USE, T::NW, sizeof(R) == 8 ? 4 : 6, sm_count);
-    a.total_ctas = grid;
+    a.total_ctas = grid; a.march_runs = march_runs(a, T::USE, T::NW, grid);
     if (alt) mh_step_march<R, true><<<grid, T::NW * 32, T::SMEM_BYTES, st>>>(a, maps);
     else mh_step_march<R, false><<<grid, T::NW * 32, T::SMEM_BYTES, st>>>(a, maps);
     return 1;
@@ -773,7 +835,7 @@ template <class R> static int launch_godunov_march(const StepArgs& a_in, const T
         configured = true;
     }
     const int grid = march_grid(a, T::USE, T::NW, sizeof(R) == 8 ? HP_MARCH_GOD_CTAS64 : HP_MARCH_GOD_CTAS32, sm_count);
-    a.total_ctas = grid;
+    a.total_ctas = grid; a.march_runs = march_runs(a, T::USE, T::NW, grid);
     if (alt) godunov_step_march<R, true><<<grid, T::NW * 32, T::SMEM_BYTES, st>>>(a, maps);
     else godunov_step_march<R, false><<<grid, T::NW * 32, T::SMEM_BYTES, st>>>(a, maps);
     return 1;
@@ -790,7 +852,7 @@ template <class R> static int launch_inertial_march(const StepArgs& a_in, const 
         configured = true;
     }
     const int grid = march_grid(a, T::USE, T::NW, sizeof(R) == 8 ? HP_MARCH_INE_CTAS64 : 8, sm_count);
-    a.total_ctas = grid;
+    a.total_ctas = grid; a.march_runs = march_runs(a, T::USE, T::NW, grid);
     if (alt) inertial_step_march<R, true><<<grid, T::NW * 32, T::SMEM_BYTES, st>>>(a, maps);
     else inertial_step_march<R, false><<<grid, T::NW * 32, T::SMEM_BYTES, st>>>(a, maps);
     return 1;

@@ -509,18 +509,11 @@ godunov_step_march(const StepArgs a, const __grid_constant__ TmaBlockMap maps) {
 
             if (j >= 2) {
                 const int yc = y - 1, gyc = yc + g.gy0;
-                // west face of row y-1: the cell of lane-1 against the own cell
-                const R wU = shfl_up1(P.u), wV = shfl_up1(P.v), wC = shfl_up1(P.c);
-                const unsigned drym = __ballot_sync(FULL, dry_p);
-                FaceOut<R> fx;
-                if (stepping) face_solve<R>(k, ld(o_m, T::P_ETA, lw), ld(o_m, T::P_ZB, lw), wU, wV, wC, P.eta, P.zb, P.u, P.v, P.c, true,
-                                            ld(o_m, T::P_QX, lw), p_qx, fx);
-                else { fx.m = fx.n = fx.t = fx.zmax = fx.hL = fx.hR = R(0); fx.stopL = fx.stopR = 0; }
-                const R eM = shfl_dn1(fx.m), eN = shfl_dn1(fx.n), eT = shfl_dn1(fx.t), eZ = shfl_dn1(fx.zmax), eH = shfl_dn1(fx.hR);
-                const int eStop = __shfl_down_sync(FULL, fx.stopL, 1);
-
                 Cell<R> c{P.eta, ld(o_m, T::P_EMAX, lc), p_qx, p_qy};
                 const R zb = P.zb;
+                // rows y-2, y-1, y dry in every lane: the stencil of every cell of row y-1 is dry, the reference returns
+                // without writing (CLSchemeGodunov.clc:248-255) -- no face of that row is needed
+                const bool skip = stepping && __all_sync(FULL, dry_s && dry_p && dry_c && !(c.emax <= R(-9999.0) || c.eta == R(-9999.0)));
                 if (a.reduce_mode == hp::kReduceSrc && x_store) {
                     const R h = c.eta - zb;
                     if (h > k.eps10 && c.emax > R(-9999.0)) {
@@ -531,6 +524,16 @@ godunov_step_march(const StepArgs a, const __grid_constant__ TmaBlockMap maps) {
                 bool wrote = false;
                 R rh_new = R(0);
                 bool have_new = false;
+                if (!skip) {
+                // west face of row y-1: the cell of lane-1 against the own cell
+                const R wU = shfl_up1(P.u), wV = shfl_up1(P.v), wC = shfl_up1(P.c);
+                const unsigned drym = __ballot_sync(FULL, dry_p);
+                FaceOut<R> fx;
+                if (stepping) face_solve<R>(k, ld(o_m, T::P_ETA, lw), ld(o_m, T::P_ZB, lw), wU, wV, wC, P.eta, P.zb, P.u, P.v, P.c, true,
+                                            ld(o_m, T::P_QX, lw), p_qx, fx);
+                else { fx.m = fx.n = fx.t = fx.zmax = fx.hL = fx.hR = R(0); fx.stopL = fx.stopR = 0; }
+                const R eM = shfl_dn1(fx.m), eN = shfl_dn1(fx.n), eT = shfl_dn1(fx.t), eZ = shfl_dn1(fx.zmax), eH = shfl_dn1(fx.hR);
+                const int eStop = __shfl_down_sync(FULL, fx.stopL, 1);
                 if (x_interior && gyc >= 1 && gyc <= g.grows - 2) {                  // frozen outer ring
                     if (!stepping) {
                         wrote = true;                                                   // CLSchemeGodunov.clc:201-206
@@ -556,6 +559,7 @@ godunov_step_march(const StepArgs a, const __grid_constant__ TmaBlockMap maps) {
                             wrote = true;
                         }
                     }
+                }
                 }
                 if (x_store) {
                     const size_t id = static_cast<size_t>(yc) * g.pitch + x;

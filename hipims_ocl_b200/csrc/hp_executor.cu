@@ -97,6 +97,7 @@ struct hp_scheme {
 namespace {
 
 constexpr int kGraphPairs = 8;
+constexpr int kCommSpareSMs = 4;     // SMs left to NCCL during the interior launch of a strip
 
 void drop_graphs(hp_scheme* s) {
     for (auto& g : s->graph_exec) { if (g) cudaGraphExecDestroy(g); g = nullptr; }
@@ -150,11 +151,12 @@ int enqueue_iteration(hp_scheme* s, bool alt, int* launched) {
         if (mh || !(s->cfg.quirks & HP_QUIRK_REDUCE_BUFFER_A)) a.reduce_mode = hp::kReduceDst;
         else a.reduce_mode = alt ? hp::kReduceDst : hp::kReduceSrc;   // Q1: always buffer A
     }
-    auto step = [&](const hp::StepArgs& args) {
-        if (s->use_march) return s->K->step_march(static_cast<int>(s->cfg.scheme), rb, args, &s->march_map, alt ? 1 : 0,
-                                                  s->ex->prop.multiProcessorCount, st);
-        if (s->use_tma) return s->K->step_tma(static_cast<int>(s->cfg.scheme), rb, args, alt ? &s->maps_b : &s->maps_a,
-                                              s->ex->prop.multiProcessorCount, st);
+    // `spare_sms`: the persistent kernels fill every SM; the interior launch of a strip leaves a few SMs free so that
+    // the NCCL send/recv kernels of the halo exchange can run beside it instead of after it
+    auto step = [&](const hp::StepArgs& args, int spare_sms = 0) {
+        const int sms = s->ex->prop.multiProcessorCount - spare_sms > 0 ? s->ex->prop.multiProcessorCount - spare_sms : 1;
+        if (s->use_march) return s->K->step_march(static_cast<int>(s->cfg.scheme), rb, args, &s->march_map, alt ? 1 : 0, sms, st);
+        if (s->use_tma) return s->K->step_tma(static_cast<int>(s->cfg.scheme), rb, args, alt ? &s->maps_b : &s->maps_a, sms, st);
         return s->K->step(static_cast<int>(s->cfg.scheme), rb, args, st);
     };
     if (s->comm == nullptr) {
@@ -176,7 +178,7 @@ int enqueue_iteration(hp_scheme* s, bool alt, int* launched) {
         const char* err = hp::comm_exchange_halos(s->comm, a.dst, s->grid, halo, s->rb, s->comm_stream);
         if (err) return fail(HP_ERR_NCCL, "halo exchange: %s", err);
         if (cudaEventRecord(s->ev_halo, s->comm_stream) != cudaSuccess) return fail(HP_ERR_CUDA, "cudaEventRecord failed");
-        n += step(mid);
+        n += step(mid, kCommSpareSMs);
         if (cudaStreamWaitEvent(st, s->ev_halo, 0) != cudaSuccess) return fail(HP_ERR_CUDA, "cudaStreamWaitEvent failed");
         err = hp::comm_allreduce_max(s->comm, s->max_bits, st);
         if (err) return fail(HP_ERR_NCCL, "allreduce: %s", err);

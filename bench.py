@@ -432,7 +432,7 @@ def main():
 def run_variants(hx, ex, args):
     """Short device-resident runs of the other precision / schemes on the same 4096^2 dam break."""
     out = {}
-    for name in ("dambreak4096-f32", "dambreak4096-mh", "dambreak4096-mh-f32", "dambreak4096-inertial-f32"):
+    for name in ("dambreak4096-f32", "dambreak4096-mh", "dambreak4096-mh-f32", "dambreak4096-inertial", "dambreak4096-inertial-f32"):
         w = WORKLOADS[name]
         cfg = cfg_for(w, w["rows_per_gpu"], w["cols"])
         dtype = np.float64 if cfg.precision == "double" else np.float32

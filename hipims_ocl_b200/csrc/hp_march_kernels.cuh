@@ -40,8 +40,11 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
 #ifndef HP_MARCH_RR
 #define HP_MARCH_RR 4
 #endif
-template <class R, int HALO, bool ALT> struct March {
-    static constexpr int NW = hp::kMarchWarps, RR = HP_MARCH_RR, NP = 6;      // RR: ring rows (power of two)
+#ifndef HP_MARCH_MH_RR
+#define HP_MARCH_MH_RR 4
+#endif
+template <class R, int HALO, bool ALT, int RING = HP_MARCH_RR> struct March {
+    static constexpr int NW = hp::kMarchWarps, RR = RING, NP = 6;              // RR: ring rows (power of two)
     static constexpr int A16 = 16 / int(sizeof(R));                       // elements per 16 bytes
     static constexpr int USE = hp::march_use(int(sizeof(R)), HALO);       // cells updated per warp row
     static constexpr int PADL = ((-HALO) % A16 + A16) % A16;              // box starts 16-byte aligned
@@ -115,7 +118,7 @@ __global__ void __launch_bounds__(hp::kMarchWarps * 32, sizeof(R) == 8 ? 4 : 6)
 mh_step_march(const StepArgs a, const __grid_constant__ TmaBlockMap maps) {
     // lane halo of ONE column per side: the raw values two columns out come from the TMA box, which is two columns
     // wider than the warp (geometry of HALO = 1); only predictor values need a lane.  30 of 32 lanes update cells.
-    using T = March<R, 1, ALT>;
+    using T = March<R, 1, ALT, HP_MARCH_MH_RR>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* const ring = smem_raw + warp * T::WARP_BYTES;
@@ -812,7 +815,7 @@ static int march_grid(const StepArgs& a, int use, int nw, int ctas_per_sm, int s
 }
 
 template <class R> static int launch_mh_march(const StepArgs& a_in, const TmaBlockMap& maps, int alt, int sm_count, cudaStream_t st) {
-    using T = March<R, 1, false>;
+    using T = March<R, 1, false, HP_MARCH_MH_RR>;
     StepArgs a = a_in;
     if (a.y1 <= a.y0) return 0;
     static bool configured = false;

@@ -426,6 +426,7 @@ def main():
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
+        sim.close()                  # the NCCL communicator of the strip goes before the process group
         dist.destroy_process_group()
 
 

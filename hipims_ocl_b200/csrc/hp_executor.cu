@@ -8,6 +8,7 @@
 // reference blocks the host once per batch, CSchemeGodunov.cpp:1337-1341 -- so do we).
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -92,6 +93,11 @@ struct hp_scheme {
     hp::Comm* comm = nullptr;
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t ev_edges = nullptr, ev_halo = nullptr;
+    // HIPIMS_STRIP_TIMING=1 (with HP_OPT_NO_GRAPH): per-phase device times of the strip iteration, printed at destroy
+    bool strip_timing = false;
+    cudaEvent_t ev_t[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    double t_phase[5] = {0, 0, 0, 0, 0};
+    uint64_t t_count = 0, t_seen = 0;
 };
 
 namespace {
@@ -171,18 +177,32 @@ int enqueue_iteration(hp_scheme* s, bool alt, int* launched) {
         const int e0 = y0 + halo < y1 ? y0 + halo : y1, e1 = y1 - halo > e0 ? y1 - halo : e0;
         hp::StepArgs lo = a, hi = a, mid = a;
         lo.y1 = e0; hi.y0 = e1; mid.y0 = e0; mid.y1 = e1;
+        const bool timing = s->strip_timing && (s->cfg.options & HP_OPT_NO_GRAPH);
+        if (timing) cudaEventRecord(s->ev_t[0], st);
         n += step(lo);
         n += step(hi);
+        if (timing) cudaEventRecord(s->ev_t[1], st);
         if (cudaEventRecord(s->ev_edges, st) != cudaSuccess) return fail(HP_ERR_CUDA, "cudaEventRecord failed");
         if (cudaStreamWaitEvent(s->comm_stream, s->ev_edges, 0) != cudaSuccess) return fail(HP_ERR_CUDA, "cudaStreamWaitEvent failed");
         const char* err = hp::comm_exchange_halos(s->comm, a.dst, s->grid, halo, s->rb, s->comm_stream);
         if (err) return fail(HP_ERR_NCCL, "halo exchange: %s", err);
         if (cudaEventRecord(s->ev_halo, s->comm_stream) != cudaSuccess) return fail(HP_ERR_CUDA, "cudaEventRecord failed");
         n += step(mid, kCommSpareSMs);
+        if (timing) cudaEventRecord(s->ev_t[2], st);
         if (cudaStreamWaitEvent(st, s->ev_halo, 0) != cudaSuccess) return fail(HP_ERR_CUDA, "cudaStreamWaitEvent failed");
+        if (timing) cudaEventRecord(s->ev_t[3], st);
         err = hp::comm_allreduce_max(s->comm, s->max_bits, st);
         if (err) return fail(HP_ERR_NCCL, "allreduce: %s", err);
+        if (timing) cudaEventRecord(s->ev_t[4], st);
         n += s->K->advance(rb, a, st);
+        if (timing) {
+            cudaEventRecord(s->ev_t[5], st);
+            cudaEventSynchronize(s->ev_t[5]);
+            if (++s->t_seen > 10) {                                  // the first iterations carry NCCL's connection set-up
+                for (int i = 0; i < 5; ++i) { float ms = 0; cudaEventElapsedTime(&ms, s->ev_t[i], s->ev_t[i + 1]); s->t_phase[i] += ms; }
+                ++s->t_count;
+            }
+        }
     }
     if (launched) *launched += n;
     cudaError_t e = cudaGetLastError();
@@ -474,6 +494,11 @@ void hp_scheme_destroy(hp_scheme* s) {
     drop_graphs(s);
     if (s->comm) hp::comm_destroy(s->comm);
     if (s->comm_stream) cudaStreamDestroy(s->comm_stream);
+    if (s->strip_timing && s->t_count)
+        fprintf(stderr, "[hipims strip timing] %llu iterations, ms per iteration: edges %.4f | interior %.4f | wait halo %.4f | all-reduce %.4f | clock %.4f\n",
+                (unsigned long long)s->t_count, s->t_phase[0] / s->t_count, s->t_phase[1] / s->t_count, s->t_phase[2] / s->t_count,
+                s->t_phase[3] / s->t_count, s->t_phase[4] / s->t_count);
+    for (auto& e : s->ev_t) if (e) cudaEventDestroy(e);
     if (s->ev_edges) cudaEventDestroy(s->ev_edges);
     if (s->ev_halo) cudaEventDestroy(s->ev_halo);
     cudaFree(s->block); cudaFree(s->clock); cudaFree(s->max_bits); cudaFree(s->ticket); cudaFree(s->staging);
@@ -633,8 +658,12 @@ int hp_scheme_iterate(hp_scheme* s, uint32_t iterations) {
     HP_CUDA(cudaSetDevice(s->ex->device));
     uint32_t left = iterations;
     // with a communicator the halo send/recv, the all-reduce and the fork/join onto the communication stream are
-    // captured too (NCCL records its kernels into the graph), so a strip costs one graph launch per 16 iterations
-    const bool use_graph = !(s->cfg.options & HP_OPT_NO_GRAPH);
+    // captured too (NCCL records its kernels into the graph), so a strip costs one graph launch per 16 iterations.
+    // Measured on 4 GPUs: that pays on small strips (4096 x 4096: +1.5 %), but a captured exchange no longer overlaps
+    // the interior kernel of a large strip (32768 x 4096: 2.74 ms per step against 2.38 ms launched directly), so
+    // large strips are launched directly -- their launch latency is hidden anyway.
+    const bool small_strip = static_cast<long long>(s->grid.rows) * s->grid.cols <= (32ll << 20);
+    const bool use_graph = !(s->cfg.options & HP_OPT_NO_GRAPH) && (s->comm == nullptr || small_strip);
     int rc = HP_OK;
     auto direct = [&]() {
         int launched = 0;
@@ -701,6 +730,8 @@ int hp_scheme_attach_comm(hp_scheme* s, const void* id, int rank, int world_size
     HP_CUDA(cudaStreamCreateWithFlags(&s->comm_stream, cudaStreamNonBlocking));
     HP_CUDA(cudaEventCreateWithFlags(&s->ev_edges, cudaEventDisableTiming));
     HP_CUDA(cudaEventCreateWithFlags(&s->ev_halo, cudaEventDisableTiming));
+    if (const char* t = getenv("HIPIMS_STRIP_TIMING")) s->strip_timing = t[0] == '1';
+    if (s->strip_timing) for (auto& e : s->ev_t) HP_CUDA(cudaEventCreate(&e));
     drop_graphs(s);
     return HP_OK;
 }

@@ -102,12 +102,55 @@ def build_variant(name, force=False):
     return out
 
 
+# ---------------------------------------------------------------------------------------------
+# Output rasters: the per-cell `switch( ucValue )` of CRasterDataset::domainToRaster
+# (src/Datasets/CRasterDataset.cpp) is the only arithmetic of that GDAL writer.  Its text is cut out
+# of the reference file where it lies and compiled between stand-ins for pDomain / pBand
+# (oracle/ref_shim/raster_shim.h) into oracle/_ref/ref_raster.so: ref_raster_value(code, state4,
+# bed, resolution) returns exactly what the reference would hand to RasterIO for one cell.
+# ---------------------------------------------------------------------------------------------
+RASTER_LIB = os.path.join(OUT, "ref_raster.so")
+
+
+def _raster_switch_text():
+    with open(os.path.join(REF_SRC, "Datasets/CRasterDataset.cpp"), "r", encoding="latin-1") as f:
+        text = f.read()
+    start = text.index("switch( ucValue )", text.index("CRasterDataset::domainToRaster"))
+    depth, i = 0, text.index("{", start)
+    for j in range(i, len(text)):
+        depth += text[j] == "{"
+        depth -= text[j] == "}"
+        if depth == 0:
+            return text[start:j + 1]
+    raise RuntimeError("unbalanced switch in CRasterDataset.cpp")
+
+
+def build_raster(force=False):
+    shim = os.path.join(HERE, "ref_shim", "raster_shim.h")
+    if os.path.exists(RASTER_LIB) and not force and \
+            all(os.path.getmtime(RASTER_LIB) >= os.path.getmtime(d) for d in (shim, os.path.abspath(__file__))):
+        return RASTER_LIB
+    os.makedirs(OUT, exist_ok=True)
+    tu = '#include "raster_shim.h"\nextern "C" double ref_raster_value(unsigned char ucValue, const double* state4, double bed, double dResolution) {\n' \
+         '    RASTER_SHIM_PROLOGUE\n#line 1 "Datasets/CRasterDataset.cpp (switch)"\n' + _raster_switch_text() + '\n    return dRow[iCol];\n}\n'
+    with tempfile.TemporaryDirectory(prefix="hpo_ref_") as tmp:
+        src = os.path.join(tmp, "unit_raster.cpp")
+        with open(src, "w") as f:
+            f.write(tu)
+        cmd = ["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-w", "-shared", "-fPIC", "-I", os.path.join(HERE, "ref_shim"), src, "-o", RASTER_LIB]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("reference raster shim build failed:\n%s" % res.stderr[-4000:])
+    return RASTER_LIB
+
+
 def build_all(variants=None, force=False):
     if not reference_available():
         return []
     variants = variants or DEFAULT_VARIANTS
     with ThreadPoolExecutor(max_workers=min(8, len(variants))) as ex:
-        return list(ex.map(lambda v: build_variant(v, force), variants))
+        libs = list(ex.map(lambda v: build_variant(v, force), variants))
+    return libs + [build_raster(force)]
 
 
 if __name__ == "__main__":

@@ -4,9 +4,11 @@ TEST INFRASTRUCTURE (see oracle/hpo_api.h): follows CRasterDataset::domainToRast
 src/Datasets/CRasterDataset.cpp:180-280 of the reference, value by value, in float64 like the
 reference's host loop (numpy evaluates every operation separately: no FMA contraction).
 
-Parity UNPINNED for this function: the reference routine cannot be compiled here (it is a GDAL
-writer) and the reference ships no golden rasters; the restatement is anchored on the source lines
-cited below and on hand-computed cases in tests/test_raster_outputs.py.
+Pinned to the reference: the routine itself is a GDAL writer and cannot be built here, but its only
+arithmetic -- the per-cell `switch( ucValue )` -- is cut out of the reference source where it lies and
+compiled between stand-ins for pDomain / pBand (oracle/build_ref.py:build_raster,
+oracle/ref_shim/raster_shim.h).  This restatement is bit-identical to it on adversarial cells
+(tests/test_raster_outputs.py, live and through tests/golden/raster_values.npz).
 """
 import numpy as np
 

@@ -78,9 +78,42 @@ def newcastle():
         outs[600][1]["time"], int(((outs[600][0][..., 0] - bed) > 1e-10).sum())))
 
 
+def raster_values():
+    """Output-raster derivation: the reference's own per-cell switch (CRasterDataset::domainToRaster, compiled by
+    oracle/build_ref.py:build_raster) on adversarial cells -- thresholds at 1e-8, dry, disabled, bed above 9999."""
+    import ctypes as C
+    from oracle import build_ref
+    lib = C.CDLL(build_ref.build_raster())
+    lib.ref_raster_value.restype = C.c_double
+    lib.ref_raster_value.argtypes = [C.c_ubyte, C.POINTER(C.c_double), C.c_double, C.c_double]
+    rng = np.random.default_rng(20260817)
+    rows, cols, res = 24, 40, 2.0
+    bed = np.round(rng.uniform(-5.0, 60.0, size=(rows, cols)), 4)
+    depth = np.where(rng.random((rows, cols)) < 0.4, 0.0, rng.uniform(0.0, 3.0, size=(rows, cols)))
+    depth.flat[::7] = rng.choice([1e-8, 0.99e-8, 1.01e-8, 1e-10, 5e-9], size=depth.flat[::7].size)     # around the 1e-8 rule
+    st = np.zeros((rows, cols, 4))
+    st[..., 0] = bed + depth
+    st[..., 1] = st[..., 0] + np.where(rng.random((rows, cols)) < 0.5, 0.0, rng.uniform(0.0, 1.0, size=(rows, cols)))
+    st[..., 2:] = rng.normal(size=(rows, cols, 2)) * (depth > 0)[..., None]
+    st[3, 5, 1] = -9999.0                      # disabled cell
+    bed[7, 9] = 9999.9; st[7, 9, :2] = 9999.9  # closed-edge bed (CDomainCartesian.cpp:773-799)
+    bed[8, 9] = 10000.5; st[8, 9, :2] = 10001.0
+    out = {}
+    for code in range(12):
+        a = np.empty((rows, cols))
+        for y in range(rows):
+            for x in range(cols):
+                cell = np.ascontiguousarray(st[y, x])
+                a[rows - 1 - y, x] = lib.ref_raster_value(code, cell.ctypes.data_as(C.POINTER(C.c_double)), float(bed[y, x]), res)
+        out["value_%d" % code] = a
+    np.savez_compressed(os.path.join(HERE, "raster_values.npz"), states=st, bed=bed, resolution=res, **out)
+    print("wrote raster_values.npz (%d cells x 12 value codes from the reference's switch)" % (rows * cols))
+
+
 def main():
     if os.path.exists("/root/reference/test/newcastle-centre.xml"):
         newcastle()
+        raster_values()
     for name, (scheme, precision, scen, bdy, rows, cols, iters, extra) in CASES.items():
         cfg = make_cfg(scheme, precision, rows, cols, **extra)
         bed, st, man = scenario(scen, rows, cols, dtype_of(precision))

@@ -1,5 +1,7 @@
 """Output rasters: the device derivation against the oracle, and the oracle against
 hand-computed cases of CRasterDataset::domainToRaster (src/Datasets/CRasterDataset.cpp:180-280)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -34,6 +36,57 @@ def test_oracle_matches_hand_computed_cases():
     assert ro.derive_raster(0, st, bed, 2.0).tolist() == [[nd] * 3, [nd] * 3]      # codes without a case stay no-data
     assert set(hc.RASTER_VALUES.values()) == {ro.DEPTH, ro.FSL, ro.VELOCITY_X, ro.VELOCITY_Y, ro.DISCHARGE_X, ro.DISCHARGE_Y,
                                               ro.MAX_DEPTH, ro.MAX_FSL, ro.FROUDE}
+
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "raster_values.npz")
+
+
+def test_oracle_matches_the_reference_switch_golden():
+    """tests/golden/raster_values.npz holds what the reference's own `switch( ucValue )` of CRasterDataset::domainToRaster
+    (compiled from /root/reference by oracle/build_ref.py:build_raster) returns for 960 adversarial cells."""
+    z = np.load(GOLDEN)
+    for code in range(12):
+        np.testing.assert_array_equal(ro.derive_raster(code, z["states"], z["bed"], float(z["resolution"])), z["value_%d" % code],
+                                      err_msg="value code %d" % code)
+
+
+def test_oracle_matches_the_reference_switch_live():
+    """Same check against the reference source itself, on fresh random cells (skipped where /root/reference is absent)."""
+    import ctypes as C
+    from oracle import build_ref
+    if not build_ref.reference_available():
+        pytest.skip("reference tree not present")
+    lib = C.CDLL(build_ref.build_raster())
+    lib.ref_raster_value.restype = C.c_double
+    lib.ref_raster_value.argtypes = [C.c_ubyte, C.POINTER(C.c_double), C.c_double, C.c_double]
+    rng = np.random.default_rng(99)
+    n = 600
+    bed = rng.uniform(-10.0, 100.0, size=(1, n))
+    depth = np.where(rng.random((1, n)) < 0.3, 0.0, 10.0 ** rng.uniform(-10.0, 1.0, size=(1, n)))
+    st = np.zeros((1, n, 4))
+    st[..., 0] = bed + depth
+    st[..., 1] = st[..., 0] + rng.uniform(0.0, 0.5, size=(1, n)) * (rng.random((1, n)) < 0.5)
+    st[..., 2:] = rng.normal(size=(1, n, 2))
+    for code in range(12):
+        want = np.array([[lib.ref_raster_value(code, np.ascontiguousarray(st[0, i]).ctypes.data_as(C.POINTER(C.c_double)), float(bed[0, i]), 3.0)
+                          for i in range(n)]])
+        np.testing.assert_array_equal(ro.derive_raster(code, st, bed, 3.0), want, err_msg="value code %d" % code)
+
+
+@pytest.mark.gpu
+def test_device_rasters_match_the_reference_switch_golden():
+    from hipims_ocl_b200 import executor as hx
+    z = np.load(GOLDEN)
+    st, bed = z["states"], z["bed"]
+    rows, cols = bed.shape
+    cfg = make_cfg("godunov", "double", rows, cols, delta=float(z["resolution"]))
+    ex = hx.Executor(0)
+    sim = hx.CudaScheme(ex, cfg)
+    sim.upload(st, bed, np.full((rows, cols), 0.03))
+    for code in range(12):
+        np.testing.assert_array_equal(sim.derive_raster(code), z["value_%d" % code], err_msg="value code %d" % code)
+    sim.close()
+    ex.close()
 
 
 @pytest.mark.gpu

@@ -144,13 +144,43 @@ def build_raster(force=False):
     return RASTER_LIB
 
 
+# Util::round (src/util.cpp): the 4-decimal rounding every ingested DEM / depth value goes through.
+UTIL_LIB = os.path.join(OUT, "ref_util.so")
+
+
+def build_util(force=False):
+    if os.path.exists(UTIL_LIB) and not force and os.path.getmtime(UTIL_LIB) >= os.path.getmtime(os.path.abspath(__file__)):
+        return UTIL_LIB
+    with open(os.path.join(REF_SRC, "util.cpp"), "r", encoding="latin-1") as f:
+        text = f.read()
+    start = text.index("double\tround( double dValue, unsigned char ucPlaces )")
+    depth, i = 0, text.index("{", start)
+    for j in range(i, len(text)):
+        depth += text[j] == "{"
+        depth -= text[j] == "}"
+        if depth == 0:
+            break
+    os.makedirs(OUT, exist_ok=True)
+    tu = "#include <cmath>\nnamespace Util {\n" + text[start:j + 1] + "\n}\n" \
+         'extern "C" double ref_round(double v, unsigned char places) { return Util::round(v, places); }\n'
+    with tempfile.TemporaryDirectory(prefix="hpo_ref_") as tmp:
+        src = os.path.join(tmp, "unit_util.cpp")
+        with open(src, "w") as f:
+            f.write(tu)
+        res = subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-w", "-shared", "-fPIC", src, "-o", UTIL_LIB],
+                             capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("reference util shim build failed:\n%s" % res.stderr[-4000:])
+    return UTIL_LIB
+
+
 def build_all(variants=None, force=False):
     if not reference_available():
         return []
     variants = variants or DEFAULT_VARIANTS
     with ThreadPoolExecutor(max_workers=min(8, len(variants))) as ex:
         libs = list(ex.map(lambda v: build_variant(v, force), variants))
-    return libs + [build_raster(force)]
+    return libs + [build_raster(force), build_util(force)]
 
 
 if __name__ == "__main__":

@@ -199,6 +199,27 @@ def test_rounding_matches_reference_util_round(host):
         assert host.hph_round(v, 4) == float(sc.round4(v))
 
 
+def test_rounding_is_the_reference_function(host):
+    """The mirror's Util::round and the scenario generator's round4 against the reference's own Util::round, compiled from
+    src/util.cpp where it lies (skipped where /root/reference is absent)."""
+    from oracle import build_ref
+    if not build_ref.reference_available():
+        pytest.skip("reference tree not present")
+    ref = C.CDLL(build_ref.build_util())
+    ref.ref_round.restype = C.c_double
+    ref.ref_round.argtypes = [C.c_double, C.c_ubyte]
+    rng = np.random.default_rng(4)
+    values = np.concatenate([rng.normal(scale=50.0, size=4000), rng.normal(scale=1e-3, size=1000),
+                             np.round(rng.normal(scale=10.0, size=1000), 4) + 0.00005, [0.0, -0.0, 1e-9, -1e-9, 9999.9, -9999.0]])
+    for v in values:
+        want = ref.ref_round(float(v), 4)
+        assert host.hph_round(float(v), 4) == want
+        assert float(sc.round4(float(v))) == want
+    for places in (0, 1, 2, 6):
+        for v in values[:500]:
+            assert host.hph_round(float(v), places) == ref.ref_round(float(v), places)
+
+
 def test_raster_writers_round_trip(host, tmp_path):
     """GeoTIFF / ENVI / ESRI ASCII written by the GDAL-free CRasterDataset stand-in: values bit-exact, georeferencing
     as src/Datasets/CRasterDataset.cpp:163-176 sets it (top-left origin, negative y resolution, no-data -9999)."""

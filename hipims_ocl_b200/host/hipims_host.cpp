@@ -640,6 +640,97 @@ bool CDomainCartesian::writeOutputs(double dTime, CScheme* pScheme) {       // s
 }
 
 // ---------------------------------------------------------------------------------------------
+// Multi-domain sets -> one domain
+// ---------------------------------------------------------------------------------------------
+CDomainCartesian* CDomainCartesian::mergeStacked(std::vector<std::unique_ptr<CDomainCartesian>>& parts, std::vector<unsigned long>& off) {
+    const size_t n = parts.size();
+    std::vector<size_t> order(n);
+    for (size_t i = 0; i < n; ++i) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return parts[a]->dRealOffsetY < parts[b]->dRealOffsetY; });
+    const CDomainCartesian& first = *parts[order[0]];
+    const double res = first.dCellResolution;
+    off.assign(n, 0);
+    std::vector<unsigned long> split(n + 1, 0);          // merged row where part order[k] starts to be authoritative
+    unsigned long total = first.ulRows;
+    for (size_t k = 1; k < n; ++k) {
+        const CDomainCartesian &lo = *parts[order[k - 1]], &hi = *parts[order[k]];
+        // the linking rules of CDomainLink::canLink (Links/CDomainLink.cpp:73-136)
+        if (hi.dCellResolution != res) { model::doError("Cannot merge domains of mismatched resolutions.", model::errorCodes::kLevelModelStop); return nullptr; }
+        if (hi.ulCols != first.ulCols || std::fabs(hi.dRealOffsetX - first.dRealOffsetX) > 0.1 * res) {
+            model::doError("Only domains stacked north-south over the same columns can be merged.", model::errorCodes::kLevelModelStop); return nullptr; }
+        const double top = lo.dRealOffsetY + res * lo.ulRows;
+        const double gap = top - hi.dRealOffsetY;       // overlap in metres
+        if (gap < -0.1 * res) { model::doError("Domains do not overlap or touch on the N/S axis.", model::errorCodes::kLevelModelStop); return nullptr; }
+        if (std::fabs(std::remainder(gap, res)) > 0.1 * res) { model::doError("Cannot merge domains that are not aligned N/S.", model::errorCodes::kLevelModelStop); return nullptr; }
+        const unsigned long ov = static_cast<unsigned long>(std::llround(gap / res));
+        if (ov >= lo.ulRows || ov >= hi.ulRows) { model::doError("A domain lies entirely inside another.", model::errorCodes::kLevelModelStop); return nullptr; }
+        off[order[k]] = off[order[k - 1]] + lo.ulRows - ov;
+        split[k] = off[order[k]] + ov / 2;
+        total = off[order[k]] + hi.ulRows;
+    }
+    split[n] = total;
+    std::unique_ptr<CDomainCartesian> m(new CDomainCartesian());
+    m->ulCols = first.ulCols; m->ulRows = total; m->dCellResolution = res; m->dRealOffsetX = first.dRealOffsetX; m->dRealOffsetY = first.dRealOffsetY;
+    m->sSourceDir = first.sSourceDir; m->sTargetDir = first.sTargetDir;
+    m->dCellStates.assign(4 * m->getCellCount(), 0.0); m->dBedElevations.assign(m->getCellCount(), 0.0); m->dManningValues.assign(m->getCellCount(), 0.0);
+    for (size_t k = 0; k < n; ++k) {
+        CDomainCartesian& p = *parts[order[k]];
+        const unsigned long o = off[order[k]];
+        for (unsigned long y = 0; y < p.ulRows; ++y) {
+            const unsigned long my = o + y;
+            if (my < split[k] || my >= split[k + 1]) continue;           // the neighbour is authoritative there
+            std::copy(p.dCellStates.begin() + 4 * y * p.ulCols, p.dCellStates.begin() + 4 * (y + 1) * p.ulCols, m->dCellStates.begin() + 4 * my * m->ulCols);
+            std::copy(p.dBedElevations.begin() + y * p.ulCols, p.dBedElevations.begin() + (y + 1) * p.ulCols, m->dBedElevations.begin() + my * m->ulCols);
+            std::copy(p.dManningValues.begin() + y * p.ulCols, p.dManningValues.begin() + (y + 1) * p.ulCols, m->dManningValues.begin() + my * m->ulCols);
+        }
+        // boundaries: cell maps move with their part and keep only the cells the part is authoritative for; domain-wide
+        // (atmospheric / gridded) series apply to the merged domain once
+        for (auto& b : p.boundaryMap.boundaries) {
+            if (auto* cell = dynamic_cast<CBoundaryCell*>(b.get())) {
+                std::vector<std::pair<unsigned int, unsigned int>> kept;
+                for (const auto& r : cell->relations) { const unsigned long my = o + r.second; if (my >= split[k] && my < split[k + 1]) kept.emplace_back(r.first, static_cast<unsigned int>(my)); }
+                if (kept.size() != cell->relations.size() && cell->bDischargeIsTotal)
+                    model::doError("Boundary '" + cell->getName() + "': cells in another domain's half of an overlap were dropped.", model::errorCodes::kLevelInformation);
+                cell->relations = kept;
+                m->boundaryMap.boundaries.push_back(std::move(b));
+            } else if (!m->boundaryMap.getBoundaryByName(b->getName())) {
+                if (k > 0) model::doError("Boundary '" + b->getName() + "' now applies to the whole merged domain.", model::errorCodes::kLevelInformation);
+                m->boundaryMap.boundaries.push_back(std::move(b));
+            }
+        }
+        p.boundaryMap.boundaries.clear();
+    }
+    return m.release();
+}
+
+bool CDomainCartesian::writeCroppedOutputs(double dTime, const CDomainCartesian& merged, unsigned long o, CScheme* pScheme,
+                                           std::map<unsigned char, std::vector<double>>& cache) const {
+    bool ok = true;
+    for (const auto& out : outputs) {
+        const unsigned char code = getDataValueCode(out.sValue);
+        auto it = cache.find(code);
+        if (it == cache.end()) {
+            std::vector<double> band;
+            if (!(pScheme && pScheme->deriveRaster(code, band))) {
+                band.resize(merged.getCellCount());
+                for (unsigned long y = 0; y < merged.ulRows; ++y) for (unsigned long x = 0; x < merged.ulCols; ++x) {
+                    const unsigned long i = merged.getCellID(x, y);
+                    band[(merged.ulRows - 1 - y) * merged.ulCols + x] = deriveOutput(code, &merged.dCellStates[4 * i], merged.dBedElevations[i], merged.dCellResolution, -9999.0);
+                }
+            }
+            it = cache.emplace(code, std::move(band)).first;
+        }
+        std::string file = out.sTarget; const size_t pos = file.find("%t");
+        char tbuf[64]; snprintf(tbuf, sizeof(tbuf), "%g", std::floor(dTime * 100.0) / 100.0);
+        if (pos != std::string::npos) file.replace(pos, 2, tbuf);
+        // north-first band: this part's northern edge is merged row o + ulRows - 1
+        const double* start = it->second.data() + (merged.ulRows - (o + ulRows)) * merged.ulCols;
+        ok = CRasterDataset::writeRaster(out.sFormat, sTargetDir + file, ulCols, ulRows, dRealOffsetX, dRealOffsetY, dCellResolution, start) && ok;
+    }
+    return ok;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Raster writers
 // ---------------------------------------------------------------------------------------------
 namespace {
@@ -888,12 +979,27 @@ bool CModel::loadConfiguration(const std::string& sPath, bool bDeviceless) {
     const XMLElement* set = sim->FirstChildElement("domainSet");
     const XMLElement* dom = set ? set->FirstChildElement("domain") : nullptr;
     if (!dom) { model::doError("No <domain> defined.", model::errorCodes::kLevelModelStop); return false; }
-    if (dom->NextSiblingElement("domain")) model::doError("Only the first <domain> is used; multi-domain sets map onto row strips (see DESIGN.md).", model::errorCodes::kLevelWarning);
-    if (Util::toLowercase(dom->Attribute("type")) != "cartesian") { model::doError("Unsupported domain type.", model::errorCodes::kLevelModelStop); return false; }
-    pDomain.reset(new CDomainCartesian());
-    // boundary files are relative to the configuration file
-    if (!pDomain->configureDomain(dom, dir)) return false;
-    pScheme.reset(CScheme::createFromConfig(dom->FirstChildElement("scheme")));
+    const XMLElement* pXScheme = dom->FirstChildElement("scheme");
+    if (!dom->NextSiblingElement("domain")) {
+        if (Util::toLowercase(dom->Attribute("type")) != "cartesian") { model::doError("Unsupported domain type.", model::errorCodes::kLevelModelStop); return false; }
+        pDomain.reset(new CDomainCartesian());
+        // boundary files are relative to the configuration file
+        if (!pDomain->configureDomain(dom, dir)) return false;
+    } else {
+        // several <domain>s (CDomainManager.cpp:56-282): merged into one, see CDomainCartesian::mergeStacked
+        const std::string schemeName = Util::toLowercase(pXScheme ? pXScheme->Attribute("name") : nullptr);
+        for (const XMLElement* d = dom; d; d = d->NextSiblingElement("domain")) {
+            if (Util::toLowercase(d->Attribute("type")) != "cartesian") { model::doError("Unsupported domain type.", model::errorCodes::kLevelModelStop); return false; }
+            parts.emplace_back(new CDomainCartesian());
+            if (!parts.back()->configureDomain(d, dir)) return false;
+            const XMLElement* sch = d->FirstChildElement("scheme");
+            if (Util::toLowercase(sch ? sch->Attribute("name") : nullptr) != schemeName)
+                model::doError("Domains name different schemes; the first domain's scheme is used for the merged domain.", model::errorCodes::kLevelWarning);
+        }
+        pDomain.reset(CDomainCartesian::mergeStacked(parts, partRowOffsets));
+        if (!pDomain) return false;
+    }
+    pScheme.reset(CScheme::createFromConfig(pXScheme));
     if (!pScheme) return false;
     if (bDeviceless) return true;      // host-side parsing only (CPU tests)
     return pScheme->prepareAll(pExecutor.get(), pDomain.get(), ucFloatPrecision, dSimulationTime);
@@ -906,7 +1012,12 @@ bool CModel::runModel() {
     while (!model::forceAbort && pScheme->getCurrentTime() < dSimulationTime - 1E-5) {
         const double target = std::min(nextOutput, dSimulationTime);
         while (!model::forceAbort && pScheme->getCurrentTime() < target - 1E-5) pScheme->runSimulation(target, 0.0);
-        pDomain->writeOutputs(pScheme->getCurrentTime(), pScheme.get());      // derived on the device; no full-state read-back
+        if (parts.empty()) {
+            pDomain->writeOutputs(pScheme->getCurrentTime(), pScheme.get());  // derived on the device; no full-state read-back
+        } else {                                                              // every original domain gets its own rasters
+            std::map<unsigned char, std::vector<double>> bands;
+            for (size_t i = 0; i < parts.size(); ++i) parts[i]->writeCroppedOutputs(pScheme->getCurrentTime(), *pDomain, partRowOffsets[i], pScheme.get(), bands);
+        }
         nextOutput += dOutputFrequency > 0.0 ? dOutputFrequency : dSimulationTime;
     }
     pScheme->readDomainAll();                                              // final state back in the CDomain arrays
@@ -931,6 +1042,11 @@ void hph_model_info(void* h, unsigned long* cols, unsigned long* rows, double* r
     *cols = m->getDomain()->getCols(); *rows = m->getDomain()->getRows(); *resolution = m->getDomain()->getCellResolution();
     *duration = m->getSimulationLength(); *output_frequency = m->getOutputFrequency(); *precision = m->getFloatPrecision();
     *scheme = m->getScheme()->getSchemeType(); *boundaries = m->getDomain()->getBoundaries()->getBoundaryCount();
+}
+unsigned int hph_model_parts(void* h, unsigned long* row_offsets, unsigned int capacity) {
+    CModel* m = static_cast<CModel*>(h);
+    for (unsigned int i = 0; i < m->getPartCount() && i < capacity; ++i) row_offsets[i] = m->getPartRowOffset(i);
+    return m->getPartCount();
 }
 void hph_model_scheme_params(void* h, double* courant, double* dry, double* timestep, int* dynamic, int* friction, unsigned int* queue) {
     CScheme* s = static_cast<CModel*>(h)->getScheme();

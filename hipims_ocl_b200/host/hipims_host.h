@@ -195,6 +195,15 @@ class CDomainCartesian {
     // 8-byte value per cell crosses PCIe instead of the whole state), else from the host arrays
     bool writeOutputs(double dTime, CScheme* pScheme = nullptr);
     static double deriveOutput(unsigned char ucValue, const double* state, double bed, double resolution, double nodata);
+    // Multi-domain sets (src/Domain/CDomainManager.cpp:56-282, Links/CDomainLink.cpp:73-136): domains stacked north-south
+    // with overlapping extents become ONE domain -- a B200's 180 GB holds what the reference spreads over several
+    // devices, and the overlap exchange disappears.  Each part is authoritative up to the middle of its overlaps.
+    // Returns the merged domain (boundaries moved into it, cell maps shifted) or NULL with doError; `rowOffsets[i]` is
+    // the merged row of part i's southern edge.
+    static CDomainCartesian* mergeStacked(std::vector<std::unique_ptr<CDomainCartesian>>& parts, std::vector<unsigned long>& rowOffsets);
+    // one part's rasters cut out of the merged domain's (north-first) band
+    bool writeCroppedOutputs(double dTime, const CDomainCartesian& merged, unsigned long ulRowOffset, CScheme* pScheme,
+                             std::map<unsigned char, std::vector<double>>& bandCache) const;
     CBoundaryMap* getBoundaries() { return &boundaryMap; }
     // host cell arrays, reference layout (src/Domain/CDomain.h:28-33); always double on the host side
     std::vector<double> dCellStates;      // cells x {eta, eta_max, qx, qy}
@@ -286,4 +295,10 @@ class CModel {
     std::unique_ptr<CExecutorControlCUDA> pExecutor;
     std::unique_ptr<CDomainCartesian> pDomain;
     std::unique_ptr<CScheme> pScheme;
+    // multi-domain configurations: the original domains (for their data targets) and where they sit in pDomain
+    std::vector<std::unique_ptr<CDomainCartesian>> parts;
+    std::vector<unsigned long> partRowOffsets;
+  public:
+    unsigned int getPartCount() const { return static_cast<unsigned int>(parts.size()); }
+    unsigned long getPartRowOffset(unsigned int i) const { return partRowOffsets[i]; }
 };

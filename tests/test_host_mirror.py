@@ -380,3 +380,109 @@ def test_model_run_matches_oracle_driven_the_same_way(host, model_dir, scheme, n
     maxd, _ = read_tiff(os.path.join(out, "maxdepth_30.tif"))
     np.testing.assert_array_equal(maxd, ro.derive_raster(ro.MAX_DEPTH, st1, bed, 2.0))
     host.hph_model_destroy(C.c_void_p(h))
+
+
+# ---- multi-domain sets: domains stacked north-south are merged into one ------------------------------
+MULTI_XML = """<?xml version="1.0"?>
+<configuration>
+	<metadata><name>Two stacked domains</name><description>same schema as the reference's multi-domain sets</description></metadata>
+	<execution><executor name="OpenCL"><parameter name="deviceFilter" value="GPU" /></executor></execution>
+	<simulation>
+		<parameter name="duration" value="{duration}" />
+		<parameter name="outputFrequency" value="{duration}" />
+		<parameter name="floatingPointPrecision" value="double" />
+		<domainSet syncMethod="timestep">
+{domains}
+		</domainSet>
+	</simulation>
+</configuration>
+"""
+DOMAIN_XML = """			<domain type="cartesian" deviceNumber="{device}">
+				<data sourceDir="topography/" targetDir="output/">
+					<dataSource type="constant" value="depth" source="0.0" />
+					<dataSource type="constant" value="manningCoefficient" source="0.030" />
+					<dataSource type="raster" value="structure,dem" source="{dem}" />
+					<dataTarget type="raster" value="depth" format="GTiff" target="{tag}_depth_%t.tif" />
+				</data>
+				<scheme name="Godunov"><parameter name="courantNumber" value="0.50" /><parameter name="queueSize" value="16" /></scheme>
+				<boundaryConditions sourceDir="boundaries/">
+					<timeseries type="atmospheric" name="Rainfall" value="rain-intensity" source="rainfall.csv" />
+					<timeseries type="cell" name="Inflow_{tag}" depthValue="ignore" dischargeValue="volume" source="inflow.csv" mapFile="map_{tag}.csv" />
+				</boundaryConditions>
+			</domain>"""
+
+
+def make_stacked(tmp_path, overlap_marker=0.0, duration=20):
+    """A 70 x 40 terrain as two 40-row domains overlapping by 10 rows (upper listed FIRST), plus the same terrain as one
+    domain.  `overlap_marker` is added to the upper file's overlap rows to show which part the merge trusts."""
+    for d in ("topography", "output", "boundaries"):
+        os.makedirs(tmp_path / d, exist_ok=True)
+    rows, cols, res, yll = 70, 40, 2.0, 565146.0
+    bed = np.round(sc.fractal_dem(rows, cols, 9, amplitude=3.0), 4)
+    write_asc(tmp_path / "topography" / "full.asc", bed, res, yll=yll)
+    write_asc(tmp_path / "topography" / "lower.asc", bed[:40], res, yll=yll)
+    upper = bed[30:].copy()
+    upper[:10] += overlap_marker
+    write_asc(tmp_path / "topography" / "upper.asc", upper, res, yll=yll + 30 * res)
+    (tmp_path / "boundaries" / "rainfall.csv").write_text("Time (s),Rainfall intensity (mm/hr)\n0,70\n3600,70\n7200,0\n10800,0\n")
+    (tmp_path / "boundaries" / "inflow.csv").write_text("t,depth,qx,qy\n0,0,0,0\n5,0,4.0,0\n100000,0,4.0,0\n")
+    (tmp_path / "boundaries" / "map_lower.csv").write_text("x,y\n1,10\n1,36\n")     # local row 36 = merged 36: the upper part's half
+    (tmp_path / "boundaries" / "map_upper.csv").write_text("x,y\n2,3\n2,20\n")      # local row 3 = merged 33: the lower part's half
+    (tmp_path / "boundaries" / "map_full.csv").write_text("x,y\n1,10\n")
+    two = "\n".join(DOMAIN_XML.format(device=i + 1, dem=t + ".asc", tag=t) for i, t in enumerate(("upper", "lower")))
+    (tmp_path / "stacked.xml").write_text(MULTI_XML.format(duration=duration, domains=two))
+    (tmp_path / "single.xml").write_text(MULTI_XML.format(duration=duration, domains=DOMAIN_XML.format(device=1, dem="full.asc", tag="full")))
+    return bed
+
+
+def test_stacked_domains_merge_into_one(host, tmp_path):
+    bed = make_stacked(tmp_path, overlap_marker=100.0)
+    h = host.hph_model_load(str(tmp_path / "stacked.xml").encode(), 1)
+    assert h, [host.hph_error(i) for i in range(host.hph_error_count())]
+    i = info(host, h)
+    assert (i["rows"], i["cols"], i["resolution"]) == (70, 40, 2.0)
+    offsets = (C.c_ulong * 4)()
+    host.hph_model_parts.argtypes = [C.c_void_p, C.POINTER(C.c_ulong), C.c_uint]
+    assert host.hph_model_parts(C.c_void_p(h), offsets, 4) == 2 and list(offsets[:2]) == [30, 0]     # XML order: upper, lower
+    st, merged, man = arrays(host, h, 70, 40)
+    expect = bed.copy()
+    expect[35:40] = sc.round4(bed[35:40] + 100.0)            # rows 30..34 of the overlap from the lower part, 35..39 from the upper
+    np.testing.assert_array_equal(merged, expect)
+    np.testing.assert_array_equal(st[..., 0], expect)
+    assert (man == 0.03).all()
+    # boundaries: one Rainfall for the merged domain, each cell map keeps the cells its part is authoritative for
+    b = boundaries(host, h, i["boundaries"])
+    assert sorted((x["kind"], x["relations"]) for x in b) == [(0, 0), (2, 1), (2, 1)]
+    host.hph_model_destroy(C.c_void_p(h))
+    # misaligned / non-overlapping stacks are refused like CDomainLink::canLink refuses them
+    write_asc(tmp_path / "topography" / "upper.asc", bed[30:], 2.0, yll=565146.0 + 30 * 2.0 + 0.7)
+    assert not host.hph_model_load(str(tmp_path / "stacked.xml").encode(), 1)
+    assert b"not aligned" in host.hph_error(host.hph_error_count() - 1)
+    write_asc(tmp_path / "topography" / "upper.asc", bed[30:], 2.0, yll=565146.0 + 50 * 2.0)
+    assert not host.hph_model_load(str(tmp_path / "stacked.xml").encode(), 1)
+    assert b"do not overlap" in host.hph_error(host.hph_error_count() - 1)
+
+
+@pytest.mark.gpu
+def test_stacked_domains_run_like_the_single_domain(host, tmp_path):
+    """The merged run equals the run of the same terrain configured as one domain (same inflow cell), and every original
+    domain gets its own raster, cropped from the merged band."""
+    from oracle import raster_oracle as ro
+    bed = make_stacked(tmp_path)
+    (tmp_path / "boundaries" / "map_lower.csv").write_text("x,y\n1,10\n")
+    (tmp_path / "boundaries" / "map_upper.csv").write_text("x,y\n")
+    results = {}
+    for name in ("stacked", "single"):
+        h = host.hph_model_load(str(tmp_path / (name + ".xml")).encode(), 0)
+        assert h, [host.hph_error(i) for i in range(host.hph_error_count())]
+        assert host.hph_model_run(C.c_void_p(h)) == 0
+        results[name] = arrays(host, h, 70, 40)[0]
+        host.hph_model_destroy(C.c_void_p(h))
+    np.testing.assert_array_equal(results["stacked"], results["single"])
+    full, _ = read_tiff(str(tmp_path / "output" / "full_depth_20.tif"))
+    np.testing.assert_array_equal(full, ro.derive_raster(ro.DEPTH, results["single"], bed, 2.0))
+    lower, tl = read_tiff(str(tmp_path / "output" / "lower_depth_20.tif"))
+    upper, tu = read_tiff(str(tmp_path / "output" / "upper_depth_20.tif"))
+    np.testing.assert_array_equal(lower, full[30:])          # north-first: the lower domain is the last 40 rows
+    np.testing.assert_array_equal(upper, full[:40])
+    assert tl[33922][4] == 565146.0 + 40 * 2.0 and tu[33922][4] == 565146.0 + 70 * 2.0

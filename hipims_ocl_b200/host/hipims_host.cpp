@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cctype>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -865,10 +866,14 @@ void CScheme::setupFromConfig(const XMLElement* pXScheme) {            // CSchem
         }
         else if (key == "timestepinitial" || key == "timestepfixed") { if (isValidFloat(val.c_str())) setTimestep(atof(val.c_str())); else model::doError("Invalid initial/fixed timestep given.", model::errorCodes::kLevelWarning); }
         else if (key == "frictioneffects") { if (val == "yes") setFrictionStatus(true); else if (val == "no") setFrictionStatus(false); else model::doError("Invalid friction state given.", model::errorCodes::kLevelWarning); }
-        else if (key == "queuesize" || key == "queueinitialsize" || key == "queuefixedsize") { if (atoi(val.c_str()) > 0) setQueueSize(atoi(val.c_str())); }
+        else if (key == "queuesize" || key == "queueinitialsize" || key == "queuefixedsize") { if (atoi(val.c_str()) > 0) setQueueSize(atoi(val.c_str())); else model::doError("Invalid queue size given.", model::errorCodes::kLevelWarning); }
+        else if (key == "queuemode") {                                              // CScheme.cpp:79-95
+            if (val == "auto") setQueueMode(true); else if (val == "fixed") setQueueMode(false);
+            else model::doError("Invalid queue mode given.", model::errorCodes::kLevelWarning);
+        }
         else if (key == "riemannsolver") { if (val != "hllc") model::doError("Invalid Riemann solver given.", model::errorCodes::kLevelWarning); }
         else if (key == "groupsize" || key == "cachedgroupsize" || key == "noncachedgroupsize" || key == "localcachelevel" || key == "localcacheconstraints" ||
-                 key == "queuemode" || key == "timestepreductiondivisions" || key == "contiguousextrapolationdata") { /* launch geometry and cache strategy are the executor's business */ }
+                 key == "timestepreductiondivisions" || key == "contiguousextrapolationdata") { /* launch geometry and cache strategy are the executor's business */ }
         else model::doError("Unrecognised parameter: " + key, model::errorCodes::kLevelWarning);
     }
 }
@@ -887,7 +892,8 @@ bool CScheme::prepareAll(CExecutorControlCUDA* pExec, CDomainCartesian* pDom, un
     return true;
 }
 
-void CScheme::prepareSimulation() {        // CSchemeGodunov.cpp:1053-1071
+void CScheme::prepareSimulation() { prepareSimulationState(); }
+void CScheme::prepareSimulationState() {   // CSchemeGodunov.cpp:1053-1071
     if (!pScheme) return;
     const unsigned long n = pDomain->getCellCount();
     if (ucFloatPrecision == model::floatPrecision::kSingle) {
@@ -904,8 +910,19 @@ void CScheme::prepareSimulation() {        // CSchemeGodunov.cpp:1053-1071
     ulCurrentCellsCalculated = 0;
 }
 
-void CScheme::runSimulation(double dTarget, double) {      // CSchemeGodunov.cpp:1374-1453 + one Threaded_runBatch pass
+void CScheme::runSimulation(double dTarget, double dRealTime) {      // CSchemeGodunov.cpp:1374-1453 + one Threaded_runBatch pass
     if (!pScheme) return;
+    if (dCurrentTime > dTarget + 1E-5) { model::doError("Simulation has exceeded target time", model::errorCodes::kLevelWarning); return; }   // :1389-1405
+    // batch size: aim for a second of wall clock per batch (:1419-1450; single domain, so no rollback budget to respect)
+    if (bAutomaticQueue && dRealTime > 1E-5) {
+        const double dBatchDuration = dRealTime - dBatchStartedTime;
+        const unsigned int uiOld = uiQueueAdditionSize;
+        if (dBatchDuration > 0.0)
+            uiQueueAdditionSize = std::max(1u, std::min(uiBatchRate * 3, static_cast<unsigned int>(std::ceil(1.0 / (dBatchDuration / static_cast<double>(uiQueueAdditionSize))))));
+        if (uiQueueAdditionSize > uiOld * 2 && uiQueueAdditionSize > 40) uiQueueAdditionSize = std::min(uiBatchRate * 3, uiOld * 2);   // no silly jumps
+        if (uiQueueAdditionSize < 1) uiQueueAdditionSize = 1;
+    }
+    dBatchStartedTime = dRealTime;
     if (dTarget != dTargetTime) {
         dTargetTime = dTarget;
         HP_CHECK(hp_scheme_set_target_time(pScheme, dTarget), "target time");
@@ -920,6 +937,7 @@ void CScheme::runSimulation(double dTarget, double) {      // CSchemeGodunov.cpp
 void CScheme::readKeyStatistics() {
     hp_scheme_stats st{};
     if (hp_scheme_read_stats(pScheme, &st) < 0) { model::doError(hp_last_error(), model::errorCodes::kLevelModelStop); return; }
+    uiBatchRate = st.batch_successful > uiBatchSuccessful ? st.batch_successful - uiBatchSuccessful : 1;    // CSchemeGodunov.cpp:1834
     dCurrentTime = st.time; dCurrentTimestep = st.timestep; dBatchTimesteps = st.batch_timesteps;
     uiBatchSuccessful = st.batch_successful; uiBatchSkipped = st.batch_skipped;
 }
@@ -939,6 +957,30 @@ bool CScheme::deriveRaster(unsigned char ucValue, std::vector<double>& northFirs
     northFirst.resize(pDomain->getCellCount());
     if (hp_scheme_derive_raster(pScheme, ucValue, -9999.0, northFirst.data()) < 0) { model::doError(hp_last_error(), model::errorCodes::kLevelWarning); return false; }
     return true;
+}
+bool CScheme::isSimulationSyncReady(double dExpected) const { return !(dExpected - dCurrentTime > 1E-5); }       // CSchemeGodunov.cpp:1568-1612
+bool CScheme::isSimulationFailure(double dExpected) const {                                                      // :1523-1555
+    if (dCurrentTime > dExpected + 1E-5) { model::doError("Scheme has exceeded target sync time. Rolling back...", model::errorCodes::kLevelWarning); return true; }
+    return false;
+}
+void CScheme::rollbackSimulation(double dTime, double dTarget) {                                                 // :1474-1518
+    if (!pScheme) return;
+    prepareSimulationState();
+    dCurrentTime = dTime; dTargetTime = dTarget;
+    HP_CHECK(hp_scheme_set_clock(pScheme, dTime, dCurrentTimestep, 0.0), "rollback clock");
+    HP_CHECK(hp_scheme_set_target_time(pScheme, dTarget), "rollback target");
+    if (bDynamicTimestep) HP_CHECK(hp_scheme_update_timestep(pScheme), "rollback timestep");                     // tst_Reduce + tst_UpdateTimestep
+    HP_CHECK(hp_scheme_reset_counters(pScheme), "rollback counters");
+    HP_CHECK(hp_scheme_sync(pScheme), "rollback");
+    readKeyStatistics();
+}
+double CScheme::proposeSyncPoint(double dTime) const {                                                           // :1758-1790
+    const double dLimit = 999999999.0, dSpares = 3.0;                   // CDomain.cpp:45, CDomainManager default spare iterations
+    double dProposal = dTime + std::fabs(dTimestep);
+    if (dTime > 1E-5 && uiBatchSuccessful > 0)
+        dProposal = dTime + std::max(std::fabs(dTimestep), dLimit * (dBatchTimesteps / uiBatchSuccessful) * ((dLimit - dSpares) / dLimit));
+    else if (dProposal - dTime < 1E-5) dProposal = dTime + std::fabs(dTimestep);
+    return dProposal;
 }
 void CScheme::forceTimestep(double dt) { if (pScheme) HP_CHECK(hp_scheme_force_timestep(pScheme, dt), "force timestep"); }
 void CScheme::cleanupSimulation() { if (pScheme) { hp_scheme_destroy(pScheme); pScheme = nullptr; } }
@@ -1008,10 +1050,15 @@ bool CModel::loadConfiguration(const std::string& sPath, bool bDeviceless) {
 bool CModel::runModel() {
     if (!pScheme || !pScheme->isReady()) return false;
     pScheme->prepareSimulation();
+    const auto tStart = std::chrono::steady_clock::now();
     double nextOutput = dOutputFrequency > 0.0 ? dOutputFrequency : dSimulationTime;
     while (!model::forceAbort && pScheme->getCurrentTime() < dSimulationTime - 1E-5) {
         const double target = std::min(nextOutput, dSimulationTime);
-        while (!model::forceAbort && pScheme->getCurrentTime() < target - 1E-5) pScheme->runSimulation(target, 0.0);
+        while (!model::forceAbort && !pScheme->isSimulationSyncReady(target)) {
+            const double dRealTime = bRealTimeQueue ? std::chrono::duration<double>(std::chrono::steady_clock::now() - tStart).count() + 1E-4 : 0.0;
+            pScheme->runSimulation(target, dRealTime);
+            if (pScheme->isSimulationFailure(target)) { model::forceAbort = true; break; }     // cannot happen: the device clock stops at the target
+        }
         if (parts.empty()) {
             pDomain->writeOutputs(pScheme->getCurrentTime(), pScheme.get());  // derived on the device; no full-state read-back
         } else {                                                              // every original domain gets its own rasters
@@ -1048,6 +1095,14 @@ unsigned int hph_model_parts(void* h, unsigned long* row_offsets, unsigned int c
     for (unsigned int i = 0; i < m->getPartCount() && i < capacity; ++i) row_offsets[i] = m->getPartRowOffset(i);
     return m->getPartCount();
 }
+void hph_model_set_realtime_queue(void* h, int on) { static_cast<CModel*>(h)->setRealTimeQueue(on != 0); }
+// rollback: put the host arrays and clock back on the device, then report the recomputed timestep
+double hph_model_rollback(void* h, double time, double target) {
+    CScheme* s = static_cast<CModel*>(h)->getScheme();
+    s->rollbackSimulation(time, target);
+    return s->getCurrentTimestep();
+}
+double hph_model_propose_sync(void* h, double time) { return static_cast<CModel*>(h)->getScheme()->proposeSyncPoint(time); }
 void hph_model_scheme_params(void* h, double* courant, double* dry, double* timestep, int* dynamic, int* friction, unsigned int* queue) {
     CScheme* s = static_cast<CModel*>(h)->getScheme();
     *courant = s->dCourantNumber; *dry = s->dThresholdVerySmall; *timestep = s->dTimestep; *dynamic = s->bDynamicTimestep; *friction = s->bFrictionEffects;

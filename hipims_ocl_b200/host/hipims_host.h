@@ -228,11 +228,21 @@ class CScheme {
     virtual void setupFromConfig(const XMLElement* pXScheme);
     bool prepareAll(CExecutorControlCUDA* pExec, CDomainCartesian* pDomain, unsigned char ucFloatPrecision, double dSimulationLength);
     void prepareSimulation();                          // uploads cells and clock
+    void prepareSimulationState();
     void runSimulation(double dTargetTime, double dRealTime);   // sets the target and schedules a batch
     void readKeyStatistics();
     void readDomainAll();                              // device -> CDomain host arrays
     void saveCurrentState() { readDomainAll(); }
     bool deriveRaster(unsigned char ucValue, std::vector<double>& northFirst);   // hp_scheme_derive_raster
+    // synchronisation surface of CScheme (src/Schemes/CScheme.h:85-129, CSchemeGodunov.cpp:1474-1616, 1741-1816).  With one
+    // merged domain per device there are no link zones, so the rollback limit never binds; the calls keep their meaning.
+    bool isSimulationSyncReady(double dExpectedTargetTime) const;       // the target has been reached (to 1e-5 s)
+    bool isSimulationFailure(double dExpectedTargetTime) const;         // the scheme has run past the target
+    void rollbackSimulation(double dCurrentTime, double dTargetTime);   // host cell arrays + clock back onto the device
+    double proposeSyncPoint(double dCurrentTime) const;
+    void forceTimeAdvance() {}                                          // the device clock always advances (no suspended state to leave)
+    void setQueueMode(bool bAuto) { bAutomaticQueue = bAuto; }
+    bool getQueueMode() const { return bAutomaticQueue; }
     void forceTimestep(double dTimestep);
     void cleanupSimulation();
     bool isReady() const { return pScheme != nullptr; }
@@ -264,6 +274,9 @@ class CScheme {
     CDomainCartesian* pDomain = nullptr;
     CExecutorControlCUDA* pExecutor = nullptr;
     unsigned int uiQueueAdditionSize = 256;
+    bool bAutomaticQueue = true;                       // CScheme.cpp:46
+    unsigned int uiBatchRate = 1;                      // successful iterations of the last batch (CSchemeGodunov.cpp:1834)
+    double dBatchStartedTime = 0.0;
     uint32_t uiQuirks = HP_QUIRK_REDUCE_BUFFER_A | HP_QUIRK_BDY_COVERAGE, uiOptions = 0;
     double dCurrentTime = 0, dCurrentTimestep = 0, dBatchTimesteps = 0, dTargetTime = 0;
     unsigned int uiBatchSuccessful = 0, uiBatchSkipped = 0;
@@ -283,6 +296,9 @@ class CModel {
     // src/main.cpp:376 + src/Datasets/CXMLDataset.cpp:115-260; bDeviceless parses only (no executor, CPU tests)
     bool loadConfiguration(const std::string& sPath, bool bDeviceless = false);
     bool runModel();
+    // pass wall-clock time to CScheme::runSimulation so that queueMode="auto" sizes batches for about a second of work
+    // (src/CModel.cpp:1041-1139); off by default so that iteration counts are reproducible
+    void setRealTimeQueue(bool b) { bRealTimeQueue = b; }
     double getSimulationLength() const { return dSimulationTime; }
     double getOutputFrequency() const { return dOutputFrequency; }
     unsigned char getFloatPrecision() const { return ucFloatPrecision; }
@@ -290,6 +306,7 @@ class CModel {
     CScheme* getScheme() { return pScheme.get(); }
     std::string sName, sDescription;
   private:
+    bool bRealTimeQueue = false;
     double dSimulationTime = 0, dOutputFrequency = 0;
     unsigned char ucFloatPrecision = model::floatPrecision::kDouble;
     std::unique_ptr<CExecutorControlCUDA> pExecutor;

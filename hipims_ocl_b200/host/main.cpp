@@ -14,6 +14,7 @@ int main(int argc, char** argv) {
     if (config.empty()) { fprintf(stderr, "usage: %s -c <configuration.xml>\n", argv[0]); return 2; }
     CModel m;
     if (!m.loadConfiguration(config)) return 1;
+    m.setRealTimeQueue(true);                        // queueMode="auto": batches of about a second, like the reference
     printf("%s: %lu x %lu cells, %s, duration %.1f s\n", m.sName.c_str(), m.getDomain()->getCols(), m.getDomain()->getRows(),
            m.getFloatPrecision() == model::floatPrecision::kSingle ? "single" : "double", m.getSimulationLength());
     const double v0 = m.getDomain()->getVolume();

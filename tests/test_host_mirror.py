@@ -486,3 +486,34 @@ def test_stacked_domains_run_like_the_single_domain(host, tmp_path):
     np.testing.assert_array_equal(lower, full[30:])          # north-first: the lower domain is the last 40 rows
     np.testing.assert_array_equal(upper, full[:40])
     assert tl[33922][4] == 565146.0 + 40 * 2.0 and tu[33922][4] == 565146.0 + 70 * 2.0
+
+
+@pytest.mark.gpu
+def test_automatic_queue_and_rollback(host, model_dir):
+    """queueMode="auto" with wall-clock batch sizing (CSchemeGodunov.cpp:1419-1450) changes how many iterations are
+    skipped at the targets, never the result; rollbackSimulation puts the host state and clock back on the device."""
+    host.hph_model_set_realtime_queue.argtypes = [C.c_void_p, C.c_int]
+    host.hph_model_rollback.restype = C.c_double
+    host.hph_model_rollback.argtypes = [C.c_void_p, C.c_double, C.c_double]
+    host.hph_model_propose_sync.restype = C.c_double
+    host.hph_model_propose_sync.argtypes = [C.c_void_p, C.c_double]
+    cfg, _ = model_dir(scheme="Godunov", duration=30, outfreq=10)
+    runs = []
+    for realtime in (0, 1):
+        h = host.hph_model_load(cfg.encode(), 0)
+        assert h
+        host.hph_model_set_realtime_queue(C.c_void_p(h), realtime)
+        assert host.hph_model_run(C.c_void_p(h)) == 0
+        t, dt, ok, skipped = C.c_double(), C.c_double(), C.c_uint(), C.c_uint()
+        host.hph_model_clock(C.c_void_p(h), C.byref(t), C.byref(dt), C.byref(ok), C.byref(skipped))
+        runs.append((arrays(host, h, 30, 40)[0], t.value, ok.value))
+        if realtime:
+            # propose a sync point from the batch statistics, then roll back to t = 12 s with a target of 50 s
+            assert host.hph_model_propose_sync(C.c_void_p(h), t.value) > t.value
+            new_dt = host.hph_model_rollback(C.c_void_p(h), 12.0, 50.0)
+            assert new_dt > 0.0
+            host.hph_model_clock(C.c_void_p(h), C.byref(t), C.byref(dt), C.byref(ok), C.byref(skipped))
+            assert t.value == 12.0 and (ok.value, skipped.value) == (0, 0) and dt.value == new_dt
+        host.hph_model_destroy(C.c_void_p(h))
+    np.testing.assert_array_equal(runs[0][0], runs[1][0])
+    assert runs[0][1] == runs[1][1] == 30.0 and runs[0][2] == runs[1][2]

@@ -25,7 +25,11 @@ import sys
 import threading
 import time
 
-import numpy as np
+# The CPU legs (cpu_baseline, --impl reference) use every host thread through OpenMP.  torchrun exports OMP_NUM_THREADS=1
+# to its workers, and libgomp reads the variable when it is first loaded: set it before anything can load it.
+os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+
+import numpy as np  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -225,8 +229,10 @@ def cpu_backend(cfg):
     return "oracle", "port"
 
 
-def cpu_rate(w, n, steps, warmup, threads=0):
-    """cell-updates/s of the CPU implementation on an n x n crop of the workload."""
+def cpu_rate(w, n, steps, warmup, threads=None):
+    """cell-updates/s of the CPU implementation on an n x n crop of the workload, on all host threads (set explicitly:
+    torchrun exports OMP_NUM_THREADS=1 to its workers)."""
+    threads = threads or (os.cpu_count() or 1)
     from oracle import cpu_sim
     cfg = cfg_for(w, n, n)
     backend, kind = cpu_backend(cfg)

@@ -386,14 +386,23 @@ godunov_step_tma(const StepArgs a, const __grid_constant__ TmaMaps maps) {
     block_reduce_finalize<R>(ws, a, k);
 }
 
+// kernels with more than 48 KB of dynamic shared memory need the opt-in on every device they run on
+constexpr int kMaxDevices = 64;
+static int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev >= 0 && dev < kMaxDevices ? dev : 0;
+}
+
 template <class R> static int launch_godunov_tma(const StepArgs& a_in, const TmaMaps& maps, int sm_count, cudaStream_t st) {
     using T = Tile<R>;
     StepArgs a = a_in;
     if (a.y1 <= a.y0) return 0;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[kMaxDevices] = {};          // the attribute is per device
+    const int dev = current_device();
+    if (!configured[dev]) {
         cudaFuncSetAttribute(godunov_step_tma<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES);
-        configured = true;
+        configured[dev] = true;
     }
     const int tiles = ((a.grid.cols + T::TX - 1) / T::TX) * ((a.y1 - a.y0 + T::TY - 1) / T::TY);
     int grid = T::CTAS_PER_SM * sm_count;          // all resident CTAs of every SM, persistent
@@ -719,10 +728,11 @@ template <class R> static int launch_mh_tma(const StepArgs& a_in, const TmaMaps&
     using T = TileMH<R>;
     StepArgs a = a_in;
     if (a.y1 <= a.y0) return 0;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[kMaxDevices] = {};          // the attribute is per device
+    const int dev = current_device();
+    if (!configured[dev]) {
         cudaFuncSetAttribute(mh_step_tma<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES);
-        configured = true;
+        configured[dev] = true;
     }
     const int tiles = ((a.grid.cols + T::TX - 1) / T::TX) * ((a.y1 - a.y0 + T::TY - 1) / T::TY);
     int grid = T::CTAS_PER_SM * sm_count;

@@ -5,8 +5,8 @@
 // (profiles/r01_*): per cell-update only ~36 % of their instructions are fp64 arithmetic, the rest
 // is index arithmetic, shared-memory traffic for predictor / flux planes and CTA barriers between
 // the phases.  Here
-//   * raw rows arrive through TMA (cp.async.bulk.tensor.3d + mbarrier, ONE box = one row of six planes) into a per-warp ring of
-//     four rows x six planes, one row ahead of the arithmetic; every plane is read from HBM once;
+//   * raw rows arrive through TMA (cp.async.bulk.tensor.3d + mbarrier; ONE box = one row of the six
+//     planes a step reads) into a per-warp ring of four rows, two rows ahead of the arithmetic;
 //   * the y-direction never leaves the thread: the predictor of the row below, the flux through the
 //     southern face and its owner terms are carried in registers from the previous row;
 //   * the x-direction is exchanged between neighbouring lanes with warp shuffles: the east-side
@@ -17,9 +17,10 @@
 //   * work is split into equal runs of (strip group, row) units over a persistent grid that
 //     exactly fills the SMs; each CTA takes several runs spread round-robin over the domain, so all
 //     CTAs finish together (no tail wave) even where wet and dry regions cost differently.
-// The lane at either strip edge only feeds its neighbour (halo lanes): 30 of 32 lanes update cells in fp64,
-// 28 in fp32 (the TMA box must start on a 16-byte boundary).  MUSCL-Hancock needs raw values two columns out;
-// those come straight from the box, which is wider than the warp.
+//   * rows that cannot change (exactly dry stencils) are recognised by one warp vote and skipped.
+// The lane at either strip edge only feeds its neighbour (halo lanes): 30 of 32 lanes update cells
+// in fp64, 28 in fp32 (the TMA box must start on a 16-byte boundary).  MUSCL-Hancock needs raw
+// values two columns out; those come straight from the box, which is wider than the warp.
 // The per-cell arithmetic is the one of the tile kernels (same helper functions), so results are
 // identical to them to the last bit where the operation order is the same.
 #pragma once
@@ -818,11 +819,12 @@ template <class R> static int launch_mh_march(const StepArgs& a_in, const TmaBlo
     using T = March<R, 1, false, HP_MARCH_MH_RR>;
     StepArgs a = a_in;
     if (a.y1 <= a.y0) return 0;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[kMaxDevices] = {};          // the attribute is per device
+    const int dev = current_device();
+    if (!configured[dev]) {
         cudaFuncSetAttribute(mh_step_march<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES);
         cudaFuncSetAttribute(mh_step_march<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES);
-        configured = true;
+        configured[dev] = true;
     }
     const int grid = march_grid(a, T::USE, T::NW, sizeof(R) == 8 ? 4 : 6, sm_count);
     a.total_ctas = grid; a.march_runs = march_runs(a, T::USE, T::NW, grid);
@@ -835,11 +837,12 @@ template <class R> static int launch_godunov_march(const StepArgs& a_in, const T
     using T = March<R, 1, false>;
     StepArgs a = a_in;
     if (a.y1 <= a.y0) return 0;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[kMaxDevices] = {};          // the attribute is per device
+    const int dev = current_device();
+    if (!configured[dev]) {
         cudaFuncSetAttribute(godunov_step_march<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES);
         cudaFuncSetAttribute(godunov_step_march<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES);
-        configured = true;
+        configured[dev] = true;
     }
     const int grid = march_grid(a, T::USE, T::NW, sizeof(R) == 8 ? HP_MARCH_GOD_CTAS64 : HP_MARCH_GOD_CTAS32, sm_count);
     a.total_ctas = grid; a.march_runs = march_runs(a, T::USE, T::NW, grid);
@@ -852,11 +855,12 @@ template <class R> static int launch_inertial_march(const StepArgs& a_in, const 
     using T = March<R, 1, false>;
     StepArgs a = a_in;
     if (a.y1 <= a.y0) return 0;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[kMaxDevices] = {};          // the attribute is per device
+    const int dev = current_device();
+    if (!configured[dev]) {
         cudaFuncSetAttribute(inertial_step_march<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES);
         cudaFuncSetAttribute(inertial_step_march<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES);
-        configured = true;
+        configured[dev] = true;
     }
     const int grid = march_grid(a, T::USE, T::NW, sizeof(R) == 8 ? HP_MARCH_INE_CTAS64 : 8, sm_count);
     a.total_ctas = grid; a.march_runs = march_runs(a, T::USE, T::NW, grid);

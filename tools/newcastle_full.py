@@ -3,7 +3,7 @@
 then dry, losses 12 mm/h, Godunov fp64, 7200 s) on the CUDA executor against the CPU oracle, compared on the rasters the
 reference writes (depth, maxdepth).  The DEM comes from tests/golden/newcastle_centre.npz.
 
-    python tools/newcastle_full.py [end_time_s] [queue]
+    python tools/newcastle_full.py [end_time_s] [queue] [HP_OPT_* mask, 1 = strict flavour]
 """
 import os
 import sys
@@ -18,9 +18,10 @@ from tests.test_golden import newcastle_sim                # noqa: E402
 
 end = float(sys.argv[1]) if len(sys.argv) > 1 else 7200.0
 queue = int(sys.argv[2]) if len(sys.argv) > 2 else 512
+options = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 ex = hx.Executor(0)
 runs = {}
-for name, make in (("cuda", lambda cfg: hx.CudaScheme(ex, cfg.with_(end_time=end))), ("oracle", lambda cfg: cpu_sim.CpuSim("oracle", cfg.with_(end_time=end), threads=os.cpu_count()))):
+for name, make in (("cuda", lambda cfg: hx.CudaScheme(ex, cfg.with_(end_time=end), options=options)), ("oracle", lambda cfg: cpu_sim.CpuSim("oracle", cfg.with_(end_time=end), threads=os.cpu_count()))):
     z, bed, sim = newcastle_sim(make)
     sim.set_target(end)
     t0 = time.perf_counter()

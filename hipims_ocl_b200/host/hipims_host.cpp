@@ -798,6 +798,105 @@ bool writeGeoTIFF(const std::string& path, unsigned long cols, unsigned long row
     return fclose(f) == 0 && ok;
 }
 
+
+// ERDAS IMAGINE (.img / HFA) writer: one Float64 layer in uncompressed 64 x 64 blocks, no-data value, map info.
+// The node tree and the binary layout of every node follow what GDAL's HFA driver writes (the reference's own test
+// DEM is such a file: root -> IMGFormatInfo, Layer_1 -> RasterDMS, Ehfa_Layer, Eimg_NonInitializedValue, Map_Info); the
+// MIF dictionary carries the definitions of exactly those object types.  HFA offsets are 32 bit: rasters of 2 GB and
+// more are refused (GDAL spills them into a separate .ige file) and the caller falls back to GeoTIFF.
+bool writeHFA(const std::string& path, unsigned long cols, unsigned long rows, double ulx, double uly, double res, const double* data) {
+    const uint32_t B = 64;
+    const uint64_t nbx = (cols + B - 1) / B, nby = (rows + B - 1) / B, nblocks = nbx * nby, block_bytes = uint64_t(B) * B * 8;
+    if (nblocks * block_bytes >= 0x7ff00000ull) return false;
+    static const char* kDictionary =
+        "{1:lversion,1:LfreeList,1:LrootEntryPtr,1:sentryHeaderLength,1:LdictionaryPtr,}Ehfa_File,"
+        "{1:Lnext,1:Lprev,1:Lparent,1:Lchild,1:Ldata,1:ldataSize,64:cname,32:ctype,1:tmodTime,}Ehfa_Entry,"
+        "{16:clabel,1:LheaderPtr,}Ehfa_HeaderTag,"
+        "{1:lwidth,1:lheight,1:e3:thematic,athematic,fft of real-valued data,layerType,"
+        "1:e13:u1,u2,u4,u8,s8,u16,s16,u32,s32,f32,f64,c64,c128,pixelType,1:lblockWidth,1:lblockHeight,}Eimg_Layer,"
+        "{1:e2:raster,vector,type,1:LdictionaryPtr,}Ehfa_Layer,"
+        "{1:LspaceUsedForRasterData,}ImgFormatInfo831,"
+        "{1:sfileCode,1:Loffset,1:lsize,1:e2:false,true,logvalid,1:e2:no compression,ESRI GRID compression,compressionType,}Edms_VirtualBlockInfo,"
+        "{1:lmin,1:lmax,}Edms_FreeIDList,"
+        "{1:lnumvirtualblocks,1:lnumobjectsperblock,1:lnextobjectnum,1:e2:no compression,RLC compression,compressionType,"
+        "0:poEdms_VirtualBlockInfo,blockinfo,0:poEdms_FreeIDList,freelist,1:tmodTime,}Edms_State,"
+        "{1:*bvalueBD,}Eimg_NonInitializedValue,"
+        "{1:dx,1:dy,}Eprj_Coordinate,{1:dwidth,1:dheight,}Eprj_Size,"
+        "{0:pcproName,1:*oEprj_Coordinate,upperLeftCenter,1:*oEprj_Coordinate,lowerRightCenter,1:*oEprj_Size,pixelSize,0:pcunits,}Eprj_MapInfo,.";
+    std::vector<unsigned char> f;
+    auto at = [&]() { return static_cast<uint32_t>(f.size()); };
+    auto patch32 = [&](size_t o, uint32_t v) { memcpy(&f[o], &v, 4); };
+    const char tag[16] = "EHFA_HEADER_TAG";
+    f.insert(f.end(), tag, tag + 16);
+    put<uint32_t>(f, 20);                                               // Ehfa_HeaderTag.headerPtr
+    put<int32_t>(f, 1); put<uint32_t>(f, 0); const size_t rootPtrAt = f.size(); put<uint32_t>(f, 0); put<int16_t>(f, 128); put<uint32_t>(f, 38);   // Ehfa_File
+    f.insert(f.end(), kDictionary, kDictionary + strlen(kDictionary) + 1);
+    // entries: 128 bytes {next, prev, parent, child, data, dataSize, name[64], type[32], modTime, pad}
+    struct Node { uint32_t at, next, prev, parent, child, data; int32_t size; };
+    auto entry = [&](const char* name, const char* type) {
+        Node n{at(), 0, 0, 0, 0, 0, 0};
+        f.resize(f.size() + 128, 0);
+        strncpy(reinterpret_cast<char*>(&f[n.at + 24]), name, 63);
+        strncpy(reinterpret_cast<char*>(&f[n.at + 88]), type, 31);
+        return n;
+    };
+    auto commit = [&](const Node& n) { const uint32_t v[5] = {n.next, n.prev, n.parent, n.child, n.data}; memcpy(&f[n.at], v, 20); memcpy(&f[n.at + 20], &n.size, 4); };
+    Node root = entry("root", "root");
+    patch32(rootPtrAt, root.at);
+    Node info = entry("IMGFormatInfo", "ImgFormatInfo831");
+    info.parent = root.at; info.data = at(); info.size = 4;
+    put<uint32_t>(f, static_cast<uint32_t>(nblocks * block_bytes));
+    Node layer = entry("Layer_1", "Eimg_Layer");
+    layer.parent = root.at; layer.prev = info.at; info.next = layer.at; root.child = info.at;
+    layer.data = at(); layer.size = 20;
+    put<int32_t>(f, static_cast<int32_t>(cols)); put<int32_t>(f, static_cast<int32_t>(rows)); put<uint16_t>(f, 1 /* athematic */);
+    put<uint16_t>(f, 10 /* f64 */); put<int32_t>(f, B); put<int32_t>(f, B);
+    Node dms = entry("RasterDMS", "Edms_State");
+    dms.parent = layer.at; layer.child = dms.at; dms.data = at(); dms.size = static_cast<int32_t>(14 + 8 + 14 * nblocks + 16);
+    put<int32_t>(f, static_cast<int32_t>(nblocks)); put<int32_t>(f, B * B); put<int32_t>(f, static_cast<int32_t>(nblocks * B * B)); put<uint16_t>(f, 0);
+    put<uint32_t>(f, static_cast<uint32_t>(nblocks)); put<uint32_t>(f, at() + 4);       // blockinfo: count, pointer to the array that follows
+    const size_t tableAt = f.size();
+    f.resize(f.size() + 14 * nblocks, 0);
+    f.resize(f.size() + 16, 0);                                          // freelist {0, 0}, modTime, pad
+    Node ehl = entry("Ehfa_Layer", "Ehfa_Layer");
+    ehl.parent = layer.at; ehl.prev = dms.at; dms.next = ehl.at; ehl.data = at(); ehl.size = 6;
+    put<uint16_t>(f, 0 /* raster */); put<uint32_t>(f, at() + 4);
+    const char* layerDict = "{4096:ddata,}RasterDMS,.";
+    f.insert(f.end(), layerDict, layerDict + strlen(layerDict) + 1);
+    Node nd = entry("Eimg_NonInitializedValue", "Eimg_NonInitializedValue");
+    nd.parent = layer.at; nd.prev = ehl.at; ehl.next = nd.at; nd.data = at(); nd.size = 28;
+    put<uint32_t>(f, 1); put<uint32_t>(f, at() + 4); put<int32_t>(f, 1); put<int32_t>(f, 1); put<uint16_t>(f, 10); put<uint16_t>(f, 0); put<double>(f, -9999.0);
+    Node map = entry("Map_Info", "Eprj_MapInfo");
+    map.parent = layer.at; map.prev = nd.at; nd.next = map.at; map.data = at();
+    const char* pro = "Unknown"; const char* units = "meters";
+    put<uint32_t>(f, static_cast<uint32_t>(strlen(pro) + 1)); put<uint32_t>(f, at() + 4); f.insert(f.end(), pro, pro + strlen(pro) + 1);
+    put<uint32_t>(f, 1); put<uint32_t>(f, at() + 4); put<double>(f, ulx + 0.5 * res); put<double>(f, uly - 0.5 * res);                               // upperLeftCenter
+    put<uint32_t>(f, 1); put<uint32_t>(f, at() + 4); put<double>(f, ulx + res * cols - 0.5 * res); put<double>(f, uly - res * rows + 0.5 * res);     // lowerRightCenter
+    put<uint32_t>(f, 1); put<uint32_t>(f, at() + 4); put<double>(f, res); put<double>(f, res);                                                       // pixelSize
+    put<uint32_t>(f, static_cast<uint32_t>(strlen(units) + 1)); put<uint32_t>(f, at() + 4); f.insert(f.end(), units, units + strlen(units) + 1);
+    map.size = static_cast<int32_t>(at() - map.data);
+    for (const Node& n : {root, info, layer, dms, ehl, nd, map}) commit(n);
+    // block table, then the blocks themselves (north-west block first, rows of a block north first, edge blocks padded)
+    const uint32_t first = at();
+    for (uint64_t b = 0; b < nblocks; ++b) {
+        unsigned char* rec = &f[tableAt + 14 * b];
+        const uint16_t zero = 0, one = 1; const uint32_t off = static_cast<uint32_t>(first + b * block_bytes); const int32_t size = static_cast<int32_t>(block_bytes);
+        memcpy(rec, &zero, 2); memcpy(rec + 2, &off, 4); memcpy(rec + 6, &size, 4); memcpy(rec + 10, &one, 2); memcpy(rec + 12, &zero, 2);
+    }
+    FILE* out = fopen(path.c_str(), "wb");
+    if (!out) return false;
+    bool ok = fwrite(f.data(), 1, f.size(), out) == f.size();
+    std::vector<double> blk(B * B);
+    for (uint64_t by = 0; by < nby && ok; ++by) for (uint64_t bx = 0; bx < nbx && ok; ++bx) {
+        for (uint32_t y = 0; y < B; ++y) for (uint32_t x = 0; x < B; ++x) {
+            const uint64_t gy = by * B + y, gx = bx * B + x;
+            blk[y * B + x] = (gy < rows && gx < cols) ? data[gy * cols + gx] : -9999.0;
+        }
+        ok = fwrite(blk.data(), sizeof(double), blk.size(), out) == blk.size();
+    }
+    return fclose(out) == 0 && ok;
+}
+
 bool writeENVI(const std::string& path, unsigned long cols, unsigned long rows, double ulx, double uly, double res, const double* data) {
     FILE* f = fopen(path.c_str(), "wb");
     if (!f) return false;
@@ -827,6 +926,8 @@ bool CRasterDataset::writeRaster(const std::string& sFormat, const std::string& 
         ok = r.write(file);
     } else if (sFormat == "ENVI") {
         ok = writeENVI(file, cols, rows, ulx, uly, res, northFirst);
+    } else if (sFormat == "HFA" && writeHFA(file, cols, rows, ulx, uly, res, northFirst)) {
+        ok = true;
     } else {
         if (sFormat != "GTiff") {
             model::doError("GDAL format driver '" + sFormat + "' is not available in this build: writing GeoTIFF instead.", model::errorCodes::kLevelWarning);

@@ -83,9 +83,10 @@ struct SRaster {
 
 // GDAL-free stand-in for the writing half of CRasterDataset (src/Datasets/CRasterDataset.cpp:101-287): one
 // Float64 band, no-data -9999, geotransform {xll, res, 0, yll + res * rows, 0, -res} (:163-170).  `format` keeps
-// GDAL's driver codes: "GTiff" (uncompressed GeoTIFF, BigTIFF above 4 GB), "ENVI" (raw little-endian + .hdr),
-// "AAIGrid" (ESRI ASCII).  Other codes (e.g. "HFA") are reported through doError(kLevelWarning) like a driver
-// that cannot create files (:129-146) and written as GeoTIFF next to the requested name.
+// GDAL's driver codes: "GTiff" (uncompressed GeoTIFF, BigTIFF above 4 GB), "HFA" (ERDAS IMAGINE .img as GDAL lays it
+// out, below 2 GB), "ENVI" (raw little-endian + .hdr), "AAIGrid" (ESRI ASCII).  Other codes are reported through
+// doError(kLevelWarning) like a driver that cannot create files (:129-146) and written as GeoTIFF next to the
+// requested name.
 class CRasterDataset {
   public:
     // `northFirst`: rows x cols values, row 0 = northern edge (raster order)

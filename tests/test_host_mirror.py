@@ -220,6 +220,67 @@ def test_rounding_is_the_reference_function(host):
             assert host.hph_round(float(v), places) == ref.ref_round(float(v), places)
 
 
+def hfa_nodes(path):
+    """Walks the node tree of an ERDAS IMAGINE file: {name: (type, data bytes)} plus the MIF dictionary."""
+    import struct
+    d = open(path, "rb").read()
+    assert d[:16] == b"EHFA_HEADER_TAG\0"
+    hdr = struct.unpack_from("<I", d, 16)[0]
+    version, free, root, ehl, dictp = struct.unpack_from("<iIIhI", d, hdr)
+    assert (version, ehl) == (1, 128)
+    nodes = {}
+
+    def walk(o, parent):
+        prev = 0
+        while o:
+            nxt, prv, par, child, data, size = struct.unpack_from("<IIIIIi", d, o)
+            name = d[o + 24:o + 88].split(b"\0")[0].decode()
+            typ = d[o + 88:o + 120].split(b"\0")[0].decode()
+            assert par == parent and prv == prev and data + size <= len(d)
+            nodes[name] = (typ, d[data:data + size], data)
+            if child:
+                walk(child, o)
+            prev, o = o, nxt
+    walk(root, 0)
+    return nodes, d[dictp:d.index(b"\0", dictp)].decode(), d
+
+
+def check_hfa_structure(path, cols, rows):
+    """The written file against the layout GDAL's HFA driver produces (the reference's test DEM is such a file: compared
+    node by node where /root/reference is present)."""
+    import struct
+    nodes, dictionary, raw = hfa_nodes(path)
+    assert {"root", "IMGFormatInfo", "Layer_1", "RasterDMS", "Ehfa_Layer", "Eimg_NonInitializedValue", "Map_Info"} <= set(nodes)
+    for name, (typ, _, _) in nodes.items():
+        assert typ == "root" or ("}" + typ + ",") in dictionary            # every object type is defined in the MIF dictionary
+    assert dictionary.endswith(",.")
+    assert struct.unpack("<iiHHii", nodes["Layer_1"][1]) == (cols, rows, 1, 10, 64, 64)
+    nblocks = -(-cols // 64) * -(-rows // 64)
+    dms, dms_at = nodes["RasterDMS"][1], nodes["RasterDMS"][2]
+    assert struct.unpack_from("<iiiH", dms) == (nblocks, 4096, nblocks * 4096, 0)
+    count, ptr = struct.unpack_from("<II", dms, 14)
+    assert count == nblocks and ptr == dms_at + 22 and len(dms) == 22 + 14 * nblocks + 16
+    for b in range(nblocks):
+        code, off, size, valid, comp = struct.unpack_from("<HIiHH", dms, 22 + 14 * b)
+        assert (code, size, valid, comp) == (0, 32768, 1, 0) and off + size <= len(raw)
+    typ, ldict_ptr = struct.unpack("<HI", nodes["Ehfa_Layer"][1])
+    assert typ == 0 and raw[ldict_ptr:raw.index(b"\0", ldict_ptr)] == b"{4096:ddata,}RasterDMS,."
+    n, p, r, c, t, o = struct.unpack_from("<IIiiHH", nodes["Eimg_NonInitializedValue"][1])
+    assert (n, p, r, c, t, o) == (1, nodes["Eimg_NonInitializedValue"][2] + 8, 1, 1, 10, 0)
+    assert struct.unpack_from("<d", nodes["Eimg_NonInitializedValue"][1], 20)[0] == -9999.0
+    sample = "/root/reference/test/newcastle-centre/topography/NewcastleCentreDEM_2m.img"
+    if os.path.exists(sample):
+        ref_nodes, ref_dict, _ = hfa_nodes(sample)
+        for name in ("IMGFormatInfo", "Layer_1", "RasterDMS", "Ehfa_Layer", "Eimg_NonInitializedValue", "Map_Info"):
+            assert nodes[name][0] == ref_nodes[name][0]                      # same object types as the GDAL-written file
+            typ = nodes[name][0]
+            i = ref_dict.find("}" + typ + ",")
+            definition = ref_dict[ref_dict.rfind("{", 0, i):i + len(typ) + 2]
+            assert definition in dictionary                                  # and the same MIF definition of each
+        assert len(nodes["Layer_1"][1]) == len(ref_nodes["Layer_1"][1]) and len(nodes["Ehfa_Layer"][1]) == len(ref_nodes["Ehfa_Layer"][1])
+        assert len(nodes["Eimg_NonInitializedValue"][1]) == len(ref_nodes["Eimg_NonInitializedValue"][1])
+
+
 def test_raster_writers_round_trip(host, tmp_path):
     """GeoTIFF / ENVI / ESRI ASCII written by the GDAL-free CRasterDataset stand-in: values bit-exact, georeferencing
     as src/Datasets/CRasterDataset.cpp:163-176 sets it (top-left origin, negative y resolution, no-data -9999)."""
@@ -231,16 +292,27 @@ def test_raster_writers_round_trip(host, tmp_path):
     a[rng.random((rows, cols)) < 0.3] = -9999.0
     ptr = a.ctypes.data_as(C.POINTER(C.c_double))
     written = C.create_string_buffer(512)
-    for fmt, name in (("GTiff", "a.tif"), ("ENVI", "b.bil"), ("AAIGrid", "c.asc"), ("HFA", "d.img")):
+    host.hph_raster_read.restype = C.POINTER(C.c_double)
+    host.hph_raster_read.argtypes = [C.c_char_p, C.POINTER(C.c_ulong), C.POINTER(C.c_ulong), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                     C.POINTER(C.c_double)]
+    for fmt, name in (("GTiff", "a.tif"), ("ENVI", "b.bil"), ("AAIGrid", "c.asc"), ("HFA", "d.img"), ("PCIDSK", "e.pix")):
         before = host.hph_error_count()
         assert host.hph_write_raster(fmt.encode(), str(tmp_path / name).encode(), cols, rows, xll, yll, res, ptr, written, 512) == 0
         path = written.value.decode()
-        if fmt == "HFA":                                     # no such driver here: warned, GeoTIFF written instead
-            assert path.endswith("d.tif") and host.hph_error_count() == before + 1
+        if fmt == "PCIDSK":                                  # no such driver here: warned, GeoTIFF written instead
+            assert path.endswith("e.tif") and host.hph_error_count() == before + 1
             assert b"not available" in host.hph_error(before)
         else:
             assert path.endswith(name) and host.hph_error_count() == before
-        if path.endswith(".tif"):
+        if path.endswith(".img"):
+            # ERDAS IMAGINE: back through the reader that reads the reference's (GDAL-written) DEM
+            c, r = C.c_ulong(), C.c_ulong()
+            cs, x0, y0 = C.c_double(), C.c_double(), C.c_double()
+            vals = host.hph_raster_read(path.encode(), C.byref(c), C.byref(r), C.byref(cs), C.byref(x0), C.byref(y0))
+            assert vals and (c.value, r.value, cs.value, x0.value, y0.value) == (cols, rows, res, xll, yll)
+            got = np.ctypeslib.as_array(vals, shape=(rows, cols))[::-1].copy()      # the reader returns south-first rows
+            check_hfa_structure(path, cols, rows)
+        elif path.endswith(".tif"):
             got, tags = read_tiff(path)
             assert tags[33550] == [res, res, 0.0] and tags[33922] == [0.0, 0.0, 0.0, xll, yll + res * rows, 0.0]
             assert tags[42113] == "-9999" and tags[34735][:4] == [1, 1, 0, 1]
@@ -364,10 +436,10 @@ def test_model_run_matches_oracle_driven_the_same_way(host, model_dir, scheme, n
     assert np.abs(st1[..., 2:] - want[..., 2:]).max() <= 1e-7
     # rasters: derived exactly as CRasterDataset::domainToRaster does, written north-first, every 10 s
     out = os.path.join(os.path.dirname(cfg), "output")
-    # (derived on the device by hp_scheme_derive_raster; maxdepth asks for the HFA driver and falls back to GeoTIFF)
+    # (derived on the device by hp_scheme_derive_raster; maxdepth is written as ERDAS IMAGINE like the reference's test config)
     from oracle import raster_oracle as ro
     out = os.path.join(os.path.dirname(cfg), "output")
-    names = ["depth_%d.tif", "velX_%d.bil", "velX_%d.hdr", "fsl_%d.asc", "maxdepth_%d.tif"]
+    names = ["depth_%d.tif", "velX_%d.bil", "velX_%d.hdr", "fsl_%d.asc", "maxdepth_%d.img"]
     assert sorted(os.listdir(out)) == sorted(n % k for n in names for k in (10, 20, 30))
     depth, tags = read_tiff(os.path.join(out, "depth_30.tif"))
     np.testing.assert_array_equal(depth, ro.derive_raster(ro.DEPTH, st1, bed, 2.0))
@@ -377,8 +449,14 @@ def test_model_run_matches_oracle_driven_the_same_way(host, model_dir, scheme, n
     fsl, hdr = read_asc(os.path.join(out, "fsl_30.asc"))
     np.testing.assert_array_equal(fsl[::-1], ro.derive_raster(ro.FSL, st1, bed, 2.0))
     assert hdr["cellsize"] == 2.0 and hdr["nodata_value"] == -9999.0
-    maxd, _ = read_tiff(os.path.join(out, "maxdepth_30.tif"))
+    host.hph_raster_read.restype = C.POINTER(C.c_double)
+    host.hph_raster_read.argtypes = [C.c_char_p, C.POINTER(C.c_ulong), C.POINTER(C.c_ulong), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                     C.POINTER(C.c_double)]
+    c, r, cs, x0, y0 = C.c_ulong(), C.c_ulong(), C.c_double(), C.c_double(), C.c_double()
+    vals = host.hph_raster_read(os.path.join(out, "maxdepth_30.img").encode(), C.byref(c), C.byref(r), C.byref(cs), C.byref(x0), C.byref(y0))
+    maxd = np.ctypeslib.as_array(vals, shape=(r.value, c.value))[::-1]
     np.testing.assert_array_equal(maxd, ro.derive_raster(ro.MAX_DEPTH, st1, bed, 2.0))
+    check_hfa_structure(os.path.join(out, "maxdepth_30.img"), 40, 30)
     host.hph_model_destroy(C.c_void_p(h))
 
 

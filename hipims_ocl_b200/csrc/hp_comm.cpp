@@ -92,11 +92,25 @@ void comm_destroy(Comm* c) {
     delete c;
 }
 
+static const char* exchange_calls(Comm* c, const Planes& p, const Grid& g, int halo, size_t rb, cudaStream_t st);
+
+const char* comm_exchange_and_allreduce(Comm* c, const Planes& p, const Grid& g, int halo, size_t rb, unsigned long long* value, cudaStream_t st) {
+    if (const char* e = check(g_api.GroupStart(), "ncclGroupStart")) return e;
+    if (const char* e = exchange_calls(c, p, g, halo, rb, st)) return e;
+    if (const char* e = check(g_api.AllReduce(value, value, 1, ncclUint64, ncclMax, c->comm, st), "ncclAllReduce")) return e;
+    return check(g_api.GroupEnd(), "ncclGroupEnd");
+}
+
 const char* comm_exchange_halos(Comm* c, const Planes& p, const Grid& g, int halo, size_t rb, cudaStream_t st) {
+    if (const char* e = check(g_api.GroupStart(), "ncclGroupStart")) return e;
+    if (const char* e = exchange_calls(c, p, g, halo, rb, st)) return e;
+    return check(g_api.GroupEnd(), "ncclGroupEnd");
+}
+
+static const char* exchange_calls(Comm* c, const Planes& p, const Grid& g, int halo, size_t rb, cudaStream_t st) {
     const bool south = c->rank > 0, north = c->rank + 1 < c->world;
     const size_t row = static_cast<size_t>(g.pitch) * rb, bytes = row * halo;
     char* planes[4] = {static_cast<char*>(p.eta), static_cast<char*>(p.emax), static_cast<char*>(p.qx), static_cast<char*>(p.qy)};
-    if (const char* e = check(g_api.GroupStart(), "ncclGroupStart")) return e;
     for (char* base : planes) {
         if (south) {   // my lowest owned rows -> southern neighbour's northern halo; its top rows -> my southern halo
             if (const char* e = check(g_api.Send(base + row * g.own_y0, bytes, ncclUint8, c->rank - 1, c->comm, st), "ncclSend")) return e;
@@ -107,7 +121,7 @@ const char* comm_exchange_halos(Comm* c, const Planes& p, const Grid& g, int hal
             if (const char* e = check(g_api.Recv(base + row * g.own_y1, bytes, ncclUint8, c->rank + 1, c->comm, st), "ncclRecv")) return e;
         }
     }
-    return check(g_api.GroupEnd(), "ncclGroupEnd");
+    return nullptr;
 }
 
 const char* comm_allreduce_max(Comm* c, unsigned long long* value, cudaStream_t st) {

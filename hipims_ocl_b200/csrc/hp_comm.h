@@ -23,6 +23,9 @@ void comm_destroy(Comm* c);
 // sends the `halo` owned edge rows of every plane of `p` to the neighbouring strips and receives
 // their edge rows into this strip's halo rows (rank r-1 is the southern neighbour)
 const char* comm_exchange_halos(Comm* c, const Planes& p, const Grid& g, int halo, size_t real_bytes, cudaStream_t st);
+// both of the above in ONE NCCL group (small strips: a single aggregated launch instead of two)
+const char* comm_exchange_and_allreduce(Comm* c, const Planes& p, const Grid& g, int halo, size_t real_bytes, unsigned long long* value,
+                                        cudaStream_t st);
 // max over ranks of one unsigned 64-bit value (ordered bits of the wave speed), in place
 const char* comm_allreduce_max(Comm* c, unsigned long long* value, cudaStream_t st);
 

@@ -103,6 +103,7 @@ struct hp_scheme {
 namespace {
 
 constexpr int kGraphPairs = 8;
+constexpr long long kSmallStripCells = 32ll << 20;   // strips up to this size: unsplit step, graph replay
 constexpr int kCommSpareSMs = 4;     // SMs left to NCCL during the interior launch of a strip
 
 void drop_graphs(hp_scheme* s) {
@@ -168,8 +169,17 @@ int enqueue_iteration(hp_scheme* s, bool alt, int* launched) {
     if (s->comm == nullptr) {
         a.finalize = 1;
         n += step(a);
+    } else if (static_cast<long long>(s->grid.rows) * s->grid.cols <= kSmallStripCells && !(s->cfg.options & HP_OPT_SPLIT_STRIPS)) {
+        // Small row strips: there is too little interior work to hide the exchange behind, and the two edge launches
+        // cost more than they save.  One launch over all owned rows, then the halo send/recv and the all-reduce of the
+        // wave speed in ONE NCCL group, then the time controller.
+        a.finalize = 0;
+        n += step(a);
+        const char* err = hp::comm_exchange_and_allreduce(s->comm, a.dst, s->grid, mh ? 2 : 1, s->rb, s->max_bits, st);
+        if (err) return fail(HP_ERR_NCCL, "halo exchange + allreduce: %s", err);
+        n += s->K->advance(rb, a, st);
     } else {
-        // Row strips: edge rows first, their halo exchange overlaps the interior rows, then the
+        // Large row strips: edge rows first, their halo exchange overlaps the interior rows, then the
         // wave-speed maximum is all-reduced on the device and one thread runs the time controller.
         a.finalize = 0;
         const int halo = mh ? 2 : 1;
@@ -662,7 +672,7 @@ int hp_scheme_iterate(hp_scheme* s, uint32_t iterations) {
     // Measured on 4 GPUs: that pays on small strips (4096 x 4096: +1.5 %), but a captured exchange no longer overlaps
     // the interior kernel of a large strip (32768 x 4096: 2.74 ms per step against 2.38 ms launched directly), so
     // large strips are launched directly -- their launch latency is hidden anyway.
-    const bool small_strip = static_cast<long long>(s->grid.rows) * s->grid.cols <= (32ll << 20);
+    const bool small_strip = static_cast<long long>(s->grid.rows) * s->grid.cols <= kSmallStripCells;
     const bool use_graph = !(s->cfg.options & HP_OPT_NO_GRAPH) && (s->comm == nullptr || small_strip);
     int rc = HP_OK;
     auto direct = [&]() {

@@ -71,8 +71,10 @@ enum {
     HP_OPT_NO_TMA      = 1u << 2, /* use the plain-load kernels instead of the TMA-staged ones     */
     HP_OPT_TILE_KERNELS = 1u << 3, /* MUSCL-Hancock: use the TMA tile kernel (CTA-wide 2-D tiles) instead of
                                       the default marching kernel (one warp per column strip)      */
-    HP_OPT_MARCH_GODUNOV = 1u << 4 /* Godunov: use the marching kernel instead of the default TMA tile
+    HP_OPT_MARCH_GODUNOV = 1u << 4, /* Godunov: use the marching kernel instead of the default TMA tile
                                       kernel (equal on wet domains, slower on mostly dry ones)     */
+    HP_OPT_SPLIT_STRIPS = 1u << 5  /* row strips: always split a step into edge rows + interior rows with
+                                      the halo exchange overlapped (default only for large strips) */
 };
 
 /*

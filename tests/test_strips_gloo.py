@@ -1,4 +1,4 @@
-"""Host-side logic of the row-strip decomposition on CPU: two gloo ranks step their strips with the
+"""Host-side logic of the row-strip decomposition on CPU: two or three gloo ranks step their strips with the
 oracle kernels, exchange halo rows and all-reduce the wave-speed maximum exactly as the CUDA
 executor does with NCCL (hp_executor.cu: enqueue_iteration), and must reproduce the single-domain
 run bit for bit."""
@@ -95,9 +95,10 @@ def _worker(rank, world, port, scheme, precision, rows, cols, iters, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("scheme,precision", [("godunov", "double"), ("muscl-hancock", "double"), ("inertial", "single")])
-def test_two_rank_strips_match_single_domain(tmp_path, scheme, precision):
-    rows, cols, iters, world = 48, 40, 40, 2
+@pytest.mark.parametrize("scheme,precision,world", [("godunov", "double", 2), ("muscl-hancock", "double", 2), ("inertial", "single", 2),
+                                                    ("muscl-hancock", "double", 3)])      # 3 ranks: a strip with two neighbours
+def test_strips_match_single_domain(tmp_path, scheme, precision, world):
+    rows, cols, iters = 48, 40, 40
     mp.spawn(_worker, args=(world, _free_port(), scheme, precision, rows, cols, iters, str(tmp_path)), nprocs=world, join=True)
     parts = sorted((np.load(os.path.join(tmp_path, "rank%d.npz" % r)) for r in range(world)), key=lambda z: int(z["offset"]))
     got = np.concatenate([p["rows"] for p in parts], axis=0)

@@ -6,16 +6,22 @@
 A "step" is one iteration of the scheme over every cell of the domain: boundaries -> cell update
 -> CFL reduction -> time advance (one CSchemeGodunov::scheduleIteration of the reference).
 
-Workloads (BASELINE.json configs):
-  dambreak4096   configs[1]: circular dam break, 4096 x 4096 flat DEM, Godunov/HLLC, CFL timestep,
-                 friction on (default at N=1; at N>1 the domain is 4096 x 4096*N, one 4096-row strip
-                 per GPU -- weak scaling)
-  pluvial16384   configs[2]: uniform rain on a 16384^2 fractal DEM, MUSCL-Hancock fp64 (--workload)
-  river32768     configs[4]: 32768 columns x 4096*N rows river valley, MUSCL-Hancock fp64 (--workload)
+Default workload (BASELINE.json configs; the north star is the fp64 MUSCL-Hancock/HLLC step):
+  N = 1   pluvial16384  configs[2]: time-varying uniform rain on a 16384^2 fractal DEM, MUSCL-Hancock + MINMOD fp64,
+                        Manning friction -- the largest single-GPU configuration (268 M cells, 21.5 GB resident)
+  N > 1   river32768    configs[4]: 32768 columns x 4096*N rows river / tidal valley with imposed discharge and level
+                        cells, MUSCL-Hancock fp64, one 4096-row strip per GPU (weak scaling; N = 8 is the 32768^2
+                        domain), NCCL halo exchange + dt all-reduce
+Others with --workload: dambreak4096 (configs[1], Godunov fp64; -f32, -mh, -inertial variants), radar16384
+(configs[3]), newcastle (configs[0] shape).  At N = 1 the 4096^2 dam-break family is also run briefly and reported
+under "variants".
 
 Prints ONE JSON line (rank 0).  `value` is measured with inputs resident in HBM; `e2e` goes through
 the C ABI with HOST (pinned) buffers: upload of the whole domain, K iterations, read-back of the
-clock and of the final cell states, all inside the timed region.
+clock and of the final cell states, all inside the timed region.  Everything one-off -- CUDA graph
+capture (with the NCCL exchange inside), NCCL connection set-up -- is done before the warm-up steps,
+whatever --warmup is.  At N > 1 the line also carries `phases` (per-phase device times of the strip
+iteration) and `strip_parity` (strips against one GPU, bit for bit, on a slab of the same workload).
 """
 import argparse
 import json
@@ -78,14 +84,16 @@ def attach_boundaries(sim, w, cols, total_rows):
         sim.add_gridded(hc.GRIDDED_RAIN_INTENSITY, 300.0, 256.0, 0.0, 0.0, rng.uniform(0.0, 80.0, size=(13, gr, gc)))
         pts = rng.integers(1, [total_rows - 1, cols - 1], size=(1024, 2))
         ids = sorted(set(int(y) * cols + int(x) for y, x in pts))
-        sim.add_cell(hc.DEPTH_IGNORE, hc.DISCHARGE_IS_VOLUME, ids, [[0.0, 0.0, 0.0, 0.0], [600.0, 0.0, 2.0, 0.0], [1200.0, 0.0, 0.0, 0.0], [1.0e6, 0.0, 0.0, 0.0]])
+        # evenly spaced like every series the reference's kernels can index (CLBoundaries.clc:43-52)
+        sim.add_cell(hc.DEPTH_IGNORE, hc.DISCHARGE_IS_VOLUME, ids,
+                     [[600.0 * i, 0.0, q, 0.0] for i, q in enumerate([0.0, 2.0, 0.0] + [0.0] * 22)])
     elif kind == "river":
         # one river per 4096-row strip (see make_inputs): every strip carries the same forcing
         period = w["rows_per_gpu"]
         band = max(4, period // 64)
         mids = [k * period + period // 2 for k in range(max(1, total_rows // period))]
         west = [y * cols + 1 for mid in mids for y in range(mid - band, mid + band)]
-        ts = np.array([[0.0, 0.0, 0.0, 0.0], [600.0, 0.0, 5000.0, 0.0], [1.0e6, 0.0, 5000.0, 0.0]])
+        ts = np.array([[600.0 * i, 0.0, 5000.0 if i else 0.0, 0.0] for i in range(150)])   # evenly spaced, 25 h
         ts[:, 2] /= len(west)
         sim.add_cell(hc.DEPTH_IGNORE, hc.DISCHARGE_IS_DISCHARGE, west, ts)
         east = [y * cols + cols - 2 for mid in mids for y in range(mid - band, mid + band)]
@@ -179,8 +187,19 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def position_noise(y, x):
+    """Deterministic noise in [-1, 1) from the GLOBAL cell position (integer hash), so that a strip generated on its own
+    agrees row for row with the same rows of the whole domain (halo rows included)."""
+    h = (y.astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15)) ^ (x.astype(np.uint64) * np.uint64(0xC2B2AE3D27D4EB4F))
+    h ^= h >> np.uint64(29)
+    h *= np.uint64(0xBF58476D1CE4E5B9)
+    h ^= h >> np.uint64(32)
+    return (h >> np.uint64(11)).astype(np.float64) * (2.0 / 9007199254740992.0) - 1.0
+
+
 def make_inputs(w, rows, cols, dtype, row_offset=0, total_rows=None):
-    """Host arrays of one strip (rows [row_offset, row_offset+rows) of a total_rows-tall domain)."""
+    """Host arrays of one strip (rows [row_offset, row_offset+rows) of a total_rows-tall domain).  Every value is a
+    function of the global cell position only."""
     total_rows = rows if total_rows is None else total_rows
     if w["scenario"] == "dambreak":
         y, x = np.mgrid[row_offset:row_offset + rows, 0:cols]
@@ -191,24 +210,25 @@ def make_inputs(w, rows, cols, dtype, row_offset=0, total_rows=None):
         return bed.astype(dtype), sc.make_states(bed, depth, dtype=dtype), np.full((rows, cols), 0.03, dtype=dtype)
     if w["scenario"] == "pluvial":
         tile = sc.fractal_dem(2048, 2048, 20260817)
-        reps = (-(-rows // 2048), -(-cols // 2048))
-        bed = np.tile(tile, reps)[:rows, :cols]
+        ys = np.arange(row_offset, row_offset + rows) % 2048
+        xs_i = np.arange(cols) % 2048
+        bed = tile[ys][:, xs_i]
         xs = np.arange(cols)[None, :] * 0.002
         bed = sc.round4(bed + xs)
         level = np.quantile(tile, 0.3)
         depth = sc.round4(np.maximum(level - bed, 0.0))
         return bed.astype(dtype), sc.make_states(bed, depth, dtype=dtype), np.full((rows, cols), 0.035, dtype=dtype)
     if w["scenario"] == "valley":
-        y = (np.arange(row_offset, row_offset + rows, dtype=np.float64))[:, None]
-        x = np.arange(cols, dtype=np.float64)[None, :]
+        gy = np.arange(row_offset, row_offset + rows, dtype=np.int64)[:, None]
+        gx = np.arange(cols, dtype=np.int64)[None, :]
+        x = gx.astype(np.float64)
         # the valley repeats every rows_per_gpu rows (one west->east river per strip), so that the weak-scaling runs
         # give every rank the same wet/dry mix as the single-GPU strip instead of one wet rank and seven dry ones
         period = float(w["rows_per_gpu"])
-        y = np.mod(y, period)
+        y = np.mod(gy.astype(np.float64), period)
         mid, width = period / 2.0, max(8.0, period / 16.0)
-        rng = np.random.default_rng(20260819 + row_offset)
         bed = 0.001 * (cols - x) + 20.0 * (1.0 - np.exp(-(((y - mid) / width) ** 2))) + 1.0
-        bed = sc.round4(bed + 0.5 * rng.uniform(-1.0, 1.0, size=(rows, cols)))
+        bed = sc.round4(bed + 0.5 * position_noise(np.broadcast_to(gy, (rows, cols)), np.broadcast_to(gx, (rows, cols))))
         depth = sc.round4(np.maximum(0.001 * (cols - x) + 3.0 - bed, 0.0))
         return bed.astype(dtype), sc.make_states(bed, depth, dtype=dtype), np.full((rows, cols), 0.03, dtype=dtype)
     raise ValueError(w["scenario"])
@@ -260,7 +280,23 @@ def cpu_baseline(w, budget_s=12.0):
             "sample": "%d steps of a %dx%d crop of the workload, all %d host threads (OpenMP), %.1f s" % (steps, n, n, cores, dt)}
 
 
+def config_dict(name, w, world, options=0):
+    """The `config` object of the JSON line -- built by ONE function for both arms, so that they are equal."""
+    cols, rows_own = w["cols"], w["rows_per_gpu"]
+    rb = 8 if w["precision"] == "double" else 4
+    halo = 2 if w["scheme"] == "muscl-hancock" else 1
+    rows_held = rows_own + (2 * halo if world > 2 else halo if world == 2 else 0)
+    return {"workload": name, "scheme": w["scheme"], "riemann_solver": "hllc", "cols": cols, "rows": rows_own * world,
+            "rows_per_gpu": rows_own, "friction": True, "timestep": "cfl 0.5",
+            "boundaries": w.get("boundaries", "none"),
+            "decomposition": "row strips x%d" % world if world > 1 else "single domain",
+            "l2": "state planes %.0f MB per GPU exceed the 126 MB L2; no flush needed" % (10 * cols * rows_held * rb / 1e6),
+            "options": options}
+
+
 def run_reference_arm(args, w, name):
+    """The reference's own kernels (oracle/_ref, compiled from the reference's .clc sources; else the oracle port) on all
+    host threads; each step is one iteration over a bounded crop of the same workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -271,43 +307,108 @@ def run_reference_arm(args, w, name):
     n = int(min(w["cols"], max(256, (120.0 * rate / total) ** 0.5))) // 256 * 256
     n = max(256, n)
     rate, dt, kind = cpu_rate(w, n, args.steps, args.warmup)
-    cfg = cfg_for(w, n, n)
     line = {
         "impl": "reference", "metric": "cell-updates/s", "value": rate, "unit": "cell-updates/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64" if cfg.precision == "double" else "f32",
-        "data": "synthetic", "config": {"workload": name, "scheme": cfg.scheme, "crop": "%dx%d" % (n, n)},
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64" if w["precision"] == "double" else "f32",
+        "data": "synthetic", "config": config_dict(name, w, max(1, args.gpus), args.options),
         "cpu_baseline": {"value": rate, "unit": "cell-updates/s", "cores": cores, "kind": kind,
-                         "sample": "each step = one iteration over a %dx%d crop of %s on %d host threads" % (n, n, name, cores)},
+                         "sample": "each step = one iteration over a %dx%d crop of %s on %d host threads (OpenMP)" % (n, n, name, cores)},
         "e2e": {"value": rate, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
+def issue_roofline(name, value_per_gpu, sm_mhz):
+    """Second roofline: these kernels are bound by instruction issue, not DRAM.  From the committed opcode
+    histogram of the same kernel: cycles per 32 cell-updates >= 2.2 * N_fp64 + N_other on each of the 592 schedulers."""
+    rec = ncu_record(name)
+    if not rec or "fp64_instructions_per_32_cells" not in rec:
+        return None
+    n64, nall = rec["fp64_instructions_per_32_cells"], rec["warp_instructions_per_32_cells"]
+    ghz = (sm_mhz or 1965.0) * 1e-3
+    peak = 592 * ghz * 1e9 * 32 / (2.2 * n64 + (nall - n64))
+    return {"bound": "fp64-issue", "achieved": value_per_gpu, "peak": peak, "unit": "cell-updates/s", "frac": value_per_gpu / peak,
+            "model": "592 schedulers x SM clock x 32 / (2.2 x fp64 + other warp instructions per 32 cell-updates)",
+            "fp64_instructions_per_32_cells": n64, "warp_instructions_per_32_cells": nall,
+            "source": "committed ncu capture (profiles/%s)" % rec.get("profile", "kernels.json")}
+
+
+def strip_parity_check(hx, ex, dist, w, rank, world, options):
+    """Strips against ONE GPU, bit for bit: a 4096-column slab of the same workload with 256 rows per rank, 10 iterations
+    through the same library calls as the timed run (NCCL halo exchange + dt all-reduce); rank 0 also runs the whole slab
+    on its own GPU and compares states and clocks (what CDomainLink's exchange must guarantee,
+    src/Domain/Links/CDomainLink.cpp:168-270)."""
+    from hipims_ocl_b200 import strips
+    cols, rows_own, iters = min(w["cols"], 4096), 256, 10
+    ws = dict(w, cols=cols, rows_per_gpu=rows_own)
+    total = rows_own * world
+    cfg_full = cfg_for(ws, total, cols)
+    dtype = np.float64 if cfg_full.precision == "double" else np.float32
+    strip = strips.make_strip(total, world, rank, cfg_full.scheme)
+    cfg = cfg_full.with_(rows=strip.rows)
+    bed, st, man = make_inputs(ws, strip.rows, cols, dtype, row_offset=strip.row_offset - strip.halo_south, total_rows=total)
+    sim = hx.CudaScheme(ex, cfg, options=options, global_rows=total, row_offset=strip.row_offset,
+                        halo_south=strip.halo_south, halo_north=strip.halo_north)
+    ids = [hx.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    sim.attach_comm(ids[0], rank, world)
+    sim.upload(st, bed, man)
+    attach_boundaries(sim, ws, cols, total)
+    sim.set_target(1.0e7)
+    sim.iterate(iters)
+    mine = sim.download()[strip.owned_local_slice()]
+    stats = sim.stats()
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (strip.row_offset, mine, stats))
+    result = None
+    if rank == 0:
+        full = np.concatenate([g[1] for g in sorted(gathered, key=lambda g: g[0])], axis=0)
+        bed, st, man = make_inputs(ws, total, cols, dtype, row_offset=0, total_rows=total)
+        ref = hx.CudaScheme(ex, cfg_full, options=options)
+        ref.upload(st, bed, man)
+        attach_boundaries(ref, ws, cols, total)
+        ref.set_target(1.0e7)
+        ref.iterate(iters)
+        want, want_stats = ref.download(), ref.stats()
+        same = np.array_equal(full, want) and all(g[2] == want_stats for g in gathered)
+        changed = not np.array_equal(want, st)
+        result = {"verdict": "identical" if same and changed else "DIFFERENT", "slab": "%d x %d" % (cols, total),
+                  "iterations": iters, "max_abs_diff": float(np.abs(full - want).max()), "time": want_stats["time"],
+                  "wet_cells": int(((want[..., 0] - bed) > 1e-10).sum())}
+        ref.close()
+    dist.barrier()
+    sim.close()
+    return result
+
+
 # ------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="dambreak4096", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS),
+                    help="default: pluvial16384 (configs[2]) on one GPU, river32768 (configs[4]) on several")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-variants", action="store_true")
+    ap.add_argument("--no-strip-parity", action="store_true")
     ap.add_argument("--options", type=int, default=0, help="HP_OPT_* bit mask")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
-    w = WORKLOADS[args.workload]
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    name = args.workload or ("pluvial16384" if max(args.gpus, world) == 1 else "river32768")
+    w = WORKLOADS[name]
 
     if args.impl == "reference":
-        run_reference_arm(args, w, args.workload)
+        run_reference_arm(args, w, name)
         return
 
     import torch
     from hipims_ocl_b200 import executor as hx
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.gpus != world and world > 1:
@@ -348,6 +449,7 @@ def main():
     t_bed = torch.from_numpy(bed).pin_memory()
     t_man = torch.from_numpy(man).pin_memory()
     t_out = torch.empty_like(t_st).pin_memory()
+    del st, bed, man
     h2d = t_st.numel() * t_st.element_size() + t_bed.numel() * t_bed.element_size() + t_man.numel() * t_man.element_size()
     d2h = t_out.numel() * t_out.element_size() + 72
 
@@ -357,6 +459,14 @@ def main():
         sim.reset_counters()
         sim.set_target(1.0e7)
         sim.sync()
+
+    # ---- one-off work, before the warm-up steps and whatever --warmup is --------------------------
+    # CUDA graphs (with the NCCL exchange captured inside for small strips) are built and uploaded here, and 36
+    # untimed iterations replay each of them twice and let NCCL set up its peer connections; then the state is reset.
+    reset()
+    sim.prepare_graphs()
+    sim.iterate(36, sync=True)
+    barrier()
 
     # ---- device-resident throughput ------------------------------------------------------------
     reset()
@@ -397,34 +507,64 @@ def main():
     e2e_value = cells_total * args.steps / (float(e2e_t.item()) * 1e-3)
     assert np.isfinite(t_out.numpy()[..., 0]).all() and final.batch_successful > 0
 
+    # ---- multi-GPU: where the strip iteration spends its time, and strips against one GPU ------------
+    phases, parity = None, None
+    if world > 1:
+        sim.strip_timing(True)
+        sim.iterate(4, sync=True)
+        sim.strip_timing(True)                   # clears the accumulators: the first timed-mode iterations settle
+        sim.iterate(12, sync=True)
+        ph, n_ph = sim.strip_phases()
+        sim.strip_timing(False)
+        ph_t = torch.tensor([ph[k] for k in hx.STRIP_PHASES], dtype=torch.float64, device="cuda")
+        ph_max = ph_t.clone()
+        dist.all_reduce(ph_max, op=dist.ReduceOp.MAX)
+        phases = {"unit": "ms per iteration", "iterations": n_ph, "rank0": ph,
+                  "max_over_ranks": dict(zip(hx.STRIP_PHASES, [float(v) for v in ph_max.tolist()])),
+                  "note": "direct launches with one host sync per iteration (diagnostic mode); small strips: interior_rows is "
+                          "the whole step and allreduce is the halo exchange + all-reduce NCCL group"}
+        if not args.no_strip_parity:
+            parity = strip_parity_check(hx, ex, dist, w, rank, world, args.options)
+
     if rank == 0:
         peak, peak_src = peak_hbm()
         abytes = algorithmic_bytes_per_cell(cfg)
-        kernel_s = ms * 1e-3 / args.steps          # one step kernel per iteration on this rank
+        kernel_s = ms * 1e-3 / args.steps          # one step per iteration on this rank (edge + interior launches on large strips)
         achieved = abytes * cols * rows_own / kernel_s / 1e9
+        rec = ncu_record(name)
+        traffic = rec["dram_bytes_per_cell"] * cols * rows_own if rec and "dram_bytes_per_cell" in rec else None
         line = {
             "metric": "cell-updates/s", "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64" if cfg.precision == "double" else "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "scheme": cfg.scheme, "riemann_solver": "hllc", "cols": cols,
-                       "rows": total_rows, "rows_per_gpu": rows_own, "friction": True, "timestep": "cfl 0.5",
-                       "decomposition": "row strips x%d" % world if world > 1 else "single domain",
-                       "l2": "state planes %.0f MB per rank exceed the 126 MB L2; no flush needed" %
-                             (10 * cols * rows * cfg.real_bytes / 1e6),
-                       "options": args.options},
+            "config": config_dict(name, w, world, args.options),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": measured_traffic(args.workload), "peak_source": peak_src,
-                         "algorithmic_bytes_per_cell": abytes, "kernel_ms": kernel_s * 1e3,
+                         "traffic": traffic,
+                         "traffic_source": ("committed ncu capture (profiles/%s): %.1f dram bytes per cell-update x the cells one "
+                                            "launch covers on this GPU" % (rec.get("profile", "kernels.json"), rec["dram_bytes_per_cell"]))
+                                           if traffic else None,
+                         "peak_source": peak_src, "algorithmic_bytes_per_cell": abytes, "kernel_ms": kernel_s * 1e3,
+                         "kernel": rec.get("kernel") if rec else None,
                          # the kernels are bound by instruction issue / the fp64 pipe, not by DRAM:
-                         # the committed ncu capture of the same kernel says how far
-                         "ncu": ncu_record(args.workload)},
+                         # figures of the same kernel FROM THE COMMITTED CAPTURE, not measured in this run
+                         "ncu_from_committed_capture": rec},
+            "roofline_issue": issue_roofline(name, value / world, clocks.get("sm_mhz")),
             "e2e": {"value": e2e_value, "unit": "cell-updates/s", "h2d_bytes_per_step": h2d / args.steps,
                     "d2h_bytes_per_step": d2h / args.steps,
-                    "note": "upload of the whole domain + K iterations + clock and state read-back, amortised per step"},
+                    "note": "upload of the whole domain + K iterations + clock and state read-back, amortised per step; with "
+                            "K = %d the host<->device copies are %.0f %% of this leg" %
+                            (args.steps, 100.0 * max(0.0, 1.0 - (ms_max / max(float(e2e_t.item()), 1e-9))))},
             "gpu_launches": int(launches), "clocks": clocks,
             "sim": {"time": final.time, "timestep": final.timestep, "successful": final.batch_successful},
         }
-        if not args.no_variants and world == 1 and args.workload == "dambreak4096":
+        if phases:
+            line["phases"] = phases
+        if parity:
+            line["strip_parity"] = parity["verdict"]
+            line["strip_parity_detail"] = parity
+        if not args.no_variants and world == 1 and args.workload is None:
+            sim.close()
+            del t_st, t_bed, t_man, t_out
             line["variants"] = run_variants(hx, ex, args)
         if not args.no_cpu_baseline and world == 1:
             sim.close()
@@ -434,12 +574,16 @@ def main():
         dist.barrier()
         sim.close()                  # the NCCL communicator of the strip goes before the process group
         dist.destroy_process_group()
+    if parity and parity["verdict"] != "identical":
+        raise SystemExit("strip parity FAILED: %r" % (parity,))
 
 
 def run_variants(hx, ex, args):
-    """Short device-resident runs of the other precision / schemes on the same 4096^2 dam break."""
+    """Short device-resident runs of configs[1] (4096^2 circular dam break, Godunov fp64 / fp32) and of the other schemes
+    on the same domain."""
     out = {}
-    for name in ("dambreak4096-f32", "dambreak4096-mh", "dambreak4096-mh-f32", "dambreak4096-inertial", "dambreak4096-inertial-f32"):
+    for name in ("dambreak4096", "dambreak4096-f32", "dambreak4096-mh", "dambreak4096-mh-f32", "dambreak4096-inertial",
+                 "dambreak4096-inertial-f32"):
         w = WORKLOADS[name]
         cfg = cfg_for(w, w["rows_per_gpu"], w["cols"])
         dtype = np.float64 if cfg.precision == "double" else np.float32
@@ -448,7 +592,8 @@ def run_variants(hx, ex, args):
         sim.upload(st, bed, man)
         sim.set_target(1.0e7)
         steps = max(20, args.steps // 2)
-        sim.iterate(args.warmup, sync=True)
+        sim.prepare_graphs()
+        sim.iterate(max(args.warmup, 18), sync=True)
         ex.timer_start()
         sim.iterate(steps, sync=False)
         ms = ex.timer_stop()

@@ -67,6 +67,7 @@ const char* check(ncclResult_t r, const char* what) {
 struct Comm {
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
+    bool broken = false;
 };
 
 static_assert(sizeof(ncclUniqueId) == 128, "HP_COMM_ID_BYTES");
@@ -94,17 +95,33 @@ void comm_destroy(Comm* c) {
 
 static const char* exchange_calls(Comm* c, const Planes& p, const Grid& g, int halo, size_t rb, cudaStream_t st);
 
+// A failed call inside a group must still close the group: an open ncclGroupStart would silently defer every later
+// NCCL call of this thread (torch.distributed's included).  The first error is the one reported; the communicator
+// is marked broken and refuses further work (its state after a failed group is undefined).
+static const char* close_group(Comm* c, const char* first) {
+    const ncclResult_t r = g_api.GroupEnd();
+    if (first) { c->broken = true; return first; }
+    if (const char* e = check(r, "ncclGroupEnd")) { c->broken = true; return e; }
+    return nullptr;
+}
+static const char* broken_comm() { g_err = "the NCCL communicator failed earlier and cannot be used"; return g_err.c_str(); }
+
 const char* comm_exchange_and_allreduce(Comm* c, const Planes& p, const Grid& g, int halo, size_t rb, unsigned long long* value, cudaStream_t st) {
+    if (c->broken) return broken_comm();
     if (const char* e = check(g_api.GroupStart(), "ncclGroupStart")) return e;
-    if (const char* e = exchange_calls(c, p, g, halo, rb, st)) return e;
-    if (const char* e = check(g_api.AllReduce(value, value, 1, ncclUint64, ncclMax, c->comm, st), "ncclAllReduce")) return e;
-    return check(g_api.GroupEnd(), "ncclGroupEnd");
+    const char* e = exchange_calls(c, p, g, halo, rb, st);
+    std::string keep;
+    if (e) keep = e;
+    else if (const char* e2 = check(g_api.AllReduce(value, value, 1, ncclUint64, ncclMax, c->comm, st), "ncclAllReduce")) keep = e2;
+    if (!keep.empty()) { close_group(c, keep.c_str()); g_err = keep; return g_err.c_str(); }
+    return close_group(c, nullptr);
 }
 
 const char* comm_exchange_halos(Comm* c, const Planes& p, const Grid& g, int halo, size_t rb, cudaStream_t st) {
+    if (c->broken) return broken_comm();
     if (const char* e = check(g_api.GroupStart(), "ncclGroupStart")) return e;
-    if (const char* e = exchange_calls(c, p, g, halo, rb, st)) return e;
-    return check(g_api.GroupEnd(), "ncclGroupEnd");
+    if (const char* e = exchange_calls(c, p, g, halo, rb, st)) { const std::string keep = e; close_group(c, keep.c_str()); g_err = keep; return g_err.c_str(); }
+    return close_group(c, nullptr);
 }
 
 static const char* exchange_calls(Comm* c, const Planes& p, const Grid& g, int halo, size_t rb, cudaStream_t st) {
@@ -125,6 +142,7 @@ static const char* exchange_calls(Comm* c, const Planes& p, const Grid& g, int h
 }
 
 const char* comm_allreduce_max(Comm* c, unsigned long long* value, cudaStream_t st) {
+    if (c->broken) return broken_comm();
     return check(g_api.AllReduce(value, value, 1, ncclUint64, ncclMax, c->comm, st), "ncclAllReduce");
 }
 

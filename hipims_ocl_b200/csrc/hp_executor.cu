@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -57,7 +58,11 @@ struct Boundary {
 
 }  // namespace
 
+// Every entry point takes the handle's lock: the reference's main thread polls and reads back while the scheme's
+// worker thread enqueues batches (src/Schemes/CSchemeGodunov.cpp:1116-1141, CScheme.h:137-139).  Recursive because
+// entry points call each other (destroy from a failed create, ...).  Lock order: scheme, then executor.
 struct hp_executor {
+    std::recursive_mutex mu;
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
@@ -66,6 +71,7 @@ struct hp_executor {
 };
 
 struct hp_scheme {
+    std::recursive_mutex mu;
     hp_executor* ex = nullptr;
     hp_scheme_config cfg{};
     hp::Grid grid{};
@@ -91,13 +97,15 @@ struct hp_scheme {
     hp::TmaMapsPOD maps_a{}, maps_b{};   // descriptors with buffer A / buffer B as the source
     hp::TmaMaps6POD march_map{};         // bytes[0]: 3-D descriptor over the ten-plane block
     hp::Comm* comm = nullptr;
+    int world = 1;
+    bool small_strip = true;             // decided from rank-independent quantities in hp_scheme_attach_comm
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t ev_edges = nullptr, ev_halo = nullptr;
-    // HIPIMS_STRIP_TIMING=1 (with HP_OPT_NO_GRAPH): per-phase device times of the strip iteration, printed at destroy
+    // hp_scheme_strip_timing: per-phase device times of the strip iteration (direct launches while enabled)
     bool strip_timing = false;
     cudaEvent_t ev_t[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     double t_phase[5] = {0, 0, 0, 0, 0};
-    uint64_t t_count = 0, t_seen = 0;
+    uint64_t t_count = 0;
 };
 
 namespace {
@@ -166,18 +174,32 @@ int enqueue_iteration(hp_scheme* s, bool alt, int* launched) {
         if (s->use_tma) return s->K->step_tma(static_cast<int>(s->cfg.scheme), rb, args, alt ? &s->maps_b : &s->maps_a, sms, st);
         return s->K->step(static_cast<int>(s->cfg.scheme), rb, args, st);
     };
+    // per-phase device times of a strip iteration (hp_scheme_strip_timing; never inside a graph capture)
+    const bool timing = s->strip_timing && s->comm != nullptr;
+    auto mark = [&](int i) { if (timing) cudaEventRecord(s->ev_t[i], st); };
+    auto collect = [&]() {
+        if (!timing) return;
+        cudaEventSynchronize(s->ev_t[5]);
+        for (int i = 0; i < 5; ++i) { float ms = 0; cudaEventElapsedTime(&ms, s->ev_t[i], s->ev_t[i + 1]); s->t_phase[i] += ms; }
+        ++s->t_count;
+    };
     if (s->comm == nullptr) {
         a.finalize = 1;
         n += step(a);
-    } else if (static_cast<long long>(s->grid.rows) * s->grid.cols <= kSmallStripCells && !(s->cfg.options & HP_OPT_SPLIT_STRIPS)) {
+    } else if (s->small_strip && !(s->cfg.options & HP_OPT_SPLIT_STRIPS)) {
         // Small row strips: there is too little interior work to hide the exchange behind, and the two edge launches
         // cost more than they save.  One launch over all owned rows, then the halo send/recv and the all-reduce of the
         // wave speed in ONE NCCL group, then the time controller.
         a.finalize = 0;
+        mark(0); mark(1);
         n += step(a);
+        mark(2); mark(3);
         const char* err = hp::comm_exchange_and_allreduce(s->comm, a.dst, s->grid, mh ? 2 : 1, s->rb, s->max_bits, st);
         if (err) return fail(HP_ERR_NCCL, "halo exchange + allreduce: %s", err);
+        mark(4);
         n += s->K->advance(rb, a, st);
+        mark(5);
+        collect();
     } else {
         // Large row strips: edge rows first, their halo exchange overlaps the interior rows, then the
         // wave-speed maximum is all-reduced on the device and one thread runs the time controller.
@@ -187,32 +209,25 @@ int enqueue_iteration(hp_scheme* s, bool alt, int* launched) {
         const int e0 = y0 + halo < y1 ? y0 + halo : y1, e1 = y1 - halo > e0 ? y1 - halo : e0;
         hp::StepArgs lo = a, hi = a, mid = a;
         lo.y1 = e0; hi.y0 = e1; mid.y0 = e0; mid.y1 = e1;
-        const bool timing = s->strip_timing && (s->cfg.options & HP_OPT_NO_GRAPH);
-        if (timing) cudaEventRecord(s->ev_t[0], st);
+        mark(0);
         n += step(lo);
         n += step(hi);
-        if (timing) cudaEventRecord(s->ev_t[1], st);
+        mark(1);
         if (cudaEventRecord(s->ev_edges, st) != cudaSuccess) return fail(HP_ERR_CUDA, "cudaEventRecord failed");
         if (cudaStreamWaitEvent(s->comm_stream, s->ev_edges, 0) != cudaSuccess) return fail(HP_ERR_CUDA, "cudaStreamWaitEvent failed");
         const char* err = hp::comm_exchange_halos(s->comm, a.dst, s->grid, halo, s->rb, s->comm_stream);
         if (err) return fail(HP_ERR_NCCL, "halo exchange: %s", err);
         if (cudaEventRecord(s->ev_halo, s->comm_stream) != cudaSuccess) return fail(HP_ERR_CUDA, "cudaEventRecord failed");
         n += step(mid, kCommSpareSMs);
-        if (timing) cudaEventRecord(s->ev_t[2], st);
+        mark(2);
         if (cudaStreamWaitEvent(st, s->ev_halo, 0) != cudaSuccess) return fail(HP_ERR_CUDA, "cudaStreamWaitEvent failed");
-        if (timing) cudaEventRecord(s->ev_t[3], st);
+        mark(3);
         err = hp::comm_allreduce_max(s->comm, s->max_bits, st);
         if (err) return fail(HP_ERR_NCCL, "allreduce: %s", err);
-        if (timing) cudaEventRecord(s->ev_t[4], st);
+        mark(4);
         n += s->K->advance(rb, a, st);
-        if (timing) {
-            cudaEventRecord(s->ev_t[5], st);
-            cudaEventSynchronize(s->ev_t[5]);
-            if (++s->t_seen > 10) {                                  // the first iterations carry NCCL's connection set-up
-                for (int i = 0; i < 5; ++i) { float ms = 0; cudaEventElapsedTime(&ms, s->ev_t[i], s->ev_t[i + 1]); s->t_phase[i] += ms; }
-                ++s->t_count;
-            }
-        }
+        mark(5);
+        collect();
     }
     if (launched) *launched += n;
     cudaError_t e = cudaGetLastError();
@@ -360,8 +375,9 @@ int upload_series(hp_scheme* s, const double* host, size_t count, size_t padded,
     if (s->rb == 8) { double* d = reinterpret_cast<double*>(tmp.data()); for (size_t i = 0; i < count; ++i) d[i] = host[i]; }
     else { float* f = reinterpret_cast<float*>(tmp.data()); for (size_t i = 0; i < count; ++i) f[i] = static_cast<float>(host[i]); }
     HP_CUDA(cudaMalloc(out, tmp.size()));
-    HP_CUDA(cudaMemcpyAsync(*out, tmp.data(), tmp.size(), cudaMemcpyHostToDevice, s->ex->stream));
-    HP_CUDA(cudaStreamSynchronize(s->ex->stream));
+    cudaError_t e = cudaMemcpyAsync(*out, tmp.data(), tmp.size(), cudaMemcpyHostToDevice, s->ex->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->ex->stream);
+    if (e != cudaSuccess) { cudaFree(*out); *out = nullptr; return fail(HP_ERR_CUDA, "timeseries upload failed: %s", cudaGetErrorString(e)); }
     return HP_OK;
 }
 
@@ -395,31 +411,39 @@ int hp_executor_create(int device_ordinal, void* external_stream, hp_executor** 
     HP_CUDA(cudaSetDevice(device_ordinal));
     hp_executor* ex = new hp_executor();
     ex->device = device_ordinal;
-    HP_CUDA(cudaGetDeviceProperties(&ex->prop, device_ordinal));
-    if (ex->prop.major < 10) {
-        const int major = ex->prop.major, minor = ex->prop.minor;
-        delete ex;
-        return fail(HP_ERR_NO_DEVICE, "device is sm_%d%d; this library is built for sm_100a (B200) only", major, minor);
-    }
+    // on any failure below the half-built executor is released again (hp_executor_destroy copes with missing parts)
+    auto bail = [&](int code) { const std::string keep = g_last_error; hp_executor_destroy(ex); g_last_error = keep; return code; };
+    cudaError_t e = cudaGetDeviceProperties(&ex->prop, device_ordinal);
+    if (e != cudaSuccess) return bail(fail(HP_ERR_CUDA, "cudaGetDeviceProperties failed: %s", cudaGetErrorString(e)));
+    if (ex->prop.major < 10)
+        return bail(fail(HP_ERR_NO_DEVICE, "device is sm_%d%d; this library is built for sm_100a (B200) only", ex->prop.major, ex->prop.minor));
     if (external_stream) { ex->stream = static_cast<cudaStream_t>(external_stream); ex->own_stream = false; }
-    else { HP_CUDA(cudaStreamCreateWithFlags(&ex->stream, cudaStreamNonBlocking)); ex->own_stream = true; }
-    HP_CUDA(cudaEventCreate(&ex->ev0));
-    HP_CUDA(cudaEventCreate(&ex->ev1));
+    else {
+        e = cudaStreamCreateWithFlags(&ex->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { ex->stream = nullptr; return bail(fail(HP_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e))); }
+        ex->own_stream = true;
+    }
+    if ((e = cudaEventCreate(&ex->ev0)) != cudaSuccess || (e = cudaEventCreate(&ex->ev1)) != cudaSuccess)
+        return bail(fail(HP_ERR_CUDA, "cudaEventCreate failed: %s", cudaGetErrorString(e)));
     *out = ex;
     return HP_OK;
 }
 
 void hp_executor_destroy(hp_executor* ex) {
     if (!ex) return;
-    cudaSetDevice(ex->device);
-    if (ex->ev0) cudaEventDestroy(ex->ev0);
-    if (ex->ev1) cudaEventDestroy(ex->ev1);
-    if (ex->own_stream && ex->stream) cudaStreamDestroy(ex->stream);
+    {
+        std::lock_guard<std::recursive_mutex> lock__(ex->mu);
+        cudaSetDevice(ex->device);
+        if (ex->ev0) cudaEventDestroy(ex->ev0);
+        if (ex->ev1) cudaEventDestroy(ex->ev1);
+        if (ex->own_stream && ex->stream) cudaStreamDestroy(ex->stream);
+    }
     delete ex;
 }
 
 int hp_executor_describe(hp_executor* ex, char* name, size_t name_len, int* sm_count, size_t* total_mem) {
     if (!ex) return fail(HP_ERR_INVALID, "executor is null");
+    std::lock_guard<std::recursive_mutex> lock__(ex->mu);
     if (name && name_len) { strncpy(name, ex->prop.name, name_len - 1); name[name_len - 1] = 0; }
     if (sm_count) *sm_count = ex->prop.multiProcessorCount;
     if (total_mem) *total_mem = ex->prop.totalGlobalMem;
@@ -428,16 +452,19 @@ int hp_executor_describe(hp_executor* ex, char* name, size_t name_len, int* sm_c
 
 int hp_executor_finish(hp_executor* ex) {
     if (!ex) return fail(HP_ERR_INVALID, "executor is null");
+    // the stream handle never changes: block WITHOUT the lock so that another thread can keep enqueueing
     HP_CUDA(cudaStreamSynchronize(ex->stream));
     return HP_OK;
 }
 int hp_executor_timer_start(hp_executor* ex) {
     if (!ex) return fail(HP_ERR_INVALID, "executor is null");
+    std::lock_guard<std::recursive_mutex> lock__(ex->mu);
     HP_CUDA(cudaEventRecord(ex->ev0, ex->stream));
     return HP_OK;
 }
 int hp_executor_timer_stop(hp_executor* ex, float* ms) {
     if (!ex || !ms) return fail(HP_ERR_INVALID, "null argument");
+    std::lock_guard<std::recursive_mutex> lock__(ex->mu);
     HP_CUDA(cudaEventRecord(ex->ev1, ex->stream));
     HP_CUDA(cudaEventSynchronize(ex->ev1));
     HP_CUDA(cudaEventElapsedTime(ms, ex->ev0, ex->ev1));
@@ -499,25 +526,25 @@ int hp_scheme_create(hp_executor* ex, const hp_scheme_config* cfg, hp_scheme** o
 
 void hp_scheme_destroy(hp_scheme* s) {
     if (!s) return;
-    cudaSetDevice(s->ex->device);
-    cudaStreamSynchronize(s->ex->stream);
-    drop_graphs(s);
-    if (s->comm) hp::comm_destroy(s->comm);
-    if (s->comm_stream) cudaStreamDestroy(s->comm_stream);
-    if (s->strip_timing && s->t_count)
-        fprintf(stderr, "[hipims strip timing] %llu iterations, ms per iteration: edges %.4f | interior %.4f | wait halo %.4f | all-reduce %.4f | clock %.4f\n",
-                (unsigned long long)s->t_count, s->t_phase[0] / s->t_count, s->t_phase[1] / s->t_count, s->t_phase[2] / s->t_count,
-                s->t_phase[3] / s->t_count, s->t_phase[4] / s->t_count);
-    for (auto& e : s->ev_t) if (e) cudaEventDestroy(e);
-    if (s->ev_edges) cudaEventDestroy(s->ev_edges);
-    if (s->ev_halo) cudaEventDestroy(s->ev_halo);
-    cudaFree(s->block); cudaFree(s->clock); cudaFree(s->max_bits); cudaFree(s->ticket); cudaFree(s->staging);
-    for (auto& b : s->bdys) { cudaFree(b.series); cudaFree(b.relations); }
+    {
+        std::lock_guard<std::recursive_mutex> lock__(s->mu);
+        cudaSetDevice(s->ex->device);
+        cudaStreamSynchronize(s->ex->stream);
+        drop_graphs(s);
+        if (s->comm) hp::comm_destroy(s->comm);
+        if (s->comm_stream) cudaStreamDestroy(s->comm_stream);
+        for (auto& e : s->ev_t) if (e) cudaEventDestroy(e);
+        if (s->ev_edges) cudaEventDestroy(s->ev_edges);
+        if (s->ev_halo) cudaEventDestroy(s->ev_halo);
+        cudaFree(s->block); cudaFree(s->clock); cudaFree(s->max_bits); cudaFree(s->ticket); cudaFree(s->staging);
+        for (auto& b : s->bdys) { cudaFree(b.series); cudaFree(b.relations); }
+    }
     delete s;
 }
 
 int hp_boundary_add_uniform(hp_scheme* s, const hp_bdy_uniform* conf, const double* series) {
     if (!s || !conf || !series) return fail(HP_ERR_INVALID, "null argument");
+    std::lock_guard<std::recursive_mutex> lock__(s->mu);
     if (conf->entries < 2 || !(conf->interval > 0.0)) return fail(HP_ERR_INVALID, "a boundary timeseries is too short");
     Boundary b; b.kind = 0; b.uniform = *conf;
     int rc = upload_series(s, series, 2 * static_cast<size_t>(conf->entries), 2 * static_cast<size_t>(conf->entries) + 2, &b.series);
@@ -529,6 +556,7 @@ int hp_boundary_add_uniform(hp_scheme* s, const hp_bdy_uniform* conf, const doub
 
 int hp_boundary_add_gridded(hp_scheme* s, const hp_bdy_gridded* conf, const double* series) {
     if (!s || !conf || !series) return fail(HP_ERR_INVALID, "null argument");
+    std::lock_guard<std::recursive_mutex> lock__(s->mu);
     if (conf->entries < 1 || conf->rows < 1 || conf->cols < 1 || !(conf->interval > 0.0) || !(conf->resolution > 0.0))
         return fail(HP_ERR_INVALID, "bad gridded boundary configuration");
     Boundary b; b.kind = 1; b.gridded = *conf;
@@ -543,6 +571,7 @@ int hp_boundary_add_gridded(hp_scheme* s, const hp_bdy_gridded* conf, const doub
 
 int hp_boundary_add_cell(hp_scheme* s, const hp_bdy_cell* conf, const uint64_t* relations, const double* series) {
     if (!s || !conf || !relations || !series) return fail(HP_ERR_INVALID, "null argument");
+    std::lock_guard<std::recursive_mutex> lock__(s->mu);
     if (conf->entries < 2 || !(conf->interval > 0.0)) return fail(HP_ERR_INVALID, "a boundary timeseries is too short");
     Boundary b; b.kind = 2; b.cell = *conf; b.count = conf->relations;
     // the kernel reads entry base+1 (CLBoundaries.clc:44,49): one padding entry
@@ -556,9 +585,13 @@ int hp_boundary_add_cell(hp_scheme* s, const hp_bdy_cell* conf, const uint64_t* 
         const long long y = static_cast<long long>(gy) - g.gy0;
         local[i] = (y >= 0 && y < g.rows) ? y * g.pitch + static_cast<long long>(gx) : -1;
     }
-    HP_CUDA(cudaMalloc(reinterpret_cast<void**>(&b.relations), local.size() * sizeof(long long)));
-    HP_CUDA(cudaMemcpyAsync(b.relations, local.data(), local.size() * sizeof(long long), cudaMemcpyHostToDevice, s->ex->stream));
-    HP_CUDA(cudaStreamSynchronize(s->ex->stream));
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&b.relations), local.size() * sizeof(long long));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(b.relations, local.data(), local.size() * sizeof(long long), cudaMemcpyHostToDevice, s->ex->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->ex->stream);
+    if (e != cudaSuccess) {
+        cudaFree(b.series); cudaFree(b.relations);
+        return fail(e == cudaErrorMemoryAllocation ? HP_ERR_OOM : HP_ERR_CUDA, "boundary relations upload failed: %s", cudaGetErrorString(e));
+    }
     s->bdys.push_back(b);
     drop_graphs(s);
     return static_cast<int>(s->bdys.size()) - 1;
@@ -566,6 +599,7 @@ int hp_boundary_add_cell(hp_scheme* s, const hp_bdy_cell* conf, const uint64_t* 
 
 int hp_scheme_upload_cells(hp_scheme* s, const void* states, const void* bed, const void* manning) {
     if (!s || !states || !bed || !manning) return fail(HP_ERR_INVALID, "null argument");
+    std::lock_guard<std::recursive_mutex> lock__(s->mu);
     HP_CUDA(cudaSetDevice(s->ex->device));
     const hp::Grid& g = s->grid;
     const size_t w = static_cast<size_t>(g.cols) * s->rb, dp = static_cast<size_t>(g.pitch) * s->rb;
@@ -577,12 +611,14 @@ int hp_scheme_upload_cells(hp_scheme* s, const void* states, const void* bed, co
 
 int hp_scheme_download_cells(hp_scheme* s, void* states) {
     if (!s || !states) return fail(HP_ERR_INVALID, "null argument");
+    std::lock_guard<std::recursive_mutex> lock__(s->mu);
     HP_CUDA(cudaSetDevice(s->ex->device));
     return rows_to_host(s, src_planes(s, s->use_alt), states, 0, s->grid.rows);
 }
 
 int hp_scheme_download_both(hp_scheme* s, void* a, void* b) {
     if (!s || !a || !b) return fail(HP_ERR_INVALID, "null argument");
+    std::lock_guard<std::recursive_mutex> lock__(s->mu);
     HP_CUDA(cudaSetDevice(s->ex->device));
     int rc = rows_to_host(s, s->A, a, 0, s->grid.rows);
     if (rc) return rc;
@@ -591,6 +627,7 @@ int hp_scheme_download_both(hp_scheme* s, void* a, void* b) {
 
 int hp_scheme_read_rows(hp_scheme* s, uint64_t first_row, uint64_t row_count, void* states) {
     if (!s || !states) return fail(HP_ERR_INVALID, "null argument");
+    std::lock_guard<std::recursive_mutex> lock__(s->mu);
     if (first_row + row_count > static_cast<uint64_t>(s->grid.rows)) return fail(HP_ERR_INVALID, "row range outside the scheme");
     HP_CUDA(cudaSetDevice(s->ex->device));
     return rows_to_host(s, src_planes(s, s->use_alt), states, static_cast<int>(first_row), static_cast<int>(row_count));
@@ -598,6 +635,7 @@ int hp_scheme_read_rows(hp_scheme* s, uint64_t first_row, uint64_t row_count, vo
 
 int hp_scheme_write_rows(hp_scheme* s, uint64_t first_row, uint64_t row_count, const void* states) {
     if (!s || !states) return fail(HP_ERR_INVALID, "null argument");
+    std::lock_guard<std::recursive_mutex> lock__(s->mu);
     if (first_row + row_count > static_cast<uint64_t>(s->grid.rows)) return fail(HP_ERR_INVALID, "row range outside the scheme");
     HP_CUDA(cudaSetDevice(s->ex->device));
     return rows_to_device(s, states, static_cast<int>(first_row), static_cast<int>(row_count), false);
@@ -605,6 +643,7 @@ int hp_scheme_write_rows(hp_scheme* s, uint64_t first_row, uint64_t row_count, c
 
 int hp_scheme_derive_raster(hp_scheme* s, uint32_t value, double nodata, double* out) {
     if (!s || !out) return fail(HP_ERR_INVALID, "null argument");
+    std::lock_guard<std::recursive_mutex> lock__(s->mu);
     if (value > 11u) return fail(HP_ERR_INVALID, "unknown raster value code %u", value);
     HP_CUDA(cudaSetDevice(s->ex->device));
     const hp::Grid& g = s->grid;
@@ -626,14 +665,17 @@ int hp_scheme_derive_raster(hp_scheme* s, uint32_t value, double nodata, double*
 
 int hp_scheme_set_target_time(hp_scheme* s, double target) {
     if (!s) return fail(HP_ERR_INVALID, "scheme is null");
+    std::lock_guard<std::recursive_mutex> lock__(s->mu);
     return write_clock_field(s, 3, target);
 }
 int hp_scheme_force_timestep(hp_scheme* s, double timestep) {
     if (!s) return fail(HP_ERR_INVALID, "scheme is null");
+    std::lock_guard<std::recursive_mutex> lock__(s->mu);
     return write_clock_field(s, 1, timestep);
 }
 int hp_scheme_set_clock(hp_scheme* s, double time, double timestep, double th) {
     if (!s) return fail(HP_ERR_INVALID, "scheme is null");
+    std::lock_guard<std::recursive_mutex> lock__(s->mu);
     int rc = write_clock_field(s, 0, time);
     if (!rc) rc = write_clock_field(s, 1, timestep);
     if (!rc) rc = write_clock_field(s, 2, th);
@@ -642,6 +684,7 @@ int hp_scheme_set_clock(hp_scheme* s, double time, double timestep, double th) {
 
 int hp_scheme_update_timestep(hp_scheme* s) {
     if (!s) return fail(HP_ERR_INVALID, "scheme is null");
+    std::lock_guard<std::recursive_mutex> lock__(s->mu);
     HP_CUDA(cudaSetDevice(s->ex->device));
     // the reference's reduction kernel stays bound to "Cell states" (Q1); for MUSCL-Hancock that
     // buffer is the only one.  Here MUSCL-Hancock ping-pongs, so read the current buffer.
@@ -657,23 +700,45 @@ int hp_scheme_update_timestep(hp_scheme* s) {
 
 int hp_scheme_reset_counters(hp_scheme* s) {
     if (!s) return fail(HP_ERR_INVALID, "scheme is null");
+    std::lock_guard<std::recursive_mutex> lock__(s->mu);
     int rc = write_clock_field(s, 4, 0.0);
     if (rc) return rc;
     HP_CUDA(cudaMemsetAsync(static_cast<char*>(s->clock) + 5 * s->rb, 0, 2 * sizeof(unsigned int), s->ex->stream));
     return HP_OK;
 }
 
+// With a communicator the halo send/recv, the all-reduce and the fork/join onto the communication stream are
+// captured too (NCCL records its kernels into the graph), so a strip costs one graph launch per 16 iterations.
+// Measured on 4 GPUs: that pays on small strips (4096 x 4096: +1.5 %), but a captured exchange no longer overlaps
+// the interior kernel of a large strip (32768 x 4096: 2.74 ms per step against 2.38 ms launched directly), so
+// large strips are launched directly -- their launch latency is hidden anyway.  `small_strip` is the same on every
+// rank (hp_scheme_attach_comm), so all ranks issue the same NCCL sequence.
+static bool uses_graphs(const hp_scheme* s) {
+    return !(s->cfg.options & HP_OPT_NO_GRAPH) && !s->strip_timing && (s->comm == nullptr || s->small_strip);
+}
+
+int hp_scheme_prepare_graphs(hp_scheme* s) {
+    if (!s) return fail(HP_ERR_INVALID, "scheme is null");
+    std::lock_guard<std::recursive_mutex> lock__(s->mu);
+    HP_CUDA(cudaSetDevice(s->ex->device));
+    if (!uses_graphs(s)) return HP_OK;
+    for (int slot = 0; slot < 2; ++slot) {
+        if (s->graph_exec[slot]) continue;
+        const int rc = build_graph(s, slot, slot == 1 ? kGraphPairs : 1);
+        if (rc != HP_OK) return rc;
+        // upload the executable graph now, so that its first launch does not pay for it either
+        HP_CUDA(cudaGraphUpload(s->graph_exec[slot], s->ex->stream));
+    }
+    HP_CUDA(cudaStreamSynchronize(s->ex->stream));
+    return HP_OK;
+}
+
 int hp_scheme_iterate(hp_scheme* s, uint32_t iterations) {
     if (!s) return fail(HP_ERR_INVALID, "scheme is null");
+    std::lock_guard<std::recursive_mutex> lock__(s->mu);
     HP_CUDA(cudaSetDevice(s->ex->device));
     uint32_t left = iterations;
-    // with a communicator the halo send/recv, the all-reduce and the fork/join onto the communication stream are
-    // captured too (NCCL records its kernels into the graph), so a strip costs one graph launch per 16 iterations.
-    // Measured on 4 GPUs: that pays on small strips (4096 x 4096: +1.5 %), but a captured exchange no longer overlaps
-    // the interior kernel of a large strip (32768 x 4096: 2.74 ms per step against 2.38 ms launched directly), so
-    // large strips are launched directly -- their launch latency is hidden anyway.
-    const bool small_strip = static_cast<long long>(s->grid.rows) * s->grid.cols <= kSmallStripCells;
-    const bool use_graph = !(s->cfg.options & HP_OPT_NO_GRAPH) && (s->comm == nullptr || small_strip);
+    const bool use_graph = uses_graphs(s);
     int rc = HP_OK;
     auto direct = [&]() {
         int launched = 0;
@@ -686,6 +751,8 @@ int hp_scheme_iterate(hp_scheme* s, uint32_t iterations) {
         for (int slot = 1; slot >= 0; --slot) {
             const uint32_t per = 2u * (slot == 1 ? kGraphPairs : 1);
             if (left < per) continue;
+            // built on first use unless hp_scheme_prepare_graphs did it (boundaries and the communicator must be attached
+            // before: adding either drops the graphs)
             if (!s->graph_exec[slot] && (rc = build_graph(s, slot, static_cast<int>(per / 2))) != HP_OK) return rc;
             while (left >= per) {
                 HP_CUDA(cudaGraphLaunch(s->graph_exec[slot], s->ex->stream));
@@ -699,6 +766,8 @@ int hp_scheme_iterate(hp_scheme* s, uint32_t iterations) {
 
 int hp_scheme_sync(hp_scheme* s) {
     if (!s) return fail(HP_ERR_INVALID, "scheme is null");
+    // blocks WITHOUT the handle's lock (the stream handle never changes): the reference's main thread waits here
+    // while its worker thread goes on enqueueing (src/Schemes/CSchemeGodunov.cpp:1116-1141)
     HP_CUDA(cudaStreamSynchronize(s->ex->stream));
     HP_CUDA(cudaGetLastError());
     return HP_OK;
@@ -706,6 +775,7 @@ int hp_scheme_sync(hp_scheme* s) {
 
 int hp_scheme_read_stats(hp_scheme* s, hp_scheme_stats* out) {
     if (!s || !out) return fail(HP_ERR_INVALID, "null argument");
+    std::lock_guard<std::recursive_mutex> lock__(s->mu);
     HP_CUDA(cudaSetDevice(s->ex->device));
     char buf[64];
     HP_CUDA(cudaMemcpyAsync(buf, s->clock, 64, cudaMemcpyDeviceToHost, s->ex->stream));
@@ -732,17 +802,55 @@ int hp_comm_unique_id(void* id_out) {
 
 int hp_scheme_attach_comm(hp_scheme* s, const void* id, int rank, int world_size) {
     if (!s || !id) return fail(HP_ERR_INVALID, "null argument");
+    std::lock_guard<std::recursive_mutex> lock__(s->mu);
     if (world_size < 1 || rank < 0 || rank >= world_size) return fail(HP_ERR_INVALID, "bad rank/world size");
+    if (s->comm) return fail(HP_ERR_INVALID, "a communicator is already attached");
     HP_CUDA(cudaSetDevice(s->ex->device));
     if (world_size == 1) return HP_OK;
+    // Which iteration shape a strip runs (one launch + one NCCL group, or edges / exchange / interior) decides the ORDER
+    // of its NCCL calls, so every rank must decide alike: from the largest strip of an even split of the global rows,
+    // never from the local row count (edge strips hold one halo, inner strips two, the first strips one row more).
+    const long long halo = s->cfg.scheme == HP_SCHEME_MUSCL_HANCOCK ? 2 : 1;
+    const long long most_rows = (static_cast<long long>(s->cfg.global_rows) + world_size - 1) / world_size + 2 * halo;
+    long long small_cells = kSmallStripCells;
+    if (const char* t = getenv("HIPIMS_SMALL_STRIP_CELLS")) small_cells = atoll(t);    // test hook (tests/test_multigpu.py)
+    s->small_strip = most_rows * s->grid.cols <= small_cells;
+    s->world = world_size;
     const char* err = hp::comm_create(&s->comm, id, rank, world_size);
     if (err) return fail(HP_ERR_NCCL, "%s", err);
-    HP_CUDA(cudaStreamCreateWithFlags(&s->comm_stream, cudaStreamNonBlocking));
-    HP_CUDA(cudaEventCreateWithFlags(&s->ev_edges, cudaEventDisableTiming));
-    HP_CUDA(cudaEventCreateWithFlags(&s->ev_halo, cudaEventDisableTiming));
-    if (const char* t = getenv("HIPIMS_STRIP_TIMING")) s->strip_timing = t[0] == '1';
-    if (s->strip_timing) for (auto& e : s->ev_t) HP_CUDA(cudaEventCreate(&e));
+    cudaError_t e = cudaStreamCreateWithFlags(&s->comm_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_edges, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_halo, cudaEventDisableTiming);
+    for (auto& ev : s->ev_t) if (e == cudaSuccess) e = cudaEventCreate(&ev);
+    if (e != cudaSuccess) {
+        // leave no half-attached communicator behind
+        hp::comm_destroy(s->comm); s->comm = nullptr; s->world = 1;
+        if (s->comm_stream) { cudaStreamDestroy(s->comm_stream); s->comm_stream = nullptr; }
+        if (s->ev_edges) { cudaEventDestroy(s->ev_edges); s->ev_edges = nullptr; }
+        if (s->ev_halo) { cudaEventDestroy(s->ev_halo); s->ev_halo = nullptr; }
+        for (auto& ev : s->ev_t) if (ev) { cudaEventDestroy(ev); ev = nullptr; }
+        return fail(HP_ERR_CUDA, "attaching the communicator failed: %s", cudaGetErrorString(e));
+    }
     drop_graphs(s);
+    return HP_OK;
+}
+
+int hp_scheme_strip_timing(hp_scheme* s, int enable) {
+    if (!s) return fail(HP_ERR_INVALID, "scheme is null");
+    std::lock_guard<std::recursive_mutex> lock__(s->mu);
+    if (!s->comm) return fail(HP_ERR_INVALID, "strip timing needs an attached communicator");
+    HP_CUDA(cudaStreamSynchronize(s->ex->stream));
+    s->strip_timing = enable != 0;
+    for (double& t : s->t_phase) t = 0.0;
+    s->t_count = 0;
+    return HP_OK;
+}
+
+int hp_scheme_read_strip_phases(hp_scheme* s, double* ms_per_iteration, uint64_t* iterations) {
+    if (!s || !ms_per_iteration || !iterations) return fail(HP_ERR_INVALID, "null argument");
+    std::lock_guard<std::recursive_mutex> lock__(s->mu);
+    *iterations = s->t_count;
+    for (int i = 0; i < HP_STRIP_PHASES; ++i) ms_per_iteration[i] = s->t_count ? s->t_phase[i] / static_cast<double>(s->t_count) : 0.0;
     return HP_OK;
 }
 

@@ -265,7 +265,10 @@ template <class R> __global__ void __launch_bounds__(256) bdy_uniform_kernel(con
     const R acc = ck.time_hydro;
     if (acc < R(1.0) || ck.timestep <= R(0)) return;                       // CLBoundaries.clc:165-166
     if (ck.time >= static_cast<R>(a.length)) return;                       // :168
-    const unsigned long long step = static_cast<unsigned long long>(hp_floor(ck.time / static_cast<R>(a.interval)));
+    unsigned long long step = static_cast<unsigned long long>(hp_floor(ck.time / static_cast<R>(a.interval)));
+    // the reference trusts TimeseriesLength <= (entries - 1) * interval (only true for evenly spaced series) and reads
+    // past its buffer otherwise; stay inside the series instead
+    if (step >= a.entries) step = a.entries - 1;
     const R rate = static_cast<const R*>(a.series)[2 * step + 1];          // :172-173
     const Grid g = a.grid;
     R* __restrict__ eta = static_cast<R*>(a.state.eta);
@@ -324,7 +327,8 @@ template <class R> __global__ void __launch_bounds__(128) bdy_cell_kernel(const 
     const R t = ck.time, dt = ck.timestep;
     if (t >= static_cast<R>(a.length) || dt <= R(0)) return;              // CLBoundaries.clc:40-41
     const R interval = static_cast<R>(a.interval);
-    const unsigned long long base = static_cast<unsigned long long>(hp_floor(t / interval));   // :43-44
+    unsigned long long base = static_cast<unsigned long long>(hp_floor(t / interval));         // :43-44
+    if (base >= a.entries) base = a.entries - 1;   // unevenly spaced series: stay inside the buffer (entry `entries` is zero padding)
     const R* __restrict__ ts = static_cast<const R*>(a.series);
     const R w = hp_fmod(t, interval) / interval;                           // :52
     const R tsDepth = ts[4 * base + 1] + (ts[4 * base + 5] - ts[4 * base + 1]) * w;

@@ -92,11 +92,16 @@ ABI = {
     "hp_scheme_update_timestep": (C.c_int, [_VP]),
     "hp_scheme_reset_counters": (C.c_int, [_VP]),
     "hp_scheme_iterate": (C.c_int, [_VP, C.c_uint32]),
+    "hp_scheme_prepare_graphs": (C.c_int, [_VP]),
     "hp_scheme_sync": (C.c_int, [_VP]),
     "hp_scheme_read_stats": (C.c_int, [_VP, C.POINTER(HpSchemeStats)]),
     "hp_comm_unique_id": (C.c_int, [_VP]),
     "hp_scheme_attach_comm": (C.c_int, [_VP, _VP, C.c_int, C.c_int]),
+    "hp_scheme_strip_timing": (C.c_int, [_VP, C.c_int]),
+    "hp_scheme_read_strip_phases": (C.c_int, [_VP, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
 }
+
+STRIP_PHASES = ("edge_rows", "interior_rows", "halo_wait", "allreduce", "clock")
 
 _lib = None
 
@@ -302,6 +307,10 @@ class CudaScheme:
         if sync:
             self.sync()
 
+    def prepare_graphs(self):
+        """Builds the CUDA graphs iterate() replays (collective when a communicator is attached)."""
+        _check(self.lib.hp_scheme_prepare_graphs(self.h))
+
     def sync(self):
         _check(self.lib.hp_scheme_sync(self.h))
 
@@ -309,6 +318,17 @@ class CudaScheme:
     def attach_comm(self, unique_id, rank, world_size):
         buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id))
         _check(self.lib.hp_scheme_attach_comm(self.h, C.cast(buf, _VP), int(rank), int(world_size)))
+
+
+    def strip_timing(self, enable=True):
+        _check(self.lib.hp_scheme_strip_timing(self.h, int(bool(enable))))
+
+    def strip_phases(self):
+        """{phase: ms per iteration} accumulated since strip_timing(True), and the iteration count."""
+        ms = (C.c_double * len(STRIP_PHASES))()
+        n = C.c_uint64(0)
+        _check(self.lib.hp_scheme_read_strip_phases(self.h, ms, C.byref(n)))
+        return dict(zip(STRIP_PHASES, [float(v) for v in ms])), int(n.value)
 
 
 def comm_unique_id():

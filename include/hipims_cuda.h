@@ -23,7 +23,11 @@
  *     src/OpenCL/Executors/COCLProgram.cpp:381-399).  On the device the library keeps
  *     structure-of-arrays planes; the conversion happens inside upload/download.
  *   - all work of one scheme is issued on one CUDA stream; calls are asynchronous unless stated.
- *     A handle must not be used from two threads at once.
+ *   - handles are thread safe: every entry point takes a per-handle lock, so the reference's pattern -- the main
+ *     thread polls hp_scheme_read_stats / reads cells back while the scheme's worker thread enqueues batches
+ *     (src/Schemes/CSchemeGodunov.cpp:1116-1141, src/Schemes/CScheme.h:137-139) -- is safe; calls on one handle are
+ *     serialised in arrival order.  hp_scheme_sync and hp_executor_finish block WITHOUT the lock.  Destroying a
+ *     handle while another thread still uses it is the caller's error, as with any C handle.
  *   - there is NO CPU fallback: without a CUDA device every call fails with HP_ERR_NO_DEVICE.
  */
 #ifndef HIPIMS_CUDA_H
@@ -36,7 +40,7 @@
 extern "C" {
 #endif
 
-#define HP_ABI_VERSION 1
+#define HP_ABI_VERSION 2
 
 typedef enum hp_status {
     HP_OK = 0,
@@ -234,6 +238,13 @@ int  hp_scheme_reset_counters(hp_scheme* s);
  * the ping-pong toggle of Threaded_runBatch (src/Schemes/CSchemeGodunov.cpp:1287-1301).
  * Asynchronous; the timestep never leaves the device. */
 int  hp_scheme_iterate(hp_scheme* s, uint32_t iterations);
+/* Builds (and uploads) the CUDA graphs hp_scheme_iterate replays -- 16 iterations and 2 iterations, with the NCCL
+ * halo exchange and all-reduce captured inside when a communicator is attached -- so that the first batch does not
+ * pay for capture and instantiation.  The analogue of the reference preparing its kernels and their arguments once
+ * in prepare1OKernels / prepareGeneralKernels (src/Schemes/CSchemeGodunov.cpp:895-988) instead of on the first
+ * iteration.  Call after the boundaries and the communicator are attached (adding either drops the graphs);
+ * collective when a communicator is attached (every rank must call it).  Synchronous. */
+int  hp_scheme_prepare_graphs(hp_scheme* s);
 /* clFlush + clFinish of the batch (src/Schemes/CSchemeGodunov.cpp:1337-1341) */
 int  hp_scheme_sync(hp_scheme* s);
 /* CSchemeGodunov::readKeyStatistics (src/Schemes/CSchemeGodunov.cpp:1817-1850). Synchronous. */
@@ -249,6 +260,15 @@ int  hp_scheme_read_stats(hp_scheme* s, hp_scheme_stats* out);
 #define HP_COMM_ID_BYTES 128
 int  hp_comm_unique_id(void* id_out);
 int  hp_scheme_attach_comm(hp_scheme* s, const void* id, int rank, int world_size);
+/* Per-phase device times of the strip iteration, the counterpart of the reference's per-domain wall-clock log lines
+ * around its exchange (src/CModel.cpp:843-958).  While enabled, iterations are launched directly (no graph replay)
+ * with CUDA events between the phases and one host synchronisation per iteration: a diagnostic mode, not a fast one.
+ * Phases: 0 edge rows, 1 interior rows (the whole step on small strips), 2 wait for the halo exchange that ran beside
+ * the interior rows, 3 all-reduce of the wave speed (on small strips: halo exchange + all-reduce in one NCCL group),
+ * 4 time controller.  hp_scheme_strip_timing(s, 1) also clears the accumulated times; collective like iterate. */
+#define HP_STRIP_PHASES 5
+int  hp_scheme_strip_timing(hp_scheme* s, int enable);
+int  hp_scheme_read_strip_phases(hp_scheme* s, double* ms_per_iteration /* [HP_STRIP_PHASES] */, uint64_t* iterations);
 
 #ifdef __cplusplus
 }

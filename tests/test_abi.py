@@ -33,7 +33,7 @@ def test_header_and_binding_agree(lib):
 
 
 def test_abi_version_and_struct_sizes(lib):
-    assert lib.hp_abi_version() == 1
+    assert lib.hp_abi_version() == 2
     assert C.sizeof(hx.HpSchemeConfig) == 120
     assert C.sizeof(hx.HpSchemeStats) == 72
     assert C.sizeof(hx.HpBdyUniform) == 24 and C.sizeof(hx.HpBdyGridded) == 64 and C.sizeof(hx.HpBdyCell) == 40

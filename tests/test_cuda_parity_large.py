@@ -1,0 +1,150 @@
+"""Oracle parity of the DEFAULT fast kernels at sizes where their persistent loops wrap.
+
+The marching kernels (MUSCL-Hancock, inertial, Godunov-march) deal `march_runs` interleaved runs of rows to every
+CTA once a CTA has >= 128 (strip group, row) units (hp_march_kernels.cuh: march_runs): ring slots, mbarrier phases
+and the carried row state then cross run boundaries.  The Godunov tile kernel re-arms its mbarrier and re-issues its
+TMA boxes once there are more tiles than resident CTAs (6 x 148 in fp64, 9 x 148 in fp32).  The small parity cases
+(<= 160 x 160) never reach either path; every number bench.py quotes comes from them.  Here the bench's own
+workload generators (BASELINE configs[1], [2], [4], cropped) run 12 iterations against the CPU oracle
+(src/Schemes/CLSchemeMUSCLHancock.clc:533-801, CLSchemeInertial.clc:27-163, CLSchemeGodunov.clc:164-384 restated),
+with the north-star tolerances, identical wet-cell and timestep counts.
+"""
+import numpy as np
+import pytest
+
+import bench
+from hipims_ocl_b200 import config as hc
+from hipims_ocl_b200 import executor as hx
+from oracle import cpu_sim
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"double": 1e-9, "single": 1e-4}
+
+
+@pytest.fixture(scope="module")
+def ex():
+    e = hx.Executor(0)
+    yield e
+    e.close()
+
+
+def crop(workload, rows, cols):
+    w = dict(bench.WORKLOADS[workload])
+    w.update(cols=cols, rows_per_gpu=rows)
+    return w
+
+
+def run_both(ex, w, rows, cols, iters, options=0, warm_time=None):
+    cfg = bench.cfg_for(w, rows, cols)
+    dtype = np.float64 if cfg.precision == "double" else np.float32
+    bed, st, man = bench.make_inputs(w, rows, cols, dtype)
+    orc = cpu_sim.CpuSim("oracle", cfg)
+    gpu = hx.CudaScheme(ex, cfg, options=options)
+    for sim in (orc, gpu):
+        sim.upload(st, bed, man)
+        bench.attach_boundaries(sim, w, cols, rows)
+        sim.set_target(1.0e7)
+        if warm_time is not None:               # start inside the forcing series (rain falling, river flowing), with the
+            sim.set_clock(warm_time, cfg.initial_dt, 0.97)   # hydrological accumulator about to fire
+        sim.iterate(iters)
+    return cfg, orc, gpu, bed, st
+
+
+def check(cfg, orc, gpu, bed, st, iters):
+    so, sg = orc.stats(), gpu.stats()
+    assert sg["batch_successful"] == so["batch_successful"] == iters
+    assert sg["batch_skipped"] == so["batch_skipped"]
+    rel = 1e-9 if cfg.precision == "double" else 1e-4
+    assert abs(sg["time"] - so["time"]) <= rel * max(1.0, abs(so["time"]))
+    assert abs(sg["timestep"] - so["timestep"]) <= rel * max(1.0, abs(so["timestep"]))
+    cur_o, cur_g = orc.download(), gpu.download()
+    tol = TOL[cfg.precision]
+    assert np.isfinite(cur_g).all()
+    assert not np.array_equal(cur_o[..., 0], st[..., 0])          # the run did something
+    assert np.abs(cur_g[..., 0] - cur_o[..., 0]).max() <= tol
+    assert np.abs(cur_g[..., 1] - cur_o[..., 1]).max() <= tol
+    assert np.abs(cur_g[..., 2:] - cur_o[..., 2:]).max() <= 100 * tol
+    wet_o = int(((cur_o[..., 0] - bed) > 1e-10).sum())
+    wet_g = int(((cur_g[..., 0] - bed) > 1e-10).sum())
+    assert wet_g == wet_o
+    vol_o = (cur_o[..., 0].astype(np.float64) - bed).sum()
+    vol_g = (cur_g[..., 0].astype(np.float64) - bed).sum()
+    assert abs(vol_g - vol_o) <= (1e-10 if cfg.precision == "double" else 1e-5) * max(1.0, abs(vol_o))
+    if cfg.scheme != hc.SCHEME_MUSCL_HANCOCK:                      # stale-destination rule
+        a_o, b_o = orc.download_both()
+        a_g, b_g = gpu.download_both()
+        oth_o, oth_g = (a_o, a_g) if so["use_alternate"] else (b_o, b_g)
+        assert np.abs(oth_g[..., 0] - oth_o[..., 0]).max() <= tol
+
+
+MARCH = hx.OPT_MARCH_GODUNOV
+
+# (workload, rows, cols, options, start time): rows x cols chosen so that march_runs >= 2 for that kernel's grid
+WRAP_CASES = [
+    pytest.param("dambreak4096-mh", 3072, 4096, 0, None, id="mh-f64-dambreak"),
+    pytest.param("dambreak4096-mh-f32", 3072, 4096, 0, None, id="mh-f32-dambreak"),
+    pytest.param("pluvial16384", 3072, 4096, 0, 100.0, id="mh-f64-pluvial-rain"),            # configs[2] cropped
+    pytest.param("river32768", 4096, 4096, 0, 700.0, id="mh-f64-river-cells"),                # configs[4] cropped
+    pytest.param("dambreak4096-inertial", 4096, 4096, 0, None, id="inertial-f64-dambreak"),
+    pytest.param("dambreak4096-inertial-f32", 4096, 4096, 0, None, id="inertial-f32-dambreak"),
+    pytest.param("dambreak4096", 3072, 4096, MARCH, None, id="godunov-march-f64-dambreak"),
+    pytest.param("dambreak4096-f32", 3072, 4096, MARCH, None, id="godunov-march-f32-dambreak"),
+    # the tile kernel: 1024 x 1536 = 32 x 192 = 6144 tiles > 888 (fp64) / 1332 (fp32) resident CTAs
+    pytest.param("dambreak4096", 1024, 1536, 0, None, id="godunov-tiles-f64-dambreak"),
+    pytest.param("dambreak4096-f32", 1024, 1536, 0, None, id="godunov-tiles-f32-dambreak"),
+    pytest.param("pluvial4096", 1024, 1536, 0, None, id="godunov-tiles-f64-pluvial"),
+]
+
+
+@pytest.mark.parametrize("workload,rows,cols,options,t0", WRAP_CASES)
+def test_wrapping_kernels_match_the_oracle(ex, workload, rows, cols, options, t0):
+    iters = 12
+    w = crop(workload, rows, cols)
+    cfg, orc, gpu, bed, st = run_both(ex, w, rows, cols, iters, options, warm_time=t0)
+    check(cfg, orc, gpu, bed, st, iters)
+    gpu.close()
+    orc.close()
+
+
+def test_march_runs_really_wrap():
+    """The sizes above put >= 128 units on every CTA of the marching kernels (the condition for march_runs >= 2)."""
+    def per_cta(rows, cols, use, ctas_per_sm):
+        nstrips = -(-cols // use)
+        ngroups = -(-nstrips // 4)
+        return ngroups * rows // (ctas_per_sm * 148)
+    assert per_cta(3072, 4096, 30, 4) >= 128      # MH / Godunov-march fp64
+    assert per_cta(3072, 4096, 28, 6) >= 128      # MH / Godunov-march fp32
+    assert per_cta(4096, 4096, 30, 6) >= 128      # inertial fp64
+    assert per_cta(4096, 4096, 28, 8) >= 128      # inertial fp32
+    assert (1024 // 8) * (1536 // 32) > 9 * 148   # Godunov tiles
+
+
+def test_configs3_combination(ex):
+    """BASELINE configs[3] in small: partial-inertial fp32 + spatially gridded rain + point volume sources
+    (CLSchemeInertial.clc:27-163 with bdy_Gridded CLBoundaries.clc:186-246 and bdy_Cell's volume branch :85-93)."""
+    rows = cols = 512
+    w = crop("radar16384", rows, cols)
+    w["boundaries"] = None
+    cfg = bench.cfg_for(w, rows, cols)
+    bed, st, man = bench.make_inputs(w, rows, cols, np.float32)
+    rng = np.random.default_rng(5)
+    frames = rng.uniform(0.0, 80.0, size=(6, rows // 32 + 1, cols // 32 + 1))
+    pts = sorted(set(int(y) * cols + int(x) for y, x in rng.integers(2, rows - 2, size=(64, 2))))
+    series = [[60.0 * i, 0.0, q, 0.0] for i, q in enumerate([0.0, 2.0, 1.0, 0.0, 0.0, 0.0])]
+    orc = cpu_sim.CpuSim("oracle", cfg)
+    gpu = hx.CudaScheme(ex, cfg)
+    iters = 150
+    for sim in (orc, gpu):
+        sim.upload(st, bed, man)
+        sim.add_gridded(hc.GRIDDED_RAIN_INTENSITY, 120.0, 32.0, 0.0, 0.0, frames)
+        sim.add_cell(hc.DEPTH_IGNORE, hc.DISCHARGE_IS_VOLUME, pts, series)
+        sim.set_target(1.0e7)
+        sim.set_clock(30.0, cfg.initial_dt, 0.97)
+        sim.iterate(iters)
+    check(cfg, orc, gpu, bed, st, iters)
+    # the sources really fired: water appeared at the surcharging cells and rain fell
+    out = gpu.download()
+    assert (out[..., 0].astype(np.float64) - bed).sum() > (st[..., 0].astype(np.float64) - bed).sum()
+    gpu.close()
+    orc.close()

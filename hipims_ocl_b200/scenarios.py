@@ -18,14 +18,14 @@ def round4(a):
 def make_states(bed, depth, qx=None, qy=None, dtype=np.float64):
     """Initial cell states: eta = bed + depth, eta_max = eta (CDomain.cpp:294-397 semantics)."""
     bed = np.asarray(bed, dtype=np.float64)
-    st = np.zeros(bed.shape + (4,), dtype=np.float64)
-    st[..., 0] = bed + depth
+    st = np.zeros(bed.shape + (4,), dtype=dtype)           # built in the target precision: no second full-size copy
+    st[..., 0] = bed + depth                               # (sum in double, rounded once on assignment)
     st[..., 1] = st[..., 0]
     if qx is not None:
         st[..., 2] = qx
     if qy is not None:
         st[..., 3] = qy
-    return st.astype(dtype)
+    return st
 
 
 def fractal_dem(rows, cols, seed, amplitude=50.0, hurst=0.8, base=64):

@@ -84,7 +84,7 @@ MARCH = hx.OPT_MARCH_GODUNOV
 WRAP_CASES = [
     pytest.param("dambreak4096-mh", 3072, 4096, 0, None, id="mh-f64-dambreak"),
     pytest.param("dambreak4096-mh-f32", 3072, 4096, 0, None, id="mh-f32-dambreak"),
-    pytest.param("pluvial16384", 3072, 4096, 0, 100.0, id="mh-f64-pluvial-rain"),            # configs[2] cropped
+    pytest.param("pluvial16384", 3072, 4096, 0, None, id="mh-f64-pluvial"),                   # configs[2] cropped
     pytest.param("river32768", 4096, 4096, 0, 700.0, id="mh-f64-river-cells"),                # configs[4] cropped
     pytest.param("dambreak4096-inertial", 4096, 4096, 0, None, id="inertial-f64-dambreak"),
     pytest.param("dambreak4096-inertial-f32", 4096, 4096, 0, None, id="inertial-f32-dambreak"),
@@ -105,6 +105,35 @@ def test_wrapping_kernels_match_the_oracle(ex, workload, rows, cols, options, t0
     check(cfg, orc, gpu, bed, st, iters)
     gpu.close()
     orc.close()
+
+
+def test_rain_film_deviation_is_that_of_a_bit_faithful_run(ex):
+    """configs[2] cropped, with the rain firing in the first iteration (hydrological accumulator at 0.97 s): every dry
+    cell gets a 1.4e-5 m film, right above the scheme's `h < 1e-5 => first order` switch.  From there on NO implementation
+    that does not share the reference's pow() bit for bit can stay within 1e-9 m: the strict flavour (reference operation
+    order, IEEE division and roots, bit-identical to the oracle wherever pow() is not involved) is 7e-9 away after two
+    more iterations and 3e-8 after twelve (tools/diag_large.py).  So the bar for the fast kernels here is the deviation
+    of that bit-faithful witness: same order of magnitude, identical timestep, wet-cell count and volume."""
+    rows, cols, iters = 3072, 4096, 12
+    w = crop("pluvial16384", rows, cols)
+    cfg, orc, fast, bed, st = run_both(ex, w, rows, cols, iters, 0, warm_time=100.0)
+    want = orc.download()
+    got = fast.download()
+    so, sg = orc.stats(), fast.stats()
+    fast.close()
+    cfg2, orc2, strict, _, _ = run_both(ex, w, rows, cols, iters, hx.OPT_STRICT_FP, warm_time=100.0)
+    witness = strict.download()
+    strict.close(); orc2.close(); orc.close()
+    dev_fast = np.abs(got[..., 0] - want[..., 0]).max()
+    dev_witness = np.abs(witness[..., 0] - want[..., 0]).max()
+    assert (want[..., 0] - st[..., 0]).min() > 1.0e-5                       # it rained on every cell
+    assert dev_witness > 1e-9                                               # the premise: even the witness is off
+    assert dev_fast <= 3.0 * dev_witness and dev_fast <= 1e-6
+    assert sg["batch_successful"] == so["batch_successful"] == iters
+    assert abs(sg["timestep"] - so["timestep"]) <= 1e-9 * so["timestep"]
+    assert int(((got[..., 0] - bed) > 1e-10).sum()) == int(((want[..., 0] - bed) > 1e-10).sum())
+    vol_o, vol_g = (want[..., 0] - bed).sum(), (got[..., 0] - bed).sum()
+    assert abs(vol_g - vol_o) <= 1e-10 * vol_o
 
 
 def test_march_runs_really_wrap():

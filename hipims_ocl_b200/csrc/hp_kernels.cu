@@ -446,6 +446,7 @@ template <class R> __global__ void __launch_bounds__(256) derive_raster_kernel(P
 #ifndef HP_FLAVOUR_STRICT
 #include "hp_fast_kernels.cuh"
 #include "hp_march_kernels.cuh"
+#include "hp_march_mh.cuh"
 #endif
 
 namespace HP_NS {
@@ -467,7 +468,7 @@ static_assert(sizeof(TmaBlockMap) == sizeof(hp::TmaMaps6POD), "descriptor block 
 static int launch_step_march(int scheme, int real_bytes, const StepArgs& a, const hp::TmaMaps6POD* maps, int alt, int sm_count, cudaStream_t st) {
     const TmaBlockMap& m = *reinterpret_cast<const TmaBlockMap*>(maps);
     if (scheme == 0) return real_bytes == 8 ? launch_godunov_march<double>(a, m, alt, sm_count, st) : launch_godunov_march<float>(a, m, alt, sm_count, st);
-    if (scheme == 1) return real_bytes == 8 ? launch_mh_march<double>(a, m, alt, sm_count, st) : launch_mh_march<float>(a, m, alt, sm_count, st);
+    if (scheme == 1) return real_bytes == 8 ? launch_mh_march2<double>(a, m, alt, sm_count, st) : launch_mh_march2<float>(a, m, alt, sm_count, st);
     if (scheme == 2) return real_bytes == 8 ? launch_inertial_march<double>(a, m, alt, sm_count, st) : launch_inertial_march<float>(a, m, alt, sm_count, st);
     return -1;
 }

@@ -68,15 +68,58 @@ template <class R, int HALO, bool ALT, int RING = HP_MARCH_RR> struct March {
 // non-zero at a wet/dry front).  qOwnL / qOwnR: the owning CELLS' discharge normal to the face.
 template <class R> struct FaceOut { R m, n, t, zmax, hL, hR; int stopL, stopR; };
 
-template <class R>
-__device__ __forceinline__ void face_solve(const Params<R>& k, R etaL, R zL, R unL, R utL, R aL_cached, R etaR, R zR, R unR, R utR,
-                                           R aR_cached, const bool cached, R qOwnL, R qOwnR, FaceOut<R>& o) {
+// sqrt for a STRICTLY positive argument: no zero guard (rsqrt(0) = inf would give 0 * inf)
+__device__ __forceinline__ double fm_sqrt_pos(double a) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    double g = a * y;
+    const double h = 0.5 * y;
+    const double r = fma(-g, h, 0.5);
+    return fma(g, fma(1.5 * r, r, r), g);
+}
+__device__ __forceinline__ float fm_sqrt_pos(float a) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(a));
+    const float g = a * y, h = 0.5f * y;
+    return fmaf(fmaf(-g, g, a), h, g);
+}
+
+// One face in the normal frame, solved once for both cells: core flux (see face_core_flux), the common reconstructed
+// bed, both reconstructed depths and the stop-counter increments of the two owners (CLSchemeGodunov.clc:83-137 /
+// CLSchemeMUSCLHancock.clc:1172-1204; they can only be non-zero at a wet/dry front).  qOwnL / qOwnR: the owning CELLS'
+// discharge normal to the face.  WET FAST PATH in front: when both reconstructed depths exceed the dry threshold (one
+// combined test) there are no stop flags, no dry-side selects, no clamps and the square roots need no zero guard --
+// with identical results, the general path takes exactly these operations then.
+template <class R, bool CACHED>
+__device__ __forceinline__ void face_solve2(const Params<R>& k, R etaL, R zL, R unL, R utL, R aL_cached, R etaR, R zR, R unR, R utR,
+                                            R aR_cached, R qOwnL, R qOwnR, FaceOut<R>& o) {
     const R hg = R(0.5) * k.g;
     const R zmax = fm_max(zL, zR);
-    const R hL = fm_posdiff(etaL, zmax);
-    const R hR = fm_posdiff(etaR, zmax);
-    o.zmax = zmax; o.hL = hL; o.hR = hR; o.stopL = 0; o.stopR = 0;
-    if (hL <= k.eps || hR <= k.eps) {
+    const R dL = etaL - zmax, dR = etaR - zmax;
+    o.zmax = zmax;
+    if (dL > k.eps && dR > k.eps) {
+        o.hL = dL; o.hR = dR; o.stopL = 0; o.stopR = 0;
+        const R aL = (CACHED && zmax == zL) ? aL_cached : fm_sqrt_pos(k.g * dL);
+        const R aR = (CACHED && zmax == zR) ? aR_cached : fm_sqrt_pos(k.g * dR);
+        const R qnL = dL * unL, qnR = dR * unR;
+        const R as = hp_abs(R(0.5) * (aL + aR) + R(0.25) * (unL - unR));
+        const R us = R(0.5) * (unL + unR) + aL - aR;
+        const R sL = fm_min(unL - aL, us - as);
+        const R sR = fm_max(unR + aR, us + as);
+        const R FLn = unL * qnL + hg * dL * dL, FRn = unR * qnR + hg * dR * dR;
+        if (sL >= R(0)) { o.m = qnL; o.n = FLn; o.t = qnL * utL; return; }
+        if (!(sR >= R(0))) { o.m = qnR; o.n = FRn; o.t = qnR * utR; return; }
+        const R inv = fm_rcp(sR - sL);
+        const R ss = sL * sR;
+        const R f1 = (sR * qnL - sL * qnR + ss * (dR - dL)) * inv;
+        const R f2 = (sR * FLn - sL * FRn + ss * (qnR - qnL)) * inv;
+        o.m = f1; o.n = f2; o.t = f1 * (f1 >= R(0) ? utL : utR);
+        return;
+    }
+    // ---- general path: a dry side, stop flags (wet/dry fronts only) --------------------------------
+    const R hL = dL > R(0) ? dL : R(0), hR = dR > R(0) ? dR : R(0);
+    o.hL = hL; o.hR = hR;
+    {
         int both = 0;
         if (hR <= k.eps && unL < R(0)) ++both;
         if (hL <= k.eps && unR > R(0)) ++both;
@@ -91,8 +134,8 @@ __device__ __forceinline__ void face_solve(const Params<R>& k, R etaL, R zL, R u
     }
     if (dryL) { unL = R(0); utL = R(0); }
     if (dryR) { unR = R(0); utR = R(0); }
-    const R aL = (cached && zmax == zL) ? aL_cached : fm_sqrt(k.g * hL);
-    const R aR = (cached && zmax == zR) ? aR_cached : fm_sqrt(k.g * hR);
+    const R aL = (CACHED && zmax == zL) ? aL_cached : fm_sqrt(k.g * hL);
+    const R aR = (CACHED && zmax == zR) ? aR_cached : fm_sqrt(k.g * hR);
     const R qnL = hL * unL, qnR = hR * unR;
     const R as = hp_abs(R(0.5) * (aL + aR) + R(0.25) * (unL - unR));
     const R us = R(0.5) * (unL + unR) + aL - aR;
@@ -110,267 +153,6 @@ __device__ __forceinline__ void face_solve(const Params<R>& k, R etaL, R zL, R u
 
 template <class R> __device__ __forceinline__ R shfl_up1(R v) { return __shfl_up_sync(0xffffffffu, v, 1); }
 template <class R> __device__ __forceinline__ R shfl_dn1(R v) { return __shfl_down_sync(0xffffffffu, v, 1); }
-
-// =============================================================================================
-// MUSCL-Hancock, predictor + corrector fused, marching.
-// =============================================================================================
-template <class R, bool ALT>
-__global__ void __launch_bounds__(hp::kMarchWarps * 32, sizeof(R) == 8 ? 4 : 6)
-mh_step_march(const StepArgs a, const __grid_constant__ TmaBlockMap maps) {
-    // lane halo of ONE column per side: the raw values two columns out come from the TMA box, which is two columns
-    // wider than the warp (geometry of HALO = 1); only predictor values need a lane.  30 of 32 lanes update cells.
-    using T = March<R, 1, ALT, HP_MARCH_MH_RR>;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned char* const ring = smem_raw + warp * T::WARP_BYTES;
-    const uint32_t ring_u = smem_u32(ring);
-    const uint32_t bar_u = smem_u32(smem_raw + T::NW * T::WARP_BYTES) + warp * T::RR * 8;
-    if (lane == 0) {
-#pragma unroll
-        for (int r = 0; r < T::RR; ++r) mbar_init(bar_u + 8 * r, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
-
-    const Params<R> k = make_params<R>(a.params);
-    const Grid g = a.grid;
-    const R dt = read_timestep<R>(a.clock);
-    const R inv_delta = fm_rcp(k.delta);
-    const R hg = R(0.5) * k.g, half = R(0.5);
-    const MutView<R> d(a.dst);
-    const bool stepping = dt > R(0);
-
-    const int nrows = a.y1 - a.y0;
-    const int nstrips = (g.cols + T::USE - 1) / T::USE;
-    const int ngroups = (nstrips + T::NW - 1) / T::NW;
-    const long long units = static_cast<long long>(ngroups) * nrows;
-    // A CTA works on `march_runs` equal runs of units, taken round-robin from the whole domain (run r belongs to CTA
-    // r mod grid): every CTA gets the same amount of work AND a sample of the domain, so wet and dry regions even out.
-    const long long total_runs = static_cast<long long>(gridDim.x) * a.march_runs;
-    int run = 0;
-    long long u = units * blockIdx.x / total_runs, u1 = units * (blockIdx.x + 1) / total_runs;
-
-    // per-lane byte offsets of the own column and its clamped x-neighbours inside a plane row
-    const int lc = (lane + T::PADL) * int(sizeof(R));
-    const int lw = (lane - 1 + T::PADL) * int(sizeof(R)), le = (lane + 1 + T::PADL) * int(sizeof(R));   // PADL >= 1, BW >= 33 + PADL
-    static_assert(T::PADL >= 1 && T::BW >= 33 + T::PADL, "the box must hold one raw column beyond either edge lane");
-    auto ld = [&](int row_off, int plane, int col_off) -> R {
-        return *reinterpret_cast<const R*>(ring + row_off + plane * T::PLANE + col_off);
-    };
-    auto flags_of = [&](R em) -> int { return (em <= R(-9998.0) ? 1 : 0) | (em < k.eps ? 2 : 0); };
-
-    R ws = R(0);
-    uint32_t ph = 0;
-
-    for (;;) {
-        if (u >= u1) {
-            if (++run >= a.march_runs) break;
-            const long long r = static_cast<long long>(run) * gridDim.x + blockIdx.x;
-            u = units * r / total_runs; u1 = units * (r + 1) / total_runs;
-            continue;
-        }
-        const int grp = static_cast<int>(u / nrows);
-        const int ya = a.y0 + static_cast<int>(u - static_cast<long long>(grp) * nrows);
-        const long long gend = static_cast<long long>(grp + 1) * nrows;
-        const int yb = ya + static_cast<int>((u1 < gend ? u1 : gend) - u);
-        u += yb - ya;
-        const int strip = grp * T::NW + warp;
-        if (strip >= nstrips) continue;
-
-        const int X0 = strip * T::USE - 1;               // column of lane 0
-        const int x = X0 + lane;
-        const int rs = ya - 2;                            // first raw row of this run
-        const int J = yb - ya + 2;                        // raw rows 0 .. J+1, predictor rows 1 .. J
-        auto issue_row = [&](int j) {
-            const uint32_t bar = bar_u + 8 * (j & (T::RR - 1));
-            mbar_expect_tx(bar, uint32_t(T::ROW_TX));
-            tma_load_3d(ring_u + (j & (T::RR - 1)) * T::SLOT, &maps.block, X0 - T::PADL, rs + j, T::P0, bar);
-        };
-        auto wait_row = [&](int j) {
-            const int s = j & (T::RR - 1);
-            mbar_wait(bar_u + 8 * s, (ph >> s) & 1u);
-            ph ^= 1u << s;
-        };
-        // the previous run's rows are all consumed; order its generic reads before the async writes
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) {
-#pragma unroll
-            for (int j = 0; j < T::RR; ++j) if (j <= J + 1) issue_row(j);
-        }
-        wait_row(0);
-        wait_row(1);
-
-        // ---- state carried from row to row (registers) -------------------------------------------
-        int f_m2 = 0, f_m1 = flags_of(ld(0 * T::SLOT, T::P_EMAX, lc)), f_c = flags_of(ld(1 * T::SLOT, T::P_EMAX, lc));
-        int f_ew_prev = 0;                                   // bit1 flags of the x-neighbours of the previous row: W | E<<2
-        R pe = R(0), pqx = R(0), pqy = R(0), psxE = R(0), psxH = R(0), psxQx = R(0), psxQy = R(0);
-        R psyE = R(0), psyH = R(0), psyQx = R(0), psyQy = R(0), pzb = R(0);
-        R sM = R(0), sN = R(0), sT = R(0), sZ = R(0), sH = R(0);   // southern face of the previous row
-        int sStop = 0;
-        // Rows in which every lane is EXACTLY dry and at rest (eta == zb, q == 0, eta_max not below eta) -- most of a
-        // flood model's domain.  Such a cell falls back to first order with zero slopes, a face between two of them
-        // carries no flux at all, and a cell whose whole stencil is like that cannot change: the row is copied through
-        // (identical to what the full arithmetic produces, at a fraction of its instructions).
-        // Rows in which every lane is EXACTLY dry and at rest (eta == zb, q == 0, eta_max not below eta) -- most of a
-        // flood model's domain.  Such a cell falls back to first order with zero slopes, a face between two of them
-        // carries no flux at all, and a cell whose whole stencil is like that cannot change: the row is copied through
-        // (identical to what the full arithmetic produces, at a fraction of its instructions).
-        bool dr_m2 = false, dr_m1 = false, dr_c = false;       // rows j-2, j-1, j (warp-uniform)
-
-        for (int j = 1; j <= J; ++j) {
-            const int y = rs + j, gy = y + g.gy0;
-            const int o_m = ((j - 1) & (T::RR - 1)) * T::SLOT, o_c = (j & (T::RR - 1)) * T::SLOT,
-                      o_p = ((j + 1) & (T::RR - 1)) * T::SLOT;
-            wait_row(j + 1);
-            const int f_p = flags_of(ld(o_p, T::P_EMAX, lc));
-            int f_w = __shfl_up_sync(0xffffffffu, f_c, 1), f_e = __shfl_down_sync(0xffffffffu, f_c, 1);
-            if (lane == 0) f_w = flags_of(ld(o_c, T::P_EMAX, lw));          // the columns beyond the edge lanes have no lane
-            if (lane == 31) f_e = flags_of(ld(o_c, T::P_EMAX, le));
-
-            // ---- predictor of row y (CLSchemeMUSCLHancock.clc:301-382) ---------------------------
-            const R eta = ld(o_c, T::P_ETA, lc), qx = ld(o_c, T::P_QX, lc), qy = ld(o_c, T::P_QY, lc), zb = ld(o_c, T::P_ZB, lc);
-            // (tested on every fourth row, and on every row while the rows below are dry: wet regions pay almost nothing)
-            dr_c = false;
-            if (stepping && (dr_m1 || (j & 3) == 0))
-                dr_c = __all_sync(0xffffffffu, eta == zb && qx == R(0) && qy == R(0) && !(eta > ld(o_c, T::P_EMAX, lc)));
-            R ce = eta, cqx = qx, cqy = qy;
-            R sxE = R(0), sxH = R(0), sxQx = R(0), sxQy = R(0), syE = R(0), syH = R(0), syQx = R(0), syQy = R(0);
-            if (dr_m2 && dr_m1 && dr_c) {
-                // rows y-2, y-1, y exactly dry in every lane (so j >= 3): predictor = the raw state with zero slopes, the face
-                // (y-1 | y) carries nothing, the cell (x, y-1) cannot change
-                if (lane >= 1 && lane < 1 + T::USE && x < g.cols)
-                    d.store(static_cast<size_t>(y - 1) * g.pitch + x,
-                            Cell<R>{ld(o_m, T::P_ETA, lc), ld(o_m, T::P_EMAX, lc), ld(o_m, T::P_QX, lc), ld(o_m, T::P_QY, lc)});
-                sM = R(0); sN = R(0); sT = R(0); sZ = fm_max(pe, ce); sH = R(0); sStop = 0;
-            } else {
-                {
-                    const bool valid = stepping && x >= 1 && x <= g.cols - 2 && gy >= 1 && gy <= g.grows - 2 && y >= 1 && y <= g.rows - 2;
-                    const R h = eta - zb;
-                    if (valid && !(h < R(1E-5)) && !((f_p | f_e | f_m1 | f_w) & 1)) {
-                        const R etaE = ld(o_c, T::P_ETA, le), etaW = ld(o_c, T::P_ETA, lw), etaN = ld(o_p, T::P_ETA, lc), etaS = ld(o_m, T::P_ETA, lc);
-                        const R hE = etaE - ld(o_c, T::P_ZB, le), hW = etaW - ld(o_c, T::P_ZB, lw);
-                        const R hN = etaN - ld(o_p, T::P_ZB, lc), hS = etaS - ld(o_m, T::P_ZB, lc);
-                        if (!(hW < k.eps || hE < k.eps)) {
-                            sxE = minmod(eta - etaW, etaE - eta); sxH = minmod(h - hW, hE - h);
-                            sxQx = minmod(qx - ld(o_c, T::P_QX, lw), ld(o_c, T::P_QX, le) - qx);
-                            sxQy = minmod(qy - ld(o_c, T::P_QY, lw), ld(o_c, T::P_QY, le) - qy);
-                        }
-                        if (!(hS < k.eps || hN < k.eps)) {
-                            syE = minmod(eta - etaS, etaN - eta); syH = minmod(h - hS, hN - h);
-                            syQx = minmod(qx - ld(o_m, T::P_QX, lc), ld(o_p, T::P_QX, lc) - qx);
-                            syQy = minmod(qy - ld(o_m, T::P_QY, lc), ld(o_p, T::P_QY, lc) - qy);
-                        }
-                        const R hEf = h + half * sxH, hWf = h - half * sxH, hNf = h + half * syH, hSf = h - half * syH;
-                        const R qxE = qx + half * sxQx, qxW = qx - half * sxQx, qyE = qy + half * sxQy, qyW = qy - half * sxQy;
-                        const R qxN = qx + half * syQx, qxS = qx - half * syQx, qyN = qy + half * syQy, qyS = qy - half * syQy;
-                        const R uE = hEf < k.eps ? R(0) : qxE * fm_rcp(hEf), uW = hWf < k.eps ? R(0) : qxW * fm_rcp(hWf);
-                        const R vN = hNf < k.eps ? R(0) : qyN * fm_rcp(hNf), vS = hSf < k.eps ? R(0) : qyS * fm_rcp(hSf);
-                        R dEta = ((qxE - qxW) + (qyN - qyS)) * inv_delta;
-                        R dQx = (uE * qxE - uW * qxW + vN * qxN - vS * qxS + hg * sxE * (hEf + hWf)) * inv_delta;
-                        R dQy = (uE * qyE - uW * qyW + vN * qyN - vS * qyS + hg * syE * (hNf + hSf)) * inv_delta;
-                        dEta = fm_chop(dEta, k.eps); dQx = fm_chop(dQx, k.eps); dQy = fm_chop(dQy, k.eps);
-                        ce = eta - half * dt * dEta; cqx = qx - half * dt * dQx; cqy = qy - half * dt * dQy;
-                    }
-                }
-
-                if (stepping && j >= 2) {
-                    // ---- face between rows y-1 (left) and y (right); normal = y ----------------------
-                    FaceOut<R> fy;
-                    {
-                        const R etaL = pe + half * psyE, hfL = (pe - pzb) + half * psyH;
-                        const R qxL = pqx + half * psyQx, qyL = pqy + half * psyQy;
-                        const R etaR = ce - half * syE, hfR = (ce - zb) - half * syH;
-                        const R qxR = cqx - half * syQx, qyR = cqy - half * syQy;
-                        const R rL = hfL <= k.eps ? R(0) : fm_rcp(hfL), rR = hfR <= k.eps ? R(0) : fm_rcp(hfR);
-                        face_solve<R>(k, etaL, etaL - hfL, qyL * rL, qxL * rL, R(0), etaR, etaR - hfR, qyR * rR, qxR * rR, R(0), false,
-                                      ld(o_m, T::P_QY, lc), qy, fy);
-                    }
-                    if (j >= 3) {
-                        // ---- west face of row y-1: the east-side estimate of lane-1 against the own west side
-                        const R xe_eta = pe + half * psxE, xe_h = (pe - pzb) + half * psxH;
-                        const R xe_r = xe_h <= k.eps ? R(0) : fm_rcp(xe_h);
-                        const R xe_u = (pqx + half * psxQx) * xe_r, xe_v = (pqy + half * psxQy) * xe_r;
-                        const R etaL = shfl_up1(xe_eta), hfL = shfl_up1(xe_h), uL = shfl_up1(xe_u), vL = shfl_up1(xe_v);
-                        const R etaR = pe - half * psxE, hfR = (pe - pzb) - half * psxH;
-                        const R rR = hfR <= k.eps ? R(0) : fm_rcp(hfR);
-                        const R uR = (pqx - half * psxQx) * rR, vR = (pqy - half * psxQy) * rR;
-                        const R c_qx = ld(o_m, T::P_QX, lc);
-                        FaceOut<R> fx;
-                        face_solve<R>(k, etaL, etaL - hfL, uL, vL, R(0), etaR, etaR - hfR, uR, vR, R(0), false, ld(o_m, T::P_QX, lw), c_qx, fx);
-                        // the east face comes back from lane+1
-                        const R eM = shfl_dn1(fx.m), eN = shfl_dn1(fx.n), eT = shfl_dn1(fx.t), eZ = shfl_dn1(fx.zmax), eH = shfl_dn1(fx.hR);
-                        const int eStop = __shfl_down_sync(0xffffffffu, fx.stopL, 1);
-
-                        // ---- corrector of row y-1 (CLSchemeMUSCLHancock.clc:596-800) -----------------
-                        const int yc = y - 1, gyc = gy - 1;
-                        Cell<R> c{ld(o_m, T::P_ETA, lc), ld(o_m, T::P_EMAX, lc), c_qx, ld(o_m, T::P_QY, lc)};
-                        const bool interior = x >= 2 && x <= g.cols - 3 && gyc >= 2 && gyc <= g.grows - 3;   // ring of two is frozen
-                        if (interior && !(c.emax <= R(-9999.0) || c.eta == R(-9999.0))) {
-                            int dry = (c.eta - pzb < k.eps) ? 1 : 0;
-                            dry += (f_c >> 1) + (f_m2 >> 1) + (f_ew_prev & 1) + (f_ew_prev >> 2);
-                            if (dry < 5) {
-                                const R bN = fm_min(fy.zmax, pe + half * psyE), bS = fm_min(sZ, pe - half * psyE);
-                                const R bE = fm_min(eZ, pe + half * psxE), bW = fm_min(fx.zmax, pe - half * psxE);
-                                const int stop = fy.stopL + sStop + fx.stopR + eStop;
-                                R dEta = ((eM - fx.m) + (fy.m - sM)) * inv_delta;
-                                R dQx = ((eN - fx.n) + (fy.t - sT) + hg * (bE - bW) * (eH + fx.hL)) * inv_delta;
-                                R dQy = ((eT - fx.t) + (fy.n - sN) + hg * (bN - bS) * (fy.hR + sH)) * inv_delta;
-                                dEta = fm_chop(dEta, k.eps); dQx = fm_chop(dQx, k.eps); dQy = fm_chop(dQy, k.eps);
-                                if (stop > 0) { c.qx = R(0); c.qy = R(0); }
-                                c.eta = c.eta - dt * dEta; c.qx = c.qx - dt * dQx; c.qy = c.qy - dt * dQy;
-                                const R h_new = c.eta - pzb;
-                                if (k.friction && !(h_new < k.eps)) friction_fast(k, h_new, fm_rcp(h_new), c.qx, c.qy, ld(o_m, T::P_N, lc), dt);
-                                if (h_new < k.eps) c.eta = pzb;
-                                if (c.eta > c.emax && c.emax > R(-9990.0)) c.emax = c.eta;
-                            }
-                        }
-                        if (lane >= 1 && lane < 1 + T::USE && x < g.cols) {
-                            d.store(static_cast<size_t>(yc) * g.pitch + x, c);
-                            if (a.reduce_mode != hp::kReduceNone) {
-                                const R h = c.eta - pzb;
-                                if (h > k.eps10 && c.emax > R(-9999.0)) {
-                                    const R cc = fm_sqrt(k.g * h);
-                                    R sp = cc;
-                                    if (!k.simplified_speed) { const R rh = fm_rcp(h); sp = fm_max(hp_abs(c.qx * rh), hp_abs(c.qy * rh)) + cc; }
-                                    ws = fm_max(sp, ws);
-                                }
-                            }
-                        }
-                    }
-                    sM = fy.m; sN = fy.n; sT = fy.t; sZ = fy.zmax; sH = fy.hL; sStop = fy.stopR;
-                } else if (!stepping && j >= 3) {
-                    // dt <= 0: the reference's kernels return; the ping-pong copies the state through
-                    if (lane >= 1 && lane < 1 + T::USE && x < g.cols) {
-                        Cell<R> c{ld(o_m, T::P_ETA, lc), ld(o_m, T::P_EMAX, lc), ld(o_m, T::P_QX, lc), ld(o_m, T::P_QY, lc)};
-                        d.store(static_cast<size_t>(y - 1) * g.pitch + x, c);
-                        if (a.reduce_mode != hp::kReduceNone) {
-                            const R h = c.eta - pzb;
-                            if (h > k.eps10 && c.emax > R(-9999.0)) {
-                                const R cc = fm_sqrt(k.g * h);
-                                R sp = cc;
-                                if (!k.simplified_speed) { const R rh = fm_rcp(h); sp = fm_max(hp_abs(c.qx * rh), hp_abs(c.qy * rh)) + cc; }
-                                ws = fm_max(sp, ws);
-                            }
-                        }
-                    }
-                }
-            }
-            // rotate
-            pe = ce; pqx = cqx; pqy = cqy; psxE = sxE; psxH = sxH; psxQx = sxQx; psxQy = sxQy;
-            psyE = syE; psyH = syH; psyQx = syQx; psyQy = syQy; pzb = zb;
-            f_ew_prev = (f_w >> 1) | ((f_e >> 1) << 2);
-            f_m2 = f_m1; f_m1 = f_c; f_c = f_p;
-            dr_m2 = dr_m1; dr_m1 = dr_c;
-
-            // row j-1 is dead: refill its ring slot with row j-1+RR
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            if (lane == 0 && j - 1 + T::RR <= J + 1) issue_row(j - 1 + T::RR);
-        }
-    }
-    block_reduce_finalize<R>(ws, a, k);
-}
 
 // Cells the step leaves unwritten (frozen ring, all-dry stencil) still enter the CFL reduction with the value the
 // destination buffer holds.  That read is a dependent global load in the middle of a row; issue a
@@ -508,7 +290,7 @@ godunov_step_march(const StepArgs a, const __grid_constant__ TmaBlockMap maps) {
             }
 
             FaceOut<R> fy;
-            if (stepping) face_solve<R>(k, P.eta, P.zb, P.v, P.u, P.c, C.eta, C.zb, C.v, C.u, C.c, true, p_qy, c_qy, fy);
+            if (stepping) face_solve2<R, true>(k, P.eta, P.zb, P.v, P.u, P.c, C.eta, C.zb, C.v, C.u, C.c, p_qy, c_qy, fy);
             else { fy.m = fy.n = fy.t = fy.zmax = fy.hL = fy.hR = R(0); fy.stopL = fy.stopR = 0; }
 
             if (j >= 2) {
@@ -533,7 +315,7 @@ godunov_step_march(const StepArgs a, const __grid_constant__ TmaBlockMap maps) {
                 const R wU = shfl_up1(P.u), wV = shfl_up1(P.v), wC = shfl_up1(P.c);
                 const unsigned drym = __ballot_sync(FULL, dry_p);
                 FaceOut<R> fx;
-                if (stepping) face_solve<R>(k, ld(o_m, T::P_ETA, lw), ld(o_m, T::P_ZB, lw), wU, wV, wC, P.eta, P.zb, P.u, P.v, P.c, true,
+                if (stepping) face_solve2<R, true>(k, ld(o_m, T::P_ETA, lw), ld(o_m, T::P_ZB, lw), wU, wV, wC, P.eta, P.zb, P.u, P.v, P.c,
                                             ld(o_m, T::P_QX, lw), p_qx, fx);
                 else { fx.m = fx.n = fx.t = fx.zmax = fx.hL = fx.hR = R(0); fx.stopL = fx.stopR = 0; }
                 const R eM = shfl_dn1(fx.m), eN = shfl_dn1(fx.n), eT = shfl_dn1(fx.t), eZ = shfl_dn1(fx.zmax), eH = shfl_dn1(fx.hR);
@@ -813,24 +595,6 @@ static int march_grid(const StepArgs& a, int use, int nw, int ctas_per_sm, int s
     const long long cap = static_cast<long long>(ctas_per_sm) * sm_count;
     if (grid > cap) grid = cap;
     return static_cast<int>(grid < 1 ? 1 : grid);
-}
-
-template <class R> static int launch_mh_march(const StepArgs& a_in, const TmaBlockMap& maps, int alt, int sm_count, cudaStream_t st) {
-    using T = March<R, 1, false, HP_MARCH_MH_RR>;
-    StepArgs a = a_in;
-    if (a.y1 <= a.y0) return 0;
-    static bool configured[kMaxDevices] = {};          // the attribute is per device
-    const int dev = current_device();
-    if (!configured[dev]) {
-        cudaFuncSetAttribute(mh_step_march<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES);
-        cudaFuncSetAttribute(mh_step_march<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES);
-        configured[dev] = true;
-    }
-    const int grid = march_grid(a, T::USE, T::NW, sizeof(R) == 8 ? 4 : 6, sm_count);
-    a.total_ctas = grid; a.march_runs = march_runs(a, T::USE, T::NW, grid);
-    if (alt) mh_step_march<R, true><<<grid, T::NW * 32, T::SMEM_BYTES, st>>>(a, maps);
-    else mh_step_march<R, false><<<grid, T::NW * 32, T::SMEM_BYTES, st>>>(a, maps);
-    return 1;
 }
 
 template <class R> static int launch_godunov_march(const StepArgs& a_in, const TmaBlockMap& maps, int alt, int sm_count, cudaStream_t st) {

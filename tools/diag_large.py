@@ -9,6 +9,7 @@ from oracle import cpu_sim
 
 name, rows, cols, iters = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
 t0 = float(sys.argv[5]) if len(sys.argv) > 5 else None
+hydro = float(sys.argv[6]) if len(sys.argv) > 6 else 0.97
 w = dict(bench.WORKLOADS[name]); w.update(cols=cols, rows_per_gpu=rows)
 cfg = bench.cfg_for(w, rows, cols)
 dtype = np.float64 if cfg.precision == "double" else np.float32
@@ -19,7 +20,7 @@ def run(sim):
     bench.attach_boundaries(sim, w, cols, rows)
     sim.set_target(1e7)
     if t0 is not None:
-        sim.set_clock(t0, cfg.initial_dt, 0.97)
+        sim.set_clock(t0, cfg.initial_dt, hydro)
     out = []
     for i in range(iters):
         sim.iterate(1)

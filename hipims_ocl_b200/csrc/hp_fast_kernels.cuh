@@ -104,13 +104,49 @@ struct TmaMaps { CUtensorMap eta, qx, qy, zb; };
 // One shared face in the normal frame: state of the two sides -> core flux {m, n, t}.
 // "core" = without the -g/2 z'^2 part of the pressure, which is owner specific and handled in
 // closed form by the cell update (see header comment).
+// sqrt for a STRICTLY positive argument: no zero guard (rsqrt(0) = inf would give 0 * inf)
+__device__ __forceinline__ double fm_sqrt_pos(double a) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    double g = a * y;
+    const double h = 0.5 * y;
+    const double r = fma(-g, h, 0.5);
+    return fma(g, fma(1.5 * r, r, r), g);
+}
+__device__ __forceinline__ float fm_sqrt_pos(float a) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(a));
+    const float g = a * y, h = 0.5f * y;
+    return fmaf(fmaf(-g, g, a), h, g);
+}
+
 template <class R, bool CACHED_CELERITY = true>
 __device__ __forceinline__ Flux3<R> face_core_flux(const Params<R>& k, R etaL, R zL, R unL, R utL, R cL, R etaR, R zR, R unR,
                                                    R utR, R cR) {
     const R hg = R(0.5) * k.g;
     const R zmax = fm_max(zL, zR);
-    const R hL = fm_posdiff(etaL, zmax);
-    const R hR = fm_posdiff(etaR, zmax);
+    const R dL = etaL - zmax, dR = etaR - zmax;
+    if (dL > k.eps && dR > k.eps) {
+        // wet fast path: no clamps, no dry-side selects, no zero guard on the roots; the same operations the general
+        // path below performs when both depths exceed the threshold
+        const R aL = (CACHED_CELERITY && zmax == zL) ? cL : fm_sqrt_pos(k.g * dL);
+        const R aR = (CACHED_CELERITY && zmax == zR) ? cR : fm_sqrt_pos(k.g * dR);
+        const R qnL = dL * unL, qnR = dR * unR;
+        const R as = hp_abs(R(0.5) * (aL + aR) + R(0.25) * (unL - unR));
+        const R us = R(0.5) * (unL + unR) + aL - aR;
+        const R sL = fm_min(unL - aL, us - as);
+        const R sR = fm_max(unR + aR, us + as);
+        const R FLn = unL * qnL + hg * dL * dL, FRn = unR * qnR + hg * dR * dR;
+        if (sL >= R(0)) return Flux3<R>{qnL, FLn, qnL * utL};
+        if (!(sR >= R(0))) return Flux3<R>{qnR, FRn, qnR * utR};
+        const R inv = fm_rcp(sR - sL);
+        const R ss = sL * sR;
+        const R f1 = (sR * qnL - sL * qnR + ss * (dR - dL)) * inv;
+        const R f2 = (sR * FLn - sL * FRn + ss * (qnR - qnL)) * inv;
+        return Flux3<R>{f1, f2, f1 * (f1 >= R(0) ? utL : utR)};
+    }
+    const R hL = dL > R(0) ? dL : R(0);
+    const R hR = dR > R(0) ? dR : R(0);
     const bool dryL = hL < k.eps, dryR = hR < k.eps;
     if (dryL && dryR) {
         const R hm = R(0.5) * (hL + hR);
@@ -339,10 +375,23 @@ godunov_step_tma(const StepArgs a, const __grid_constant__ TmaMaps maps) {
                     if (!all_dry) {
                         int stop = 0;
                         R bN, bS, bE, bW, hnN, hnS, hnE, hnW;
-                        face_owner_terms<R, true>(k, c.eta, zb, v, c.qy, etaN, zN, s_v[oN], bN, hnN, stop);
-                        face_owner_terms<R, false>(k, c.eta, zb, v, c.qy, etaS, zS, s_v[oS], bS, hnS, stop);
-                        face_owner_terms<R, true>(k, c.eta, zb, u, c.qx, etaE, zE, s_u[oE], bE, hnE, stop);
-                        face_owner_terms<R, false>(k, c.eta, zb, u, c.qx, etaW, zW, s_u[oW], bW, hnW, stop);
+                        {
+                            // all four faces wet on both sides (the usual case away from fronts): the reconstructed bed the
+                            // owner sees IS the face's bed, the neighbour depth needs no clamp, no stop flag can be set
+                            const R mN = fm_max(zb, zN), mS = fm_max(zb, zS), mE = fm_max(zb, zE), mW = fm_max(zb, zW);
+                            const R hoN = c.eta - mN, hoS = c.eta - mS, hoE = c.eta - mE, hoW = c.eta - mW;
+                            hnN = etaN - mN; hnS = etaS - mS; hnE = etaE - mE; hnW = etaW - mW;
+                            const bool wet = hoN > k.eps && hoS > k.eps && hoE > k.eps && hoW > k.eps && hnN > k.eps && hnS > k.eps &&
+                                             hnE > k.eps && hnW > k.eps;
+                            if (wet) {
+                                bN = mN; bS = mS; bE = mE; bW = mW;
+                            } else {
+                                face_owner_terms<R, true>(k, c.eta, zb, v, c.qy, etaN, zN, s_v[oN], bN, hnN, stop);
+                                face_owner_terms<R, false>(k, c.eta, zb, v, c.qy, etaS, zS, s_v[oS], bS, hnS, stop);
+                                face_owner_terms<R, true>(k, c.eta, zb, u, c.qx, etaE, zE, s_u[oE], bE, hnE, stop);
+                                face_owner_terms<R, false>(k, c.eta, zb, u, c.qx, etaW, zW, s_u[oW], bW, hnW, stop);
+                            }
+                        }
                         const int fe = j * (T::TX + 1) + i + 1, fw = fe - 1;       // x-faces east / west of (i, j)
                         const int fn = (j + 1) * T::TX + i, fs = fn - T::TX;       // y-faces north / south
                         const R mE = s_fx[fe], mW = s_fx[fw], mN = s_fy[fn], mS = s_fy[fs];
@@ -352,9 +401,10 @@ godunov_step_tma(const StepArgs a, const __grid_constant__ TmaMaps maps) {
                         R dEta = ((mE - mW) + (mN - mS)) * inv_delta;
                         R dQx = ((nE - nW) + (tN - tS) + hg * (bE - bW) * (hnE + hnW)) * inv_delta;
                         R dQy = ((tE - tW) + (nN - nS) + hg * (bN - bS) * (hnN + hnS)) * inv_delta;
-                        dEta = fm_chop(dEta, k.eps); dQx = fm_chop(dQx, k.eps); dQy = fm_chop(dQy, k.eps);
                         if (stop > 0) { c.qx = R(0); c.qy = R(0); }
-                        c.eta = c.eta - dt * dEta; c.qx = c.qx - dt * dQx; c.qy = c.qy - dt * dQy;
+                        if (!(hp_abs(dEta) < k.eps)) c.eta = c.eta - dt * dEta;       // |D| < eps => 0 (CLSchemeGodunov.clc:340-348)
+                        if (!(hp_abs(dQx) < k.eps)) c.qx = c.qx - dt * dQx;
+                        if (!(hp_abs(dQy) < k.eps)) c.qy = c.qy - dt * dQy;
                         h_new = c.eta - zb;
                         if (!(h_new < k.eps)) { rh_new = fm_rcp(h_new); have_new = true; }
                         if (k.friction) friction_fast(k, h_new, rh_new, c.qx, c.qy, pre_mann[half], dt);

@@ -68,22 +68,6 @@ template <class R, int HALO, bool ALT, int RING = HP_MARCH_RR> struct March {
 // non-zero at a wet/dry front).  qOwnL / qOwnR: the owning CELLS' discharge normal to the face.
 template <class R> struct FaceOut { R m, n, t, zmax, hL, hR; int stopL, stopR; };
 
-// sqrt for a STRICTLY positive argument: no zero guard (rsqrt(0) = inf would give 0 * inf)
-__device__ __forceinline__ double fm_sqrt_pos(double a) {
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
-    double g = a * y;
-    const double h = 0.5 * y;
-    const double r = fma(-g, h, 0.5);
-    return fma(g, fma(1.5 * r, r, r), g);
-}
-__device__ __forceinline__ float fm_sqrt_pos(float a) {
-    float y;
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(a));
-    const float g = a * y, h = 0.5f * y;
-    return fmaf(fmaf(-g, g, a), h, g);
-}
-
 // One face in the normal frame, solved once for both cells: core flux (see face_core_flux), the common reconstructed
 // bed, both reconstructed depths and the stop-counter increments of the two owners (CLSchemeGodunov.clc:83-137 /
 // CLSchemeMUSCLHancock.clc:1172-1204; they can only be non-zero at a wet/dry front).  qOwnL / qOwnR: the owning CELLS'
@@ -331,12 +315,13 @@ godunov_step_march(const StepArgs a, const __grid_constant__ TmaBlockMap maps) {
                         if (!all_dry) {
                             const R bN = fm_min(fy.zmax, c.eta), bS = fm_min(sZ, c.eta), bE = fm_min(eZ, c.eta), bW = fm_min(fx.zmax, c.eta);
                             const int stop = fy.stopL + sStop + fx.stopR + eStop;
-                            R dEta = ((eM - fx.m) + (fy.m - sM)) * inv_delta;
-                            R dQx = ((eN - fx.n) + (fy.t - sT) + hg * (bE - bW) * (eH + fx.hL)) * inv_delta;
-                            R dQy = ((eT - fx.t) + (fy.n - sN) + hg * (bN - bS) * (fy.hR + sH)) * inv_delta;
-                            dEta = fm_chop(dEta, k.eps); dQx = fm_chop(dQx, k.eps); dQy = fm_chop(dQy, k.eps);
+                            const R dEta = ((eM - fx.m) + (fy.m - sM)) * inv_delta;
+                            const R dQx = ((eN - fx.n) + (fy.t - sT) + hg * (bE - bW) * (eH + fx.hL)) * inv_delta;
+                            const R dQy = ((eT - fx.t) + (fy.n - sN) + hg * (bN - bS) * (fy.hR + sH)) * inv_delta;
                             if (stop > 0) { c.qx = R(0); c.qy = R(0); }
-                            c.eta = c.eta - dt * dEta; c.qx = c.qx - dt * dQx; c.qy = c.qy - dt * dQy;
+                            if (!(hp_abs(dEta) < k.eps)) c.eta = c.eta - dt * dEta;   // |D| < eps => 0 (CLSchemeGodunov.clc:340-348)
+                            if (!(hp_abs(dQx) < k.eps)) c.qx = c.qx - dt * dQx;
+                            if (!(hp_abs(dQy) < k.eps)) c.qy = c.qy - dt * dQy;
                             const R h_new = c.eta - zb;
                             if (!(h_new < k.eps)) { rh_new = fm_rcp(h_new); have_new = true; }
                             if (k.friction) friction_fast(k, h_new, rh_new, c.qx, c.qy, ld(o_m, T::P_N, lc), dt);

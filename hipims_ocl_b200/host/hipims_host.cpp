@@ -11,12 +11,15 @@
 #include <fstream>
 #include <iterator>
 #include <sstream>
+#include <thread>
 
 namespace model {
 bool forceAbort = false;
 std::vector<std::string> errorLog;
 // src/main.cpp:631-652: warnings are logged, ModelStop sets forceAbort, Fatal ends the process
 void doError(const std::string& message, unsigned char level) {
+    static std::mutex mu;                              // strips report from their own host threads
+    std::lock_guard<std::mutex> lock(mu);
     errorLog.push_back(message);
     const char* tag = (level & errorCodes::kLevelFatal) ? "FATAL" : (level & errorCodes::kLevelModelStop) ? "STOP" : "WARNING";
     fprintf(stderr, "[hipims %s] %s\n", tag, message.c_str());
@@ -356,6 +359,7 @@ bool CExecutorControlCUDA::setupFromConfig(const XMLElement* pX) {
     }
     if (device < 1 || device > n) { model::doError("Invalid device number in configuration.", model::errorCodes::kLevelModelStop); return false; }
     if (hp_executor_create(device - 1, nullptr, &pExecutor) < 0) { model::doError(hp_last_error(), model::errorCodes::kLevelModelStop); return false; }
+    iDeviceOrdinal = device - 1;
     char buf[256]; int sms = 0; size_t mem = 0;
     hp_executor_describe(pExecutor, buf, sizeof(buf), &sms, &mem);
     sDeviceName = buf;
@@ -979,16 +983,61 @@ void CScheme::setupFromConfig(const XMLElement* pXScheme) {            // CSchem
     }
 }
 
-bool CScheme::prepareAll(CExecutorControlCUDA* pExec, CDomainCartesian* pDom, unsigned char ucPrecision, double dSimulationLength) {
+// f(strip, index) for every strip; on several devices each call runs on its own host thread, because the library's
+// collective entry points (attach_comm, iterate, update_timestep, prepare_graphs) contain NCCL calls that every rank
+// must issue concurrently -- the reference's one worker thread per scheme (CSchemeGodunov.cpp:1116-1141).
+template <class F> bool CScheme::forStrips(F f) {
+    if (strips.size() <= 1) { if (!strips.empty()) f(strips[0], 0); return !model::forceAbort; }
+    std::vector<std::thread> workers;
+    for (size_t i = 1; i < strips.size(); ++i) workers.emplace_back([&, i]() { f(strips[i], i); });
+    f(strips[0], 0);
+    for (auto& w : workers) w.join();
+    return !model::forceAbort;
+}
+
+bool CScheme::prepareAll(CExecutorControlCUDA* pExec, CDomainCartesian* pDom, unsigned char ucPrecision, double dSimulationLength,
+                         const std::vector<int>& devices) {
     pExecutor = pExec; pDomain = pDom; ucFloatPrecision = ucPrecision;
-    hp_scheme_config c{};
-    c.struct_size = sizeof(c); c.scheme = ucSchemeType; c.real_bytes = ucPrecision == model::floatPrecision::kSingle ? 4 : 8;
-    c.quirks = uiQuirks; c.options = uiOptions; c.dynamic_timestep = bDynamicTimestep ? 1 : 0; c.friction = bFrictionEffects ? 1 : 0;
-    c.cols = pDom->getCols(); c.rows = pDom->getRows(); c.global_rows = pDom->getRows();
-    c.delta = pDom->getCellResolution(); c.courant = dCourantNumber; c.dry_threshold = dThresholdVerySmall; c.end_time = dSimulationLength;
-    c.fixed_timestep = dTimestep; c.initial_timestep = dTimestep;
-    if (hp_scheme_create(pExec->getDevice(), &c, &pScheme) < 0) { model::doError(std::string("Could not prepare the scheme: ") + hp_last_error(), model::errorCodes::kLevelModelStop); pScheme = nullptr; return false; }
-    pDom->getBoundaries()->prepareBoundaries(pScheme, pDom, dSimulationLength);
+    const unsigned long ulRows = pDom->getRows();
+    const unsigned long ulHalo = ucSchemeType == model::schemeTypes::kMUSCLHancock ? 2 : 1;
+    size_t n = devices.size() > 1 ? devices.size() : 1;
+    if (n > 1 && ulRows / n < 2 * ulHalo + 1) { model::doError("The domain is too short to be split into that many row strips; running on one device.", model::errorCodes::kLevelWarning); n = 1; }
+    strips.assign(n, SStrip());
+    // rows are dealt out as evenly as possible, the first (rows % n) strips get one more (hipims_ocl_b200/strips.py)
+    const unsigned long ulBase = ulRows / n, ulExtra = ulRows % n;
+    for (size_t i = 0; i < n; ++i) {
+        SStrip& st = strips[i];
+        st.ulOwnRows = ulBase + (i < ulExtra ? 1 : 0);
+        st.ulOwnFirst = i * ulBase + std::min<unsigned long>(i, ulExtra);
+        const unsigned long ulHaloS = i > 0 ? ulHalo : 0, ulHaloN = i + 1 < n ? ulHalo : 0;
+        st.ulFirstRow = st.ulOwnFirst - ulHaloS; st.ulRows = st.ulOwnRows + ulHaloS + ulHaloN;
+        if (i == 0) { st.pExec = pExec->getDevice(); st.bOwnsExecutor = false; }
+        else if (hp_executor_create(devices[i], nullptr, &st.pExec) < 0) {
+            model::doError(std::string("Could not open a device for a row strip: ") + hp_last_error(), model::errorCodes::kLevelModelStop); cleanupSimulation(); return false;
+        } else st.bOwnsExecutor = true;
+        hp_scheme_config c{};
+        c.struct_size = sizeof(c); c.scheme = ucSchemeType; c.real_bytes = ucPrecision == model::floatPrecision::kSingle ? 4 : 8;
+        c.quirks = uiQuirks; c.options = uiOptions; c.dynamic_timestep = bDynamicTimestep ? 1 : 0; c.friction = bFrictionEffects ? 1 : 0;
+        c.cols = pDom->getCols(); c.rows = st.ulRows; c.global_rows = ulRows; c.row_offset = st.ulOwnFirst;
+        c.halo_south = static_cast<uint32_t>(ulHaloS); c.halo_north = static_cast<uint32_t>(ulHaloN);
+        c.delta = pDom->getCellResolution(); c.courant = dCourantNumber; c.dry_threshold = dThresholdVerySmall; c.end_time = dSimulationLength;
+        c.fixed_timestep = dTimestep; c.initial_timestep = dTimestep;
+        if (hp_scheme_create(st.pExec, &c, &st.pHandle) < 0) {
+            model::doError(std::string("Could not prepare the scheme: ") + hp_last_error(), model::errorCodes::kLevelModelStop); cleanupSimulation(); return false;
+        }
+    }
+    pScheme = strips[0].pHandle;
+    if (n > 1) {
+        unsigned char id[HP_COMM_ID_BYTES];
+        if (hp_comm_unique_id(id) < 0) { model::doError(std::string("NCCL: ") + hp_last_error(), model::errorCodes::kLevelModelStop); cleanupSimulation(); return false; }
+        forStrips([&](SStrip& st, size_t i) {
+            if (hp_scheme_attach_comm(st.pHandle, id, static_cast<int>(i), static_cast<int>(n)) < 0)
+                model::doError(std::string("Could not connect the row strips: ") + hp_last_error(), model::errorCodes::kLevelModelStop);
+        });
+        if (model::forceAbort) { cleanupSimulation(); return false; }
+    }
+    // every strip gets every boundary with GLOBAL cell numbers; the library keeps the cells a strip holds
+    for (auto& st : strips) pDom->getBoundaries()->prepareBoundaries(st.pHandle, pDom, dSimulationLength);
     dCurrentTimestep = dTimestep;
     return true;
 }
@@ -996,25 +1045,33 @@ bool CScheme::prepareAll(CExecutorControlCUDA* pExec, CDomainCartesian* pDom, un
 void CScheme::prepareSimulation() { prepareSimulationState(); }
 void CScheme::prepareSimulationState() {   // CSchemeGodunov.cpp:1053-1071
     if (!pScheme) return;
-    const unsigned long n = pDomain->getCellCount();
+    const unsigned long ulCols = pDomain->getCols();
+    std::vector<float> st32, bed32, man32;
     if (ucFloatPrecision == model::floatPrecision::kSingle) {
-        std::vector<float> st(pDomain->dCellStates.begin(), pDomain->dCellStates.end()), bed(pDomain->dBedElevations.begin(), pDomain->dBedElevations.end()),
-            man(pDomain->dManningValues.begin(), pDomain->dManningValues.end());
-        HP_CHECK(hp_scheme_upload_cells(pScheme, st.data(), bed.data(), man.data()), "upload");
-        HP_CHECK(hp_scheme_sync(pScheme), "upload");
-    } else {
-        HP_CHECK(hp_scheme_upload_cells(pScheme, pDomain->dCellStates.data(), pDomain->dBedElevations.data(), pDomain->dManningValues.data()), "upload");
-        HP_CHECK(hp_scheme_sync(pScheme), "upload");
+        st32.assign(pDomain->dCellStates.begin(), pDomain->dCellStates.end());
+        bed32.assign(pDomain->dBedElevations.begin(), pDomain->dBedElevations.end());
+        man32.assign(pDomain->dManningValues.begin(), pDomain->dManningValues.end());
     }
-    (void)n;
-    HP_CHECK(hp_scheme_set_clock(pScheme, 0.0, dTimestep, 0.0), "clock");
+    for (auto& st : strips) {                                    // each strip: the rows it holds, halo rows included
+        const size_t off = static_cast<size_t>(st.ulFirstRow) * ulCols;
+        if (ucFloatPrecision == model::floatPrecision::kSingle)
+            HP_CHECK(hp_scheme_upload_cells(st.pHandle, st32.data() + 4 * off, bed32.data() + off, man32.data() + off), "upload");
+        else
+            HP_CHECK(hp_scheme_upload_cells(st.pHandle, pDomain->dCellStates.data() + 4 * off, pDomain->dBedElevations.data() + off,
+                                            pDomain->dManningValues.data() + off), "upload");
+    }
+    for (auto& st : strips) {
+        HP_CHECK(hp_scheme_sync(st.pHandle), "upload");
+        HP_CHECK(hp_scheme_set_clock(st.pHandle, 0.0, dTimestep, 0.0), "clock");
+    }
     ulCurrentCellsCalculated = 0;
 }
 
 void CScheme::runSimulation(double dTarget, double dRealTime) {      // CSchemeGodunov.cpp:1374-1453 + one Threaded_runBatch pass
     if (!pScheme) return;
     if (dCurrentTime > dTarget + 1E-5) { model::doError("Simulation has exceeded target time", model::errorCodes::kLevelWarning); return; }   // :1389-1405
-    // batch size: aim for a second of wall clock per batch (:1419-1450; single domain, so no rollback budget to respect)
+    // batch size: aim for a second of wall clock per batch (:1419-1450; single domain, so no rollback budget to respect).
+    // Decided once, here, for all strips: they must enqueue the same number of iterations.
     if (bAutomaticQueue && dRealTime > 1E-5) {
         const double dBatchDuration = dRealTime - dBatchStartedTime;
         const unsigned int uiOld = uiQueueAdditionSize;
@@ -1024,20 +1081,29 @@ void CScheme::runSimulation(double dTarget, double dRealTime) {      // CSchemeG
         if (uiQueueAdditionSize < 1) uiQueueAdditionSize = 1;
     }
     dBatchStartedTime = dRealTime;
-    if (dTarget != dTargetTime) {
-        dTargetTime = dTarget;
-        HP_CHECK(hp_scheme_set_target_time(pScheme, dTarget), "target time");
-        if (dCurrentTimestep <= 0.0) HP_CHECK(hp_scheme_update_timestep(pScheme), "timestep update");   // forecast sync, :1191-1196
-    }
-    HP_CHECK(hp_scheme_iterate(pScheme, uiQueueAdditionSize), "iterate");
-    ulCurrentCellsCalculated += static_cast<unsigned long long>(uiQueueAdditionSize) * pDomain->getCellCount();
-    HP_CHECK(hp_scheme_sync(pScheme), "sync");
+    const bool bNewTarget = dTarget != dTargetTime;
+    const bool bUpdate = bNewTarget && dCurrentTimestep <= 0.0;        // forecast sync, :1191-1196
+    dTargetTime = dTarget;
+    const unsigned int uiBatch = uiQueueAdditionSize;
+    forStrips([&](SStrip& st, size_t) {
+        if (bNewTarget) HP_CHECK(hp_scheme_set_target_time(st.pHandle, dTarget), "target time");
+        if (bUpdate) HP_CHECK(hp_scheme_update_timestep(st.pHandle), "timestep update");
+        HP_CHECK(hp_scheme_iterate(st.pHandle, uiBatch), "iterate");
+        HP_CHECK(hp_scheme_sync(st.pHandle), "sync");
+    });
+    ulCurrentCellsCalculated += static_cast<unsigned long long>(uiBatch) * pDomain->getCellCount();
     readKeyStatistics();
 }
 
 void CScheme::readKeyStatistics() {
     hp_scheme_stats st{};
     if (hp_scheme_read_stats(pScheme, &st) < 0) { model::doError(hp_last_error(), model::errorCodes::kLevelModelStop); return; }
+    // every strip runs the same time controller on the same all-reduced maximum: their clocks are bit-identical
+    for (size_t i = 1; i < strips.size(); ++i) {
+        hp_scheme_stats o{};
+        if (hp_scheme_read_stats(strips[i].pHandle, &o) < 0 || o.time != st.time || o.timestep != st.timestep || o.batch_successful != st.batch_successful)
+            model::doError("The clocks of the row strips have diverged.", model::errorCodes::kLevelModelStop);
+    }
     uiBatchRate = st.batch_successful > uiBatchSuccessful ? st.batch_successful - uiBatchSuccessful : 1;    // CSchemeGodunov.cpp:1834
     dCurrentTime = st.time; dCurrentTimestep = st.timestep; dBatchTimesteps = st.batch_timesteps;
     uiBatchSuccessful = st.batch_successful; uiBatchSkipped = st.batch_skipped;
@@ -1045,18 +1111,27 @@ void CScheme::readKeyStatistics() {
 
 void CScheme::readDomainAll() {
     if (!pScheme) return;
-    if (ucFloatPrecision == model::floatPrecision::kSingle) {
-        std::vector<float> st(pDomain->dCellStates.size());
-        HP_CHECK(hp_scheme_download_cells(pScheme, st.data()), "download");
-        std::copy(st.begin(), st.end(), pDomain->dCellStates.begin());
-    } else {
-        HP_CHECK(hp_scheme_download_cells(pScheme, pDomain->dCellStates.data()), "download");
+    const unsigned long ulCols = pDomain->getCols();
+    for (auto& st : strips) {                                    // the OWNED rows of every strip, straight into the domain's arrays
+        const size_t off = static_cast<size_t>(st.ulOwnFirst) * ulCols * 4;
+        const unsigned long ulLocal = st.ulOwnFirst - st.ulFirstRow;
+        if (ucFloatPrecision == model::floatPrecision::kSingle) {
+            std::vector<float> tmp(static_cast<size_t>(st.ulOwnRows) * ulCols * 4);
+            HP_CHECK(hp_scheme_read_rows(st.pHandle, ulLocal, st.ulOwnRows, tmp.data()), "download");
+            std::copy(tmp.begin(), tmp.end(), pDomain->dCellStates.begin() + off);
+        } else {
+            HP_CHECK(hp_scheme_read_rows(st.pHandle, ulLocal, st.ulOwnRows, pDomain->dCellStates.data() + off), "download");
+        }
     }
 }
 bool CScheme::deriveRaster(unsigned char ucValue, std::vector<double>& northFirst) {
     if (!pScheme) return false;
     northFirst.resize(pDomain->getCellCount());
-    if (hp_scheme_derive_raster(pScheme, ucValue, -9999.0, northFirst.data()) < 0) { model::doError(hp_last_error(), model::errorCodes::kLevelWarning); return false; }
+    const unsigned long ulCols = pDomain->getCols(), ulRows = pDomain->getRows();
+    for (auto& st : strips) {        // a strip's owned rows [a, b) are the north-first rows [rows - b, rows - a) of the band
+        double* out = northFirst.data() + static_cast<size_t>(ulRows - (st.ulOwnFirst + st.ulOwnRows)) * ulCols;
+        if (hp_scheme_derive_raster(st.pHandle, ucValue, -9999.0, out) < 0) { model::doError(hp_last_error(), model::errorCodes::kLevelWarning); return false; }
+    }
     return true;
 }
 bool CScheme::isSimulationSyncReady(double dExpected) const { return !(dExpected - dCurrentTime > 1E-5); }       // CSchemeGodunov.cpp:1568-1612
@@ -1068,11 +1143,13 @@ void CScheme::rollbackSimulation(double dTime, double dTarget) {                
     if (!pScheme) return;
     prepareSimulationState();
     dCurrentTime = dTime; dTargetTime = dTarget;
-    HP_CHECK(hp_scheme_set_clock(pScheme, dTime, dCurrentTimestep, 0.0), "rollback clock");
-    HP_CHECK(hp_scheme_set_target_time(pScheme, dTarget), "rollback target");
-    if (bDynamicTimestep) HP_CHECK(hp_scheme_update_timestep(pScheme), "rollback timestep");                     // tst_Reduce + tst_UpdateTimestep
-    HP_CHECK(hp_scheme_reset_counters(pScheme), "rollback counters");
-    HP_CHECK(hp_scheme_sync(pScheme), "rollback");
+    forStrips([&](SStrip& st, size_t) {
+        HP_CHECK(hp_scheme_set_clock(st.pHandle, dTime, dCurrentTimestep, 0.0), "rollback clock");
+        HP_CHECK(hp_scheme_set_target_time(st.pHandle, dTarget), "rollback target");
+        if (bDynamicTimestep) HP_CHECK(hp_scheme_update_timestep(st.pHandle), "rollback timestep");              // tst_Reduce + tst_UpdateTimestep
+        HP_CHECK(hp_scheme_reset_counters(st.pHandle), "rollback counters");
+        HP_CHECK(hp_scheme_sync(st.pHandle), "rollback");
+    });
     readKeyStatistics();
 }
 double CScheme::proposeSyncPoint(double dTime) const {                                                           // :1758-1790
@@ -1083,8 +1160,18 @@ double CScheme::proposeSyncPoint(double dTime) const {                          
     else if (dProposal - dTime < 1E-5) dProposal = dTime + std::fabs(dTimestep);
     return dProposal;
 }
-void CScheme::forceTimestep(double dt) { if (pScheme) HP_CHECK(hp_scheme_force_timestep(pScheme, dt), "force timestep"); }
-void CScheme::cleanupSimulation() { if (pScheme) { hp_scheme_destroy(pScheme); pScheme = nullptr; } }
+void CScheme::forceTimestep(double dt) { for (auto& st : strips) HP_CHECK(hp_scheme_force_timestep(st.pHandle, dt), "force timestep"); }
+void CScheme::cleanupSimulation() {
+    // schemes first (their NCCL communicators are torn down collectively: one thread per strip), then the extra executors
+    if (strips.size() > 1) {
+        std::vector<std::thread> workers;
+        for (auto& st : strips) workers.emplace_back([&st]() { if (st.pHandle) hp_scheme_destroy(st.pHandle); st.pHandle = nullptr; });
+        for (auto& w : workers) w.join();
+    } else if (!strips.empty() && strips[0].pHandle) { hp_scheme_destroy(strips[0].pHandle); strips[0].pHandle = nullptr; }
+    for (auto& st : strips) if (st.bOwnsExecutor && st.pExec) hp_executor_destroy(st.pExec);
+    strips.clear();
+    pScheme = nullptr;
+}
 
 // ---------------------------------------------------------------------------------------------
 // Model
@@ -1123,6 +1210,15 @@ bool CModel::loadConfiguration(const std::string& sPath, bool bDeviceless) {
     const XMLElement* dom = set ? set->FirstChildElement("domain") : nullptr;
     if (!dom) { model::doError("No <domain> defined.", model::errorCodes::kLevelModelStop); return false; }
     const XMLElement* pXScheme = dom->FirstChildElement("scheme");
+    // <domain deviceNumber="N"> (src/Domain/CDomain.cpp:88, CDomainManager.cpp:140-177): the distinct devices the domains
+    // name, south to north in the order they appear, are the GPUs the (merged) domain is spread over as row strips
+    std::vector<int> xmlDevices;
+    for (const XMLElement* d = dom; d; d = d->NextSiblingElement("domain")) {
+        const char* a = d->Attribute("deviceNumber");
+        if (!a || !*a) continue;
+        const int n = atoi(a);
+        if (n >= 1 && std::find(xmlDevices.begin(), xmlDevices.end(), n) == xmlDevices.end()) xmlDevices.push_back(n);
+    }
     if (!dom->NextSiblingElement("domain")) {
         if (Util::toLowercase(dom->Attribute("type")) != "cartesian") { model::doError("Unsupported domain type.", model::errorCodes::kLevelModelStop); return false; }
         pDomain.reset(new CDomainCartesian());
@@ -1145,7 +1241,23 @@ bool CModel::loadConfiguration(const std::string& sPath, bool bDeviceless) {
     pScheme.reset(CScheme::createFromConfig(pXScheme));
     if (!pScheme) return false;
     if (bDeviceless) return true;      // host-side parsing only (CPU tests)
-    return pScheme->prepareAll(pExecutor.get(), pDomain.get(), ucFloatPrecision, dSimulationTime);
+    // which devices: --devices / HIPIMS_DEVICES if given, else the configuration's device numbers; numbers beyond the
+    // devices present are dropped with a warning (a configuration written for four GPUs still runs on one).  The
+    // executor's own device (<executor><parameter name="deviceNumber">) always comes first.
+    std::vector<int> numbers = stripDeviceNumbers;
+    if (numbers.empty()) if (const char* e = getenv("HIPIMS_DEVICES")) for (const char* p = e; *p;) { numbers.push_back(atoi(p)); while (*p && *p != ',') ++p; if (*p) ++p; }
+    if (numbers.empty() && !parts.empty()) numbers = xmlDevices;
+    std::vector<int> ordinals;
+    for (int n : numbers) {
+        if (n < 1 || n > static_cast<int>(pExecutor->getDeviceCount())) { model::doError("Device " + std::to_string(n) + " named by the configuration is not present; its rows go to the devices that are.", model::errorCodes::kLevelWarning); continue; }
+        if (std::find(ordinals.begin(), ordinals.end(), n - 1) == ordinals.end()) ordinals.push_back(n - 1);
+    }
+    if (ordinals.size() > 1) {
+        const int first = pExecutor->getDeviceOrdinal();
+        auto it = std::find(ordinals.begin(), ordinals.end(), first);
+        if (it == ordinals.end()) ordinals.insert(ordinals.begin(), first); else std::rotate(ordinals.begin(), it, it + 1);
+    }
+    return pScheme->prepareAll(pExecutor.get(), pDomain.get(), ucFloatPrecision, dSimulationTime, ordinals);
 }
 
 bool CModel::runModel() {
@@ -1195,6 +1307,15 @@ unsigned int hph_model_parts(void* h, unsigned long* row_offsets, unsigned int c
     CModel* m = static_cast<CModel*>(h);
     for (unsigned int i = 0; i < m->getPartCount() && i < capacity; ++i) row_offsets[i] = m->getPartRowOffset(i);
     return m->getPartCount();
+}
+unsigned int hph_model_strips(void* h) { return static_cast<CModel*>(h)->getStripCount(); }
+// like hph_model_load, with the (1-based) devices to spread the domain over given by the caller
+void* hph_model_load_on(const char* path, const int* devices, int count) {
+    model::forceAbort = false; model::errorLog.clear();
+    CModel* m = new CModel();
+    m->setStripDevices(std::vector<int>(devices, devices + count));
+    if (!m->loadConfiguration(path, false)) { delete m; return nullptr; }
+    return m;
 }
 void hph_model_set_realtime_queue(void* h, int on) { static_cast<CModel*>(h)->setRealTimeQueue(on != 0); }
 // rollback: put the host arrays and clock back on the device, then report the recomputed timestep

@@ -17,6 +17,7 @@
 #include <cstdint>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -113,10 +114,12 @@ class CExecutorControlCUDA {
     bool isReady() const { return pExecutor != nullptr; }
     unsigned int getDeviceCount() const { return uiDeviceCount; }
     hp_executor* getDevice() const { return pExecutor; }
+    int getDeviceOrdinal() const { return iDeviceOrdinal; }
     std::string getDeviceShortName() const { return sDeviceName; }
     void blockUntilFinished();
   private:
     hp_executor* pExecutor = nullptr;
+    int iDeviceOrdinal = 0;
     unsigned int uiDeviceCount = 0;
     std::string sDeviceName;
 };
@@ -227,7 +230,13 @@ class CScheme {
     static CScheme* createFromConfig(const XMLElement* pXScheme);    // <scheme name="godunov|muscl-hancock|inertial">
     virtual ~CScheme();
     virtual void setupFromConfig(const XMLElement* pXScheme);
-    bool prepareAll(CExecutorControlCUDA* pExec, CDomainCartesian* pDomain, unsigned char ucFloatPrecision, double dSimulationLength);
+    // `devices` (0-based ordinals): more than one runs the domain as row strips, one per GPU, behind this one scheme
+    // object -- the multi-device path of the reference (one CScheme per <domain deviceNumber=..>, CDomainLink overlap
+    // exchange, src/Domain/CDomainManager.cpp:56-282, Links/CDomainLink.cpp:286-382) re-targeted to the library's NCCL
+    // strip engine.  The first device is the executor's.
+    bool prepareAll(CExecutorControlCUDA* pExec, CDomainCartesian* pDomain, unsigned char ucFloatPrecision, double dSimulationLength,
+                    const std::vector<int>& devices = std::vector<int>());
+    unsigned int getStripCount() const { return static_cast<unsigned int>(strips.size()); }
     void prepareSimulation();                          // uploads cells and clock
     void prepareSimulationState();
     void runSimulation(double dTargetTime, double dRealTime);   // sets the target and schedules a batch
@@ -271,7 +280,12 @@ class CScheme {
     explicit CScheme(unsigned char type) : ucSchemeType(type) {}
     unsigned char ucSchemeType;
     unsigned char ucFloatPrecision = model::floatPrecision::kDouble;
-    hp_scheme* pScheme = nullptr;
+    hp_scheme* pScheme = nullptr;                      // the first (on one device: the only) strip
+    // one per device: executor (owned here except the first), scheme handle, and the rows it holds / owns
+    struct SStrip { hp_executor* pExec = nullptr; bool bOwnsExecutor = false; hp_scheme* pHandle = nullptr;
+                    unsigned long ulFirstRow = 0, ulRows = 0, ulOwnFirst = 0, ulOwnRows = 0; };
+    std::vector<SStrip> strips;
+    template <class F> bool forStrips(F f);            // f(strip, index) on one host thread per strip (NCCL needs them concurrent)
     CDomainCartesian* pDomain = nullptr;
     CExecutorControlCUDA* pExecutor = nullptr;
     unsigned int uiQueueAdditionSize = 256;
@@ -300,6 +314,10 @@ class CModel {
     // pass wall-clock time to CScheme::runSimulation so that queueMode="auto" sizes batches for about a second of work
     // (src/CModel.cpp:1041-1139); off by default so that iteration counts are reproducible
     void setRealTimeQueue(bool b) { bRealTimeQueue = b; }
+    // split the (merged) domain into row strips over these devices (1-based numbers as in <domain deviceNumber=..>);
+    // given before loadConfiguration it overrides the configuration's own device numbers (CLI --devices, HIPIMS_DEVICES)
+    void setStripDevices(const std::vector<int>& numbers) { stripDeviceNumbers = numbers; }
+    unsigned int getStripCount() const { return pScheme ? pScheme->getStripCount() : 0; }
     double getSimulationLength() const { return dSimulationTime; }
     double getOutputFrequency() const { return dOutputFrequency; }
     unsigned char getFloatPrecision() const { return ucFloatPrecision; }
@@ -316,6 +334,7 @@ class CModel {
     // multi-domain configurations: the original domains (for their data targets) and where they sit in pDomain
     std::vector<std::unique_ptr<CDomainCartesian>> parts;
     std::vector<unsigned long> partRowOffsets;
+    std::vector<int> stripDeviceNumbers;
   public:
     unsigned int getPartCount() const { return static_cast<unsigned int>(parts.size()); }
     unsigned long getPartRowOffset(unsigned int i) const { return partRowOffsets[i]; }

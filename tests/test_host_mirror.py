@@ -595,3 +595,73 @@ def test_automatic_queue_and_rollback(host, model_dir):
         host.hph_model_destroy(C.c_void_p(h))
     np.testing.assert_array_equal(runs[0][0], runs[1][0])
     assert runs[0][1] == runs[1][1] == 30.0 and runs[0][2] == runs[1][2]
+
+
+# ---- decomposed models from the configuration: <domain deviceNumber=..> stacks -> the strip engine --------
+def _gpu_count():
+    import torch
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scheme", ["Godunov", "MUSCL-Hancock", "Inertial"])
+def test_stacked_domains_run_as_row_strips_on_their_devices(host, tmp_path, scheme):
+    """A two-<domain> configuration naming deviceNumber 1 and 2 runs as two row strips, one per GPU (NCCL halo exchange and
+    dt all-reduce inside the library, one host thread per strip), bit-identical to the same terrain configured as one
+    domain on one GPU -- states, clock and per-domain rasters (src/Domain/CDomainManager.cpp:56-282,
+    Links/CDomainLink.cpp:286-382 re-targeted)."""
+    if _gpu_count() < 2:
+        pytest.skip("needs two GPUs")
+    from oracle import raster_oracle as ro
+    bed = make_stacked(tmp_path, duration=20)
+    (tmp_path / "boundaries" / "map_lower.csv").write_text("x,y\n1,10\n")
+    (tmp_path / "boundaries" / "map_upper.csv").write_text("x,y\n")
+    for name in ("stacked.xml", "single.xml"):
+        p = tmp_path / name
+        p.write_text(p.read_text().replace('<scheme name="Godunov">', '<scheme name="%s">' % scheme))
+    host.hph_model_strips.argtypes = [C.c_void_p]
+    host.hph_model_strips.restype = C.c_uint
+    results, clocks = {}, {}
+    for name in ("stacked", "single"):
+        h = host.hph_model_load(str(tmp_path / (name + ".xml")).encode(), 0)
+        assert h, [host.hph_error(i) for i in range(host.hph_error_count())]
+        assert host.hph_model_strips(C.c_void_p(h)) == (2 if name == "stacked" else 1)
+        assert host.hph_model_run(C.c_void_p(h)) == 0, [host.hph_error(i) for i in range(host.hph_error_count())]
+        results[name] = arrays(host, h, 70, 40)[0]
+        t, dt, ok, skipped = C.c_double(), C.c_double(), C.c_uint(), C.c_uint()
+        host.hph_model_clock(C.c_void_p(h), C.byref(t), C.byref(dt), C.byref(ok), C.byref(skipped))
+        clocks[name] = (t.value, dt.value, ok.value, skipped.value)
+        host.hph_model_destroy(C.c_void_p(h))
+    assert not np.array_equal(results["single"][..., 0], bed)                 # it rained and the inflow ran
+    np.testing.assert_array_equal(results["stacked"], results["single"])
+    assert clocks["stacked"] == clocks["single"]
+    full, _ = read_tiff(str(tmp_path / "output" / "full_depth_20.tif"))
+    np.testing.assert_array_equal(full, ro.derive_raster(ro.DEPTH, results["single"], bed, 2.0))
+    lower, _ = read_tiff(str(tmp_path / "output" / "lower_depth_20.tif"))
+    upper, _ = read_tiff(str(tmp_path / "output" / "upper_depth_20.tif"))
+    np.testing.assert_array_equal(lower, full[30:])
+    np.testing.assert_array_equal(upper, full[:40])
+
+
+@pytest.mark.gpu
+def test_single_domain_spread_over_devices_on_request(host, model_dir):
+    """--devices / hph_model_load_on: one <domain> split into row strips over every GPU of the box."""
+    n = _gpu_count()
+    if n < 2:
+        pytest.skip("needs two GPUs")
+    cfg, bed = model_dir(scheme="MUSCL-Hancock", duration=30, outfreq=30)
+    host.hph_model_load_on.restype = C.c_void_p
+    host.hph_model_load_on.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.c_int]
+    host.hph_model_strips.argtypes = [C.c_void_p]
+    host.hph_model_strips.restype = C.c_uint
+    n = min(n, 4)
+    out = {}
+    for devices in ([1], list(range(1, n + 1))):
+        arr = (C.c_int * len(devices))(*devices)
+        h = host.hph_model_load_on(cfg.encode(), arr, len(devices))
+        assert h, [host.hph_error(i) for i in range(host.hph_error_count())]
+        assert host.hph_model_strips(C.c_void_p(h)) == len(devices)
+        assert host.hph_model_run(C.c_void_p(h)) == 0, [host.hph_error(i) for i in range(host.hph_error_count())]
+        out[len(devices)] = arrays(host, h, 30, 40)[0]
+        host.hph_model_destroy(C.c_void_p(h))
+    np.testing.assert_array_equal(out[n], out[1])

@@ -459,12 +459,14 @@ int hp_executor_finish(hp_executor* ex) {
 int hp_executor_timer_start(hp_executor* ex) {
     if (!ex) return fail(HP_ERR_INVALID, "executor is null");
     std::lock_guard<std::recursive_mutex> lock__(ex->mu);
+    HP_CUDA(cudaSetDevice(ex->device));
     HP_CUDA(cudaEventRecord(ex->ev0, ex->stream));
     return HP_OK;
 }
 int hp_executor_timer_stop(hp_executor* ex, float* ms) {
     if (!ex || !ms) return fail(HP_ERR_INVALID, "null argument");
     std::lock_guard<std::recursive_mutex> lock__(ex->mu);
+    HP_CUDA(cudaSetDevice(ex->device));
     HP_CUDA(cudaEventRecord(ex->ev1, ex->stream));
     HP_CUDA(cudaEventSynchronize(ex->ev1));
     HP_CUDA(cudaEventElapsedTime(ms, ex->ev0, ex->ev1));
@@ -545,6 +547,7 @@ void hp_scheme_destroy(hp_scheme* s) {
 int hp_boundary_add_uniform(hp_scheme* s, const hp_bdy_uniform* conf, const double* series) {
     if (!s || !conf || !series) return fail(HP_ERR_INVALID, "null argument");
     std::lock_guard<std::recursive_mutex> lock__(s->mu);
+    HP_CUDA(cudaSetDevice(s->ex->device));
     if (conf->entries < 2 || !(conf->interval > 0.0)) return fail(HP_ERR_INVALID, "a boundary timeseries is too short");
     Boundary b; b.kind = 0; b.uniform = *conf;
     int rc = upload_series(s, series, 2 * static_cast<size_t>(conf->entries), 2 * static_cast<size_t>(conf->entries) + 2, &b.series);
@@ -557,6 +560,7 @@ int hp_boundary_add_uniform(hp_scheme* s, const hp_bdy_uniform* conf, const doub
 int hp_boundary_add_gridded(hp_scheme* s, const hp_bdy_gridded* conf, const double* series) {
     if (!s || !conf || !series) return fail(HP_ERR_INVALID, "null argument");
     std::lock_guard<std::recursive_mutex> lock__(s->mu);
+    HP_CUDA(cudaSetDevice(s->ex->device));
     if (conf->entries < 1 || conf->rows < 1 || conf->cols < 1 || !(conf->interval > 0.0) || !(conf->resolution > 0.0))
         return fail(HP_ERR_INVALID, "bad gridded boundary configuration");
     Boundary b; b.kind = 1; b.gridded = *conf;
@@ -572,6 +576,7 @@ int hp_boundary_add_gridded(hp_scheme* s, const hp_bdy_gridded* conf, const doub
 int hp_boundary_add_cell(hp_scheme* s, const hp_bdy_cell* conf, const uint64_t* relations, const double* series) {
     if (!s || !conf || !relations || !series) return fail(HP_ERR_INVALID, "null argument");
     std::lock_guard<std::recursive_mutex> lock__(s->mu);
+    HP_CUDA(cudaSetDevice(s->ex->device));
     if (conf->entries < 2 || !(conf->interval > 0.0)) return fail(HP_ERR_INVALID, "a boundary timeseries is too short");
     Boundary b; b.kind = 2; b.cell = *conf; b.count = conf->relations;
     // the kernel reads entry base+1 (CLBoundaries.clc:44,49): one padding entry
@@ -666,16 +671,19 @@ int hp_scheme_derive_raster(hp_scheme* s, uint32_t value, double nodata, double*
 int hp_scheme_set_target_time(hp_scheme* s, double target) {
     if (!s) return fail(HP_ERR_INVALID, "scheme is null");
     std::lock_guard<std::recursive_mutex> lock__(s->mu);
+    HP_CUDA(cudaSetDevice(s->ex->device));
     return write_clock_field(s, 3, target);
 }
 int hp_scheme_force_timestep(hp_scheme* s, double timestep) {
     if (!s) return fail(HP_ERR_INVALID, "scheme is null");
     std::lock_guard<std::recursive_mutex> lock__(s->mu);
+    HP_CUDA(cudaSetDevice(s->ex->device));
     return write_clock_field(s, 1, timestep);
 }
 int hp_scheme_set_clock(hp_scheme* s, double time, double timestep, double th) {
     if (!s) return fail(HP_ERR_INVALID, "scheme is null");
     std::lock_guard<std::recursive_mutex> lock__(s->mu);
+    HP_CUDA(cudaSetDevice(s->ex->device));
     int rc = write_clock_field(s, 0, time);
     if (!rc) rc = write_clock_field(s, 1, timestep);
     if (!rc) rc = write_clock_field(s, 2, th);
@@ -701,6 +709,7 @@ int hp_scheme_update_timestep(hp_scheme* s) {
 int hp_scheme_reset_counters(hp_scheme* s) {
     if (!s) return fail(HP_ERR_INVALID, "scheme is null");
     std::lock_guard<std::recursive_mutex> lock__(s->mu);
+    HP_CUDA(cudaSetDevice(s->ex->device));
     int rc = write_clock_field(s, 4, 0.0);
     if (rc) return rc;
     HP_CUDA(cudaMemsetAsync(static_cast<char*>(s->clock) + 5 * s->rb, 0, 2 * sizeof(unsigned int), s->ex->stream));
@@ -838,6 +847,7 @@ int hp_scheme_attach_comm(hp_scheme* s, const void* id, int rank, int world_size
 int hp_scheme_strip_timing(hp_scheme* s, int enable) {
     if (!s) return fail(HP_ERR_INVALID, "scheme is null");
     std::lock_guard<std::recursive_mutex> lock__(s->mu);
+    HP_CUDA(cudaSetDevice(s->ex->device));
     if (!s->comm) return fail(HP_ERR_INVALID, "strip timing needs an attached communicator");
     HP_CUDA(cudaStreamSynchronize(s->ex->stream));
     s->strip_timing = enable != 0;

@@ -106,6 +106,28 @@ STRIP_PHASES = ("edge_rows", "interior_rows", "halo_wait", "allreduce", "clock")
 _lib = None
 
 
+def prefer_bundled_nccl():
+    """Points the library's dlopen of NCCL (HIPIMS_NCCL_LIB, csrc/hp_comm.cpp) at the NCCL that ships with PyTorch.
+
+    One process can hold only one libnccl.so.2: whichever is loaded first serves every later user.  If the library
+    loaded the system's (older) NCCL before `import torch`, libtorch_cuda would be bound to it and fail on symbols it
+    lacks -- so in a Python process the bundled one is named up front.  The stand-alone C++ host has no such conflict
+    and uses the system library."""
+    if os.environ.get("HIPIMS_NCCL_LIB"):
+        return os.environ["HIPIMS_NCCL_LIB"]
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for base in (spec.submodule_search_locations if spec else []):
+            cand = os.path.join(base, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ["HIPIMS_NCCL_LIB"] = cand
+                return cand
+    except Exception:
+        pass
+    return None
+
+
 def load_library():
     """Loads libhipims_cuda.so and declares the ABI.  Raises if the library is not built."""
     global _lib
@@ -114,6 +136,7 @@ def load_library():
     if not os.path.exists(LIB_PATH):
         raise HipimsCudaError("%s is missing: run `python -m hipims_ocl_b200.build` (nvcc, sm_100a). "
                               "There is no CPU fallback." % LIB_PATH)
+    prefer_bundled_nccl()
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in ABI.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export the symbol

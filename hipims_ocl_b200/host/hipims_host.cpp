@@ -1017,7 +1017,11 @@ bool CScheme::prepareAll(CExecutorControlCUDA* pExec, CDomainCartesian* pDom, un
         } else st.bOwnsExecutor = true;
         hp_scheme_config c{};
         c.struct_size = sizeof(c); c.scheme = ucSchemeType; c.real_bytes = ucPrecision == model::floatPrecision::kSingle ? 4 : 8;
-        c.quirks = uiQuirks; c.options = uiOptions; c.dynamic_timestep = bDynamicTimestep ? 1 : 0; c.friction = bFrictionEffects ? 1 : 0;
+        // Strips of ONE process launch directly: capturing NCCL operations into CUDA graphs from several threads of the
+        // same process fails inside NCCL (ncclGroupEnd: internal error, NCCL 2.28, measured); with one process per GPU --
+        // bench.py, tools/multigpu_check.py -- the captured path is used.
+        c.quirks = uiQuirks; c.options = uiOptions | (n > 1 ? HP_OPT_NO_GRAPH : 0u);
+        c.dynamic_timestep = bDynamicTimestep ? 1 : 0; c.friction = bFrictionEffects ? 1 : 0;
         c.cols = pDom->getCols(); c.rows = st.ulRows; c.global_rows = ulRows; c.row_offset = st.ulOwnFirst;
         c.halo_south = static_cast<uint32_t>(ulHaloS); c.halo_north = static_cast<uint32_t>(ulHaloN);
         c.delta = pDom->getCellResolution(); c.courant = dCourantNumber; c.dry_threshold = dThresholdVerySmall; c.end_time = dSimulationLength;

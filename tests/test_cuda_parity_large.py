@@ -112,7 +112,7 @@ def test_wrapping_kernels_on_wet_dry_terrain(ex, scheme, options):
     cases) at a size where the persistent loops wrap: every dry-side / stop-flag / stale-destination branch next to a
     tile or run boundary."""
     from tests.helpers import make_cfg, scenario
-    rows, cols, iters = 2048, 3072, 3
+    rows, cols, iters = 4608, 3072, 3
     cfg = make_cfg(scheme, "double", rows, cols)
     bed, st, man = scenario("wetdry", rows, cols, np.float64, seed=77)
     orc = cpu_sim.CpuSim("oracle", cfg)
@@ -192,7 +192,7 @@ def test_march_runs_really_wrap():
     assert per_cta(4096, 4096, 30, 6) >= 128      # inertial fp64
     assert per_cta(4096, 4096, 28, 8) >= 128      # inertial fp32
     assert (1024 // 8) * (1536 // 32) > 9 * 148   # Godunov tiles
-    assert per_cta(2048, 3072, 30, 4) >= 128 and per_cta(2048, 3072, 30, 6) >= 64   # the wet/dry terrain cases
+    assert per_cta(4608, 3072, 30, 4) >= 128 and per_cta(4608, 3072, 30, 6) >= 128   # the wet/dry terrain cases
 
 
 def test_configs3_combination(ex):

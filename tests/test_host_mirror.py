@@ -146,6 +146,8 @@ def model_dir(tmp_path):
 def host():
     hpbuild.build()
     hpbuild.build_host()
+    from hipims_ocl_b200 import executor as hx
+    hx.prefer_bundled_nccl()          # the strips of the multi-device tests must share PyTorch's NCCL (one libnccl per process)
     lib = C.CDLL(hpbuild.HOST_LIB)
     lib.hph_model_load.restype = C.c_void_p
     lib.hph_model_load.argtypes = [C.c_char_p, C.c_int]

@@ -275,8 +275,16 @@ int encode_plane_map(void* out128, void* plane, const hp::Grid& g, size_t rb, in
     const cuuint32_t box[3] = {static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(box_h), static_cast<cuuint32_t>(box_planes)};
     const cuuint32_t estride[3] = {1, 1, 1};
     CUtensorMap tm;
+    // L2 promotion: how much of a line a TMA miss brings into L2.  HIPIMS_TMA_L2_PROMOTION (0 none, 1 64 B, 2 128 B, 3 256 B)
+    // is a measurement knob; the default is what measured best.
+    static const CUtensorMapL2promotion promotion = []() {
+        const char* e = getenv("HIPIMS_TMA_L2_PROMOTION");
+        const int v = e ? atoi(e) : 2;
+        return v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+             : v == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+    }();
     const CUresult r = encode(&tm, rb == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, planes > 0 ? 3 : 2, plane, gdim, gstride,
-                              box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, promotion,
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(HP_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
     static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap size");

@@ -162,31 +162,44 @@ mh_step_march2(const StepArgs a, const __grid_constant__ TmaBlockMap maps) {
         // (identical to what the full arithmetic produces, at a fraction of its instructions).
         bool dr_m2 = false, dr_m1 = false, dr_c = false;     // rows j-2, j-1, j (warp-uniform)
 
+        bool in_skip = false;                                // the previous trip copied its row through
         for (int j = 1; j <= J; ++j) {
             const int y = rs + j, gy = y + g.gy0;
             const int o_m = ((j - 1) & (T::RR - 1)) * T::SLOT, o_c = (j & (T::RR - 1)) * T::SLOT,
                       o_p = ((j + 1) & (T::RR - 1)) * T::SLOT;
             wait_row(j + 1);
-            const int f_p = flags_of(ld(o_p, T::P_EMAX, lc));
-            int f_w = __shfl_up_sync(FULL, f_c, 1), f_e = __shfl_down_sync(FULL, f_c, 1);
-            if (lane == 0) f_w = flags_of(ld(o_c, T::P_EMAX, lw));          // the columns beyond the edge lanes have no lane
-            if (lane == 31) f_e = flags_of(ld(o_c, T::P_EMAX, le));
-
             const R eta = ld(o_c, T::P_ETA, lc), qx = ld(o_c, T::P_QX, lc), qy = ld(o_c, T::P_QY, lc), zb = ld(o_c, T::P_ZB, lc);
             // (tested on every fourth row, and on every row while the rows below are dry: wet regions pay almost nothing)
             dr_c = false;
-            if (dr_m1 || (j & 3) == 0)
-                dr_c = __all_sync(FULL, eta == zb && qx == R(0) && qy == R(0) && !(eta > ld(o_c, T::P_EMAX, lc)));
+            R emax_c = R(0);
+            if (dr_m1 || (j & 3) == 0) {
+                emax_c = ld(o_c, T::P_EMAX, lc);
+                dr_c = __all_sync(FULL, eta == zb && qx == R(0) && qy == R(0) && !(eta > emax_c));
+            }
 
             if (dr_m2 && dr_m1 && dr_c) {
-                // rows y-2, y-1, y exactly dry in every lane (so j >= 3): the cell (x, y-1) cannot change; row y hands a dry
-                // northern face estimate and empty sums to the next trip
+                // rows y-2, y-1, y exactly dry in every lane (so j >= 3): the cell (x, y-1) cannot change.  A trip in this
+                // mode does the least possible: copy the row, keep the one flag bit a dry row can have (eta_max < eps; a
+                // disabled cell never has eta == zb).  Everything else is rebuilt when the mode is left.
                 if (x_store)
                     d.store(static_cast<size_t>(y - 1) * g.pitch + x,
                             Cell<R>{ld(o_m, T::P_ETA, lc), ld(o_m, T::P_EMAX, lc), ld(o_m, T::P_QX, lc), ld(o_m, T::P_QY, lc)});
-                Le = eta; Lh = R(0); Lun = R(0); Lut = R(0);
-                Aeta = R(0); Aqx = R(0); Aqy = R(0); bS = eta; sH = R(0); cStop = 0;
+                f_m2 = f_m1; f_m1 = emax_c < k.eps ? 2 : 0;          // flags of rows y-1 and y for the next trip
+                in_skip = true;
             } else {
+                if (in_skip) {
+                    // leaving the copy-through mode: row y-1 is exactly dry -- its northern face estimate is its level with no
+                    // depth and no velocity, its sums are empty; f_m1 / f_m2 were kept, the rest of the flags is re-derived
+                    in_skip = false;
+                    Le = ld(o_m, T::P_ETA, lc); Lh = R(0); Lun = R(0); Lut = R(0);
+                    Aeta = R(0); Aqx = R(0); Aqy = R(0); bS = Le; sH = R(0); cStop = 0;
+                    f_c = flags_of(ld(o_c, T::P_EMAX, lc));
+                    f_ew_prev = (__shfl_up_sync(FULL, f_m1, 1) >> 1) | ((__shfl_down_sync(FULL, f_m1, 1) >> 1) << 2);
+                }
+                const int f_p = flags_of(ld(o_p, T::P_EMAX, lc));
+                int f_w = __shfl_up_sync(FULL, f_c, 1), f_e = __shfl_down_sync(FULL, f_c, 1);
+                if (lane == 0) f_w = flags_of(ld(o_c, T::P_EMAX, lw));          // the columns beyond the edge lanes have no lane
+                if (lane == 31) f_e = flags_of(ld(o_c, T::P_EMAX, le));
                 // ---- predictor of row y (CLSchemeMUSCLHancock.clc:301-382) ---------------------------
                 R ce = eta, cqx = qx, cqy = qy;
                 R sxE = R(0), sxH = R(0), sxQx = R(0), sxQy = R(0), syE = R(0), syH = R(0), syQx = R(0), syQy = R(0);
@@ -305,9 +318,9 @@ mh_step_march2(const StepArgs a, const __grid_constant__ TmaBlockMap maps) {
                 Le = ce + half * syE; Lh = ch + half * syH;
                 const R rL = Lh <= k.eps ? R(0) : fm_rcp(Lh);
                 Lun = (cqy + half * syQy) * rL; Lut = (cqx + half * syQx) * rL;
+                f_ew_prev = (f_w >> 1) | ((f_e >> 1) << 2);
+                f_m2 = f_m1; f_m1 = f_c; f_c = f_p;
             }
-            f_ew_prev = (f_w >> 1) | ((f_e >> 1) << 2);
-            f_m2 = f_m1; f_m1 = f_c; f_c = f_p;
             dr_m2 = dr_m1; dr_m1 = dr_c;
 
             // row j-1 is dead: refill its ring slot with row j-1+RR

@@ -296,3 +296,46 @@ def test_size_independent_properties_at_scale(ex):
     assert np.abs(eta - eta[::-1, :]).max() < 1e-9 and np.abs(eta - eta[:, ::-1]).max() < 1e-9
     assert np.abs(eta - eta.T).max() < 1e-9
     assert gpu.stats()["batch_successful"] == 100
+
+
+def test_handles_are_thread_safe(ex):
+    """The reference's main thread polls readKeyStatistics and reads cells back while the scheme's worker thread enqueues
+    batches (src/Schemes/CSchemeGodunov.cpp:1116-1141, CScheme.h:137-139): every entry point takes the handle's lock, so
+    concurrent use is safe and the result is the one of the same iterations issued serially."""
+    import threading
+    n = 256
+    cfg = make_cfg("muscl-hancock", "double", n, n)
+    bed, st, man = scenario("dambreak", n, n, np.float64)
+    serial = hx.CudaScheme(ex, cfg)
+    serial.upload(st, bed, man)
+    serial.set_target(1.0e6)
+    serial.iterate(240)
+    want, want_stats = serial.download(), serial.stats()
+    serial.close()
+
+    sim = hx.CudaScheme(ex, cfg)
+    sim.upload(st, bed, man)
+    sim.set_target(1.0e6)
+    errors, seen = [], []
+
+    def worker():
+        try:
+            for _ in range(60):
+                sim.iterate(4, sync=False)
+        except Exception as e:            # pragma: no cover
+            errors.append(e)
+
+    t = threading.Thread(target=worker)
+    t.start()
+    while t.is_alive():
+        s = sim.stats()                   # synchronous read of the device clock, racing the enqueues
+        seen.append((s["batch_successful"], s["time"]))
+        rows = sim.read_rows(n // 2, 2)   # CDomainLink-style partial read-back in the middle of a batch
+        assert np.isfinite(rows).all()
+    t.join()
+    sim.sync()
+    assert not errors, errors
+    assert all(b[0] >= a[0] and b[1] >= a[1] for a, b in zip(seen, seen[1:]))     # the clock only moves forward
+    assert sim.stats() == want_stats
+    np.testing.assert_array_equal(sim.download(), want)
+    sim.close()

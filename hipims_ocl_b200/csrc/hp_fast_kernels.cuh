@@ -126,9 +126,10 @@ __device__ __forceinline__ Flux3<R> face_core_flux(const Params<R>& k, R etaL, R
     const R hg = R(0.5) * k.g;
     const R zmax = fm_max(zL, zR);
     const R dL = etaL - zmax, dR = etaR - zmax;
-    if (dL > k.eps && dR > k.eps) {
+    if (__all_sync(__activemask(), dL > k.eps && dR > k.eps)) {
         // wet fast path: no clamps, no dry-side selects, no zero guard on the roots; the same operations the general
-        // path below performs when both depths exceed the threshold
+        // path below performs when both depths exceed the threshold.  Chosen by the lanes that are here together: a warp
+        // with a single dry side takes the general path as a whole instead of executing both.
         const R aL = (CACHED_CELERITY && zmax == zL) ? cL : fm_sqrt_pos(k.g * dL);
         const R aR = (CACHED_CELERITY && zmax == zR) ? cR : fm_sqrt_pos(k.g * dR);
         const R qnL = dL * unL, qnR = dR * unR;
@@ -383,7 +384,7 @@ godunov_step_tma(const StepArgs a, const __grid_constant__ TmaMaps maps) {
                             hnN = etaN - mN; hnS = etaS - mS; hnE = etaE - mE; hnW = etaW - mW;
                             const bool wet = hoN > k.eps && hoS > k.eps && hoE > k.eps && hoW > k.eps && hnN > k.eps && hnS > k.eps &&
                                              hnE > k.eps && hnW > k.eps;
-                            if (wet) {
+                            if (__all_sync(__activemask(), wet)) {
                                 bN = mN; bS = mS; bE = mE; bW = mW;
                             } else {
                                 face_owner_terms<R, true>(k, c.eta, zb, v, c.qy, etaN, zN, s_v[oN], bN, hnN, stop);

@@ -73,7 +73,7 @@ template <class R> struct FaceOut { R m, n, t, zmax, hL, hR; int stopL, stopR; }
 // CLSchemeMUSCLHancock.clc:1172-1204; they can only be non-zero at a wet/dry front).  qOwnL / qOwnR: the owning CELLS'
 // discharge normal to the face.  WET FAST PATH in front: when both reconstructed depths exceed the dry threshold (one
 // combined test) there are no stop flags, no dry-side selects, no clamps and the square roots need no zero guard --
-// with identical results, the general path takes exactly these operations then.
+// with identical results, the general path takes exactly these operations then.  Must be called by all 32 lanes.
 template <class R, bool CACHED>
 __device__ __forceinline__ void face_solve2(const Params<R>& k, R etaL, R zL, R unL, R utL, R aL_cached, R etaR, R zR, R unR, R utR,
                                             R aR_cached, R qOwnL, R qOwnR, FaceOut<R>& o) {
@@ -81,7 +81,9 @@ __device__ __forceinline__ void face_solve2(const Params<R>& k, R etaL, R zL, R 
     const R zmax = fm_max(zL, zR);
     const R dL = etaL - zmax, dR = etaR - zmax;
     o.zmax = zmax;
-    if (dL > k.eps && dR > k.eps) {
+    // warp-uniform choice (every lane reaches the faces together): a warp with a single dry side takes the general path
+    // as a whole instead of executing both -- on thin films over rough terrain most warps are mixed
+    if (__all_sync(0xffffffffu, dL > k.eps && dR > k.eps)) {
         o.hL = dL; o.hR = dR; o.stopL = 0; o.stopR = 0;
         const R aL = (CACHED && zmax == zL) ? aL_cached : fm_sqrt_pos(k.g * dL);
         const R aR = (CACHED && zmax == zR) ? aR_cached : fm_sqrt_pos(k.g * dR);

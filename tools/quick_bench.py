@@ -11,6 +11,9 @@ options = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 ex = hx.Executor(0)
 peak, _ = bench.peak_hbm()
 for name in names:
+    spin = None
+    if "@" in name:                      # name[:size]@T -- spin up until simulated time T (rain has fallen) before timing
+        name, spin = name.split("@")[0], float(name.split("@")[1])
     w = dict(bench.WORKLOADS[name.split(":")[0]])
     if ":" in name:
         w["cols"] = w["rows_per_gpu"] = int(name.split(":")[1])
@@ -22,6 +25,8 @@ for name in names:
     bench.attach_boundaries(sim, w, cfg.cols, cfg.rows)
     sim.set_target(1e7)
     sim.iterate(10)
+    while spin is not None and sim.stats()["time"] < spin:
+        sim.iterate(32)
     best = 0.0
     for rep in range(3):
         ex.timer_start()

@@ -18,6 +18,13 @@ bed, st, man = bench.make_inputs(w, cfg.rows, cfg.cols, dtype)
 ex = hx.Executor(0)
 sim = hx.CudaScheme(ex, cfg, options=options)
 sim.upload(st, bed, man)
+bench.attach_boundaries(sim, w, cfg.cols, cfg.rows)
 sim.set_target(1e7)
+if len(sys.argv) > 5:                       # spin-up: iterate until this simulated time (rain has fallen), then `iters` more
+    while sim.stats()["time"] < float(sys.argv[5]):
+        sim.iterate(16)
+    sim.sync()
+    import torch                            # ncu --profile-from-start off: only what follows is profiled
+    torch.cuda.cudart().cudaProfilerStart()
 sim.iterate(iters)
 print(sim.stats())

@@ -518,7 +518,7 @@ def main():
     assert np.isfinite(t_st.numpy()[..., 0]).all() and final.batch_successful > 0
 
     # ---- multi-GPU: where the strip iteration spends its time, and strips against one GPU ------------
-    phases, parity = None, None
+    phases, parity, single = None, None, None
     if world > 1:
         sim.strip_timing(True)
         sim.iterate(4, sync=True)
@@ -535,6 +535,26 @@ def main():
                           "the whole step and allreduce is the halo exchange + all-reduce NCCL group"}
         if not args.no_strip_parity:
             parity = strip_parity_check(hx, ex, dist, w, rank, world, args.options)
+        # the same per-GPU workload on ONE GPU (rank 0's, no communicator), same steps and warm-up: the denominator of the
+        # weak-scaling efficiency measured in the same run (the N = 1 default of this script is another workload)
+        if rank == 0:
+            sim.sync()
+            b1, s1, m1 = make_inputs(w, rows_own, cols, dtype, row_offset=0, total_rows=rows_own)
+            one = hx.CudaScheme(ex, cfg_for(w, rows_own, cols), options=args.options)
+            one.upload(s1, b1, m1)
+            del b1, s1, m1
+            attach_boundaries(one, w, cols, rows_own)
+            one.set_target(1.0e7)
+            one.prepare_graphs()
+            one.iterate(36 + args.warmup, sync=True)
+            ex.timer_start()
+            one.iterate(args.steps, sync=False)
+            ms1 = ex.timer_stop()
+            one.close()
+            single = {"value": cols * rows_own * args.steps / (ms1 * 1e-3), "unit": "cell-updates/s", "ms_per_step": ms1 / args.steps,
+                      "note": "one %d-row strip of the same workload on one GPU without a communicator, same steps; "
+                              "value / (n_gpus x this) is the weak-scaling efficiency" % rows_own}
+        dist.barrier()
 
     if rank == 0:
         peak, peak_src = peak_hbm()
@@ -574,6 +594,8 @@ def main():
         if parity:
             line["strip_parity"] = parity["verdict"]
             line["strip_parity_detail"] = parity
+        if single:
+            line["single_gpu_same_workload"] = single
         if not args.no_variants and world == 1 and args.workload is None:
             sim.close()
             del t_st, t_bed, t_man

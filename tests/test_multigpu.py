@@ -26,7 +26,8 @@ def run_check(world, *argv):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tools", "multigpu_check.py")] + [str(a) for a in argv]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
-    out = res.stdout + res.stderr
+    out = "\n".join(l for l in (res.stdout + res.stderr).splitlines()
+                    if l.strip() and not l.startswith("*****") and "OMP_NUM_THREADS" not in l)
     assert res.returncode == 0, out[-3000:]
     assert "state IDENTICAL" in out and "clocks IDENTICAL" in out, out[-3000:]
     return out

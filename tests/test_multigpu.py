@@ -28,8 +28,9 @@ def run_check(world, *argv):
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
     out = "\n".join(l for l in (res.stdout + res.stderr).splitlines()
                     if l.strip() and not l.startswith("*****") and "OMP_NUM_THREADS" not in l)
-    assert res.returncode == 0, out[-3000:]
-    assert "state IDENTICAL" in out and "clocks IDENTICAL" in out, out[-3000:]
+    verdict = [l for l in out.splitlines() if l.startswith("multigpu_check")]
+    assert res.returncode == 0, "\n".join(verdict) + "\n" + out[-2000:]
+    assert "state IDENTICAL" in out and "clocks IDENTICAL" in out, "\n".join(verdict) + "\n" + out[-2000:]
     return out
 
 
@@ -73,4 +74,4 @@ def test_eight_strips():
     if gpu_count() < 8:
         pytest.skip("needs eight GPUs")
     run_check(8, "muscl-hancock", "double", 1024, 512, 40, "cells", 0)
-    run_check(8, "godunov", "double", 1021, 512, 40, "cells", 0)
+    run_check(8, "godunov", "double", 1021, 512, 40, "rain", 0)      # rows that do not divide by the rank count

@@ -56,12 +56,17 @@ def main():
         ref.set_target(1e6)
         ref.iterate(iters)
         want = ref.download()
-        same_state = np.array_equal(full, want)
+        same_state = np.array_equal(full, want, equal_nan=True)
         same_clock = all(g[2] == ref.stats() for g in gathered)
-        err = float(np.abs(full - want).max())
+        err = float(np.nan_to_num(np.abs(full - want)).max())
         print("multigpu_check %s %s %dx%d x%d ranks, %d iterations, bdy=%s options=%d: state %s (max diff %.3e), clocks %s, t=%.6f" % (
             scheme, precision, rows, cols, world, iters, bdy, options, "IDENTICAL" if same_state else "DIFFERENT", err,
             "IDENTICAL" if same_clock else "DIFFERENT", ref.stats()["time"]))
+        if not same_state:
+            d = np.abs(full - want).max(axis=2)
+            ys, xs = np.nonzero(d > 0)
+            print("multigpu_check detail: %d cells differ, rows %s cols %s, strip height %d" % (
+                len(ys), np.unique(ys)[:24].tolist(), np.unique(xs)[:24].tolist(), rows // world))
         ok = same_state and same_clock
     dist.barrier()
     dist.destroy_process_group()

@@ -8,7 +8,7 @@ from hipims_ocl_b200 import executor as hx
 name = sys.argv[1] if len(sys.argv) > 1 else "dambreak4096"
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 6
 options = int(sys.argv[3]) if len(sys.argv) > 3 else hx.OPT_NO_GRAPH
-n = int(sys.argv[4]) if len(sys.argv) > 4 else None
+n = int(sys.argv[4]) if len(sys.argv) > 4 and int(sys.argv[4]) > 0 else None
 w = dict(bench.WORKLOADS[name])
 if n:
     w["cols"] = w["rows_per_gpu"] = n

@@ -31,7 +31,7 @@ for wl, cells in CELLS.items():
     def val(k):
         return float(r[hdr.index(k)].replace(",", ""))
     def scale(k):
-        return {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0, "usecond": 1e-3, "msecond": 1.0, "nsecond": 1e-6, "second": 1e3}[units[hdr.index(k)]]
+        return {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0, "usecond": 1e-3, "msecond": 1.0, "nsecond": 1e-6, "second": 1e3, "us": 1e-3, "ms": 1.0, "ns": 1e-6, "s": 1e3}[units[hdr.index(k)]]
     dram = (val("dram__bytes_read.sum") + val("dram__bytes_write.sum")) * scale("dram__bytes_read.sum")
     ops = {}
     for line in res.stdout.splitlines():

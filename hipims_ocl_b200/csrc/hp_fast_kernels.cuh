@@ -40,6 +40,27 @@ template <> __device__ __forceinline__ float fm_posdiff<float>(float a, float b)
 // |v| < eps => 0: the reference's "round delta values to zero if small" (CLSchemeGodunov.clc:340-348)
 template <class R> __device__ __forceinline__ R fm_chop(R v, R eps) { return hp_abs(v) < eps ? R(0) : v; }
 
+// ---- forms the compiler cannot turn into max.f64 / min.f64 ---------------------------------------------------------
+// NVVM rewrites `v > 0 ? v : 0` into max.f64 and `a < c || b < c` into `min.f64(a, b) < c`; on this part either one
+// becomes DSETP.MAX/MIN + five register moves + SEL + FSEL + LOP3 (NaN quieting) -- ten issue slots for what a compare
+// and two selects do (profiles/r02_pluvial16384.txt: six of them per cell-update, ~5 % of the kernel's issue cycles).
+// Non-negative part by the sign bit (-0 and negative values give +0 like the comparison form; no NaNs reach it):
+__device__ __forceinline__ double fm_pos_s(double v) { return __double2hiint(v) < 0 ? 0.0 : v; }
+__device__ __forceinline__ float fm_pos_s(float v) { return fmaxf(v, 0.0f); }
+// a < b as an opaque predicate (kept out of the min/max pattern matcher)
+__device__ __forceinline__ bool fm_lt_opaque(double a, double b) {
+    int r;
+    asm("{\n\t.reg .pred p;\n\tsetp.lt.f64 p, %1, %2;\n\tselp.s32 %0, 1, 0, p;\n\t}" : "=r"(r) : "d"(a), "d"(b));
+    return r != 0;
+}
+__device__ __forceinline__ bool fm_lt_opaque(float a, float b) { return a < b; }
+__device__ __forceinline__ bool fm_le_opaque(double a, double b) {
+    int r;
+    asm("{\n\t.reg .pred p;\n\tsetp.le.f64 p, %1, %2;\n\tselp.s32 %0, 1, 0, p;\n\t}" : "=r"(r) : "d"(a), "d"(b));
+    return r != 0;
+}
+__device__ __forceinline__ bool fm_le_opaque(float a, float b) { return a <= b; }
+
 // ---------------------------------------------------------------------------------------------
 // TMA / mbarrier primitives
 // ---------------------------------------------------------------------------------------------
@@ -119,6 +140,10 @@ __device__ __forceinline__ float fm_sqrt_pos(float a) {
     const float g = a * y, h = 0.5f * y;
     return fmaf(fmaf(-g, g, a), h, g);
 }
+// sqrt(g h) for h >= 0 without a zero guard: the radicand is lifted by a denormal-free tiny constant inside the
+// multiply-add, so h = 0 yields 1e-150 (fp32: 3e-19) instead of 0 * inf -- absorbed by every sum it enters
+__device__ __forceinline__ double fm_celerity(double g, double h) { return fm_sqrt_pos(fma(g, h, 1.0e-300)); }
+__device__ __forceinline__ float fm_celerity(float g, float h) { return fm_sqrt_pos(fmaf(g, h, 1.0e-37f)); }
 
 template <class R, bool CACHED_CELERITY = true>
 __device__ __forceinline__ Flux3<R> face_core_flux(const Params<R>& k, R etaL, R zL, R unL, R utL, R cL, R etaR, R zR, R unR,
@@ -146,8 +171,8 @@ __device__ __forceinline__ Flux3<R> face_core_flux(const Params<R>& k, R etaL, R
         const R f2 = (sR * FLn - sL * FRn + ss * (qnR - qnL)) * inv;
         return Flux3<R>{f1, f2, f1 * (f1 >= R(0) ? utL : utR)};
     }
-    const R hL = dL > R(0) ? dL : R(0);
-    const R hR = dR > R(0) ? dR : R(0);
+    const R hL = fm_pos_s(dL);
+    const R hR = fm_pos_s(dR);
     const bool dryL = hL < k.eps, dryR = hR < k.eps;
     if (dryL && dryR) {
         const R hm = R(0.5) * (hL + hR);
@@ -156,8 +181,8 @@ __device__ __forceinline__ Flux3<R> face_core_flux(const Params<R>& k, R etaL, R
     if (dryL) { unL = R(0); utL = R(0); }
     if (dryR) { unR = R(0); utR = R(0); }
     // celerity: the cell's own sqrt(g h) is reused whenever the face sits on the cell's own bed
-    const R aL = (CACHED_CELERITY && zmax == zL) ? cL : fm_sqrt(k.g * hL);
-    const R aR = (CACHED_CELERITY && zmax == zR) ? cR : fm_sqrt(k.g * hR);
+    const R aL = (CACHED_CELERITY && zmax == zL) ? cL : fm_celerity(k.g, hL);
+    const R aR = (CACHED_CELERITY && zmax == zR) ? cR : fm_celerity(k.g, hR);
     const R qnL = hL * unL, qnR = hR * unR;
     const R as = hp_abs(R(0.5) * (aL + aR) + R(0.25) * (unL - unR));     // sqrt(g h*) without the sqrt
     const R us = R(0.5) * (unL + unR) + aL - aR;
@@ -188,7 +213,7 @@ __device__ __forceinline__ void face_owner_terms(const Params<R>& k, R etaOwn, R
     const R hOwn = fm_posdiff(etaOwn, zmax);
     hNb = fm_posdiff(etaNb, zmax);
     bed = fm_min(zmax, etaOwn);                                  // zmax - max(0, zmax - eta_own)
-    if (hOwn <= k.eps || hNb <= k.eps) {                                  // only possible at wet/dry fronts
+    if (fm_le_opaque(hOwn, k.eps) | fm_le_opaque(hNb, k.eps)) {           // only possible at wet/dry fronts
         const R hL = ownIsLeft ? hOwn : hNb, hR = ownIsLeft ? hNb : hOwn;
         const R unL = ownIsLeft ? unOwn : unNb, unR = ownIsLeft ? unNb : unOwn;
         if (ownIsLeft) { if (hL <= k.eps && ownQn > R(0)) ++stop; }
@@ -203,7 +228,7 @@ __device__ __forceinline__ void face_owner_terms(const Params<R>& k, R etaOwn, R
 template <class R> __device__ __forceinline__ void friction_fast(const Params<R>& k, R h, R rh, R& qx, R& qy, R n, R dt) {
     const R q2 = qx * qx + qy * qy;
     const R q = fm_sqrt(q2);
-    if (h < k.eps || q < k.eps) return;
+    if (fm_lt_opaque(h, k.eps) | fm_lt_opaque(q, k.eps)) return;
     const R A = dt * k.g * n * n * rh * rh * fm_rcbrt(h);                 // dt * Cf / h^2
     const R aq2 = A * q2;
     qx = qx - qx * aq2 * fm_rcp(q + A * (q2 + qx * qx));
@@ -313,7 +338,7 @@ godunov_step_tma(const StepArgs a, const __grid_constant__ TmaMaps maps) {
             const R rh = wet ? fm_rcp(h) : R(0);
             s_u[o] = t_qx[o] * rh;
             s_v[o] = t_qy[o] * rh;
-            s_c[o] = fm_sqrt(k.g * fm_pos(h));
+            s_c[o] = fm_celerity(k.g, fm_pos_s(h));
         }
         __syncthreads();
 
@@ -504,6 +529,16 @@ __device__ __forceinline__ double minmod(double a, double b) {
 __device__ __forceinline__ float minmod(float a, float b) {
     const float t = fabsf(b) < fabsf(a) ? b : a;
     return ((__float_as_int(a) ^ __float_as_int(b)) < 0) ? 0.0f : t;
+}
+// ... with a switch: `off` is 0, or has its sign bit set to drop the slope altogether (a dry neighbour in that
+// direction, CLSchemeMUSCLHancock.clc:301-320) -- it rides along in the sign test's LOP3 for free
+__device__ __forceinline__ double minmod_sw(double a, double b, int off) {
+    const double t = fabs(b) < fabs(a) ? b : a;
+    return (((__double2hiint(a) ^ __double2hiint(b)) | off) < 0) ? 0.0 : t;
+}
+__device__ __forceinline__ float minmod_sw(float a, float b, int off) {
+    const float t = fabsf(b) < fabsf(a) ? b : a;
+    return (((__float_as_int(a) ^ __float_as_int(b)) | off) < 0) ? 0.0f : t;
 }
 
 template <class R>

@@ -74,9 +74,9 @@ template <class R> struct FaceOut { R m, n, t, zmax, hL, hR; int stopL, stopR; }
 // discharge normal to the face.  WET FAST PATH in front: when both reconstructed depths exceed the dry threshold (one
 // combined test) there are no stop flags, no dry-side selects, no clamps and the square roots need no zero guard --
 // with identical results, the general path takes exactly these operations then.  Must be called by all 32 lanes.
-template <class R, bool CACHED>
+template <class R, bool CACHED, class QOwnL, class QOwnR>
 __device__ __forceinline__ void face_solve2(const Params<R>& k, R etaL, R zL, R unL, R utL, R aL_cached, R etaR, R zR, R unR, R utR,
-                                            R aR_cached, R qOwnL, R qOwnR, FaceOut<R>& o) {
+                                            R aR_cached, QOwnL qOwnL, QOwnR qOwnR, FaceOut<R>& o) {
     const R hg = R(0.5) * k.g;
     const R zmax = fm_max(zL, zR);
     const R dL = etaL - zmax, dR = etaR - zmax;
@@ -103,14 +103,16 @@ __device__ __forceinline__ void face_solve2(const Params<R>& k, R etaL, R zL, R 
         return;
     }
     // ---- general path: a dry side, stop flags (wet/dry fronts only) --------------------------------
-    const R hL = dL > R(0) ? dL : R(0), hR = dR > R(0) ? dR : R(0);
+    const R hL = fm_pos_s(dL), hR = fm_pos_s(dR);
     o.hL = hL; o.hR = hR;
     {
+        // qOwnL() / qOwnR() are evaluated here only: the wet path above never needs the owners' raw discharge, so a
+        // caller that can re-read it (from its ring) does not have to keep it in registers across its predictor
         int both = 0;
         if (hR <= k.eps && unL < R(0)) ++both;
         if (hL <= k.eps && unR > R(0)) ++both;
-        o.stopL = both + ((hL <= k.eps && qOwnL > R(0)) ? 1 : 0);
-        o.stopR = both + ((hR <= k.eps && qOwnR < R(0)) ? 1 : 0);
+        o.stopL = both + ((hL <= k.eps && qOwnL() > R(0)) ? 1 : 0);
+        o.stopR = both + ((hR <= k.eps && qOwnR() < R(0)) ? 1 : 0);
     }
     const bool dryL = hL < k.eps, dryR = hR < k.eps;
     if (dryL && dryR) {
@@ -120,8 +122,8 @@ __device__ __forceinline__ void face_solve2(const Params<R>& k, R etaL, R zL, R 
     }
     if (dryL) { unL = R(0); utL = R(0); }
     if (dryR) { unR = R(0); utR = R(0); }
-    const R aL = (CACHED && zmax == zL) ? aL_cached : fm_sqrt(k.g * hL);
-    const R aR = (CACHED && zmax == zR) ? aR_cached : fm_sqrt(k.g * hR);
+    const R aL = (CACHED && zmax == zL) ? aL_cached : fm_celerity(k.g, hL);
+    const R aR = (CACHED && zmax == zR) ? aR_cached : fm_celerity(k.g, hR);
     const R qnL = hL * unL, qnR = hR * unR;
     const R as = hp_abs(R(0.5) * (aL + aR) + R(0.25) * (unL - unR));
     const R us = R(0.5) * (unL + unR) + aL - aR;
@@ -245,7 +247,7 @@ godunov_step_march(const StepArgs a, const __grid_constant__ TmaBlockMap maps) {
             const R h = o.eta - o.zb;
             const R rh = !(h < k.eps) ? fm_rcp(h) : R(0);
             o.u = qx * rh; o.v = qy * rh;
-            o.c = fm_sqrt(k.g * fm_pos(h));
+            o.c = fm_celerity(k.g, fm_pos_s(h));
         };
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
@@ -276,7 +278,7 @@ godunov_step_march(const StepArgs a, const __grid_constant__ TmaBlockMap maps) {
             }
 
             FaceOut<R> fy;
-            if (stepping) face_solve2<R, true>(k, P.eta, P.zb, P.v, P.u, P.c, C.eta, C.zb, C.v, C.u, C.c, p_qy, c_qy, fy);
+            if (stepping) face_solve2<R, true>(k, P.eta, P.zb, P.v, P.u, P.c, C.eta, C.zb, C.v, C.u, C.c, [&] { return p_qy; }, [&] { return c_qy; }, fy);
             else { fy.m = fy.n = fy.t = fy.zmax = fy.hL = fy.hR = R(0); fy.stopL = fy.stopR = 0; }
 
             if (j >= 2) {
@@ -302,7 +304,7 @@ godunov_step_march(const StepArgs a, const __grid_constant__ TmaBlockMap maps) {
                 const unsigned drym = __ballot_sync(FULL, dry_p);
                 FaceOut<R> fx;
                 if (stepping) face_solve2<R, true>(k, ld(o_m, T::P_ETA, lw), ld(o_m, T::P_ZB, lw), wU, wV, wC, P.eta, P.zb, P.u, P.v, P.c,
-                                            ld(o_m, T::P_QX, lw), p_qx, fx);
+                                            [&] { return ld(o_m, T::P_QX, lw); }, [&] { return p_qx; }, fx);
                 else { fx.m = fx.n = fx.t = fx.zmax = fx.hL = fx.hR = R(0); fx.stopL = fx.stopR = 0; }
                 const R eM = shfl_dn1(fx.m), eN = shfl_dn1(fx.n), eT = shfl_dn1(fx.t), eZ = shfl_dn1(fx.zmax), eH = shfl_dn1(fx.hR);
                 const int eStop = __shfl_down_sync(FULL, fx.stopL, 1);

@@ -76,6 +76,18 @@ mh_step_march2(const StepArgs a, const __grid_constant__ TmaBlockMap maps) {
         return *reinterpret_cast<const R*>(ring + row_off + plane * T::PLANE + col_off);
     };
     auto flags_of = [&](R em) -> int { return (em <= R(-9998.0) ? 1 : 0) | (em < k.eps ? 2 : 0); };
+    // bit 0 of flags_of alone, for the columns beyond the edge lanes (their bit 1 only enters the corrector of a halo
+    // lane, which stores nothing).  -9998.0 has a zero low word: the test is one unsigned compare of the high word
+    auto disabled_at = [&](int row_off, int col_off) -> int {
+        if constexpr (sizeof(R) == 8)
+            return *reinterpret_cast<const unsigned*>(ring + row_off + T::P_EMAX * T::PLANE + col_off + 4) >= 0xC0C38700u ? 1 : 0;
+        else
+            return *reinterpret_cast<const R*>(ring + row_off + T::P_EMAX * T::PLANE + col_off) <= R(-9998.0) ? 1 : 0;
+    };
+    // re-read of a raw value the predictor has overwritten in registers (only wet/dry fronts ask for it)
+    auto ld_again = [&](int row_off, int plane, int col_off) -> R {
+        return *reinterpret_cast<const volatile R*>(ring + row_off + plane * T::PLANE + col_off);
+    };
     const bool lane_owns = lane >= 1 && lane < 1 + T::USE;
     // wave speed of a stored cell for the CFL reduction (CLDynamicTimestep.clc:81-110); rh = 1/h if the caller has it
     auto speed_of = [&](R h, R qx, R qy, R rh) -> R {
@@ -198,8 +210,8 @@ mh_step_march2(const StepArgs a, const __grid_constant__ TmaBlockMap maps) {
                 }
                 const int f_p = flags_of(ld(o_p, T::P_EMAX, lc));
                 int f_w = __shfl_up_sync(FULL, f_c, 1), f_e = __shfl_down_sync(FULL, f_c, 1);
-                if (lane == 0) f_w = flags_of(ld(o_c, T::P_EMAX, lw));          // the columns beyond the edge lanes have no lane
-                if (lane == 31) f_e = flags_of(ld(o_c, T::P_EMAX, le));
+                if (lane == 0) f_w = disabled_at(o_c, lw);                      // the columns beyond the edge lanes have no lane
+                if (lane == 31) f_e = disabled_at(o_c, le);
                 // ---- predictor of row y (CLSchemeMUSCLHancock.clc:301-382) ---------------------------
                 R ce = eta, cqx = qx, cqy = qy;
                 R sxE = R(0), sxH = R(0), sxQx = R(0), sxQy = R(0), syE = R(0), syH = R(0), syQx = R(0), syQy = R(0);
@@ -210,16 +222,16 @@ mh_step_march2(const StepArgs a, const __grid_constant__ TmaBlockMap maps) {
                         const R etaE = ld(o_c, T::P_ETA, le), etaW = ld(o_c, T::P_ETA, lw), etaN = ld(o_p, T::P_ETA, lc), etaS = ld(o_m, T::P_ETA, lc);
                         const R hE = etaE - ld(o_c, T::P_ZB, le), hW = etaW - ld(o_c, T::P_ZB, lw);
                         const R hN = etaN - ld(o_p, T::P_ZB, lc), hS = etaS - ld(o_m, T::P_ZB, lc);
-                        if (!(hW < k.eps || hE < k.eps)) {
-                            sxE = minmod(eta - etaW, etaE - eta); sxH = minmod(h - hW, hE - h);
-                            sxQx = minmod(qx - ld(o_c, T::P_QX, lw), ld(o_c, T::P_QX, le) - qx);
-                            sxQy = minmod(qy - ld(o_c, T::P_QY, lw), ld(o_c, T::P_QY, le) - qy);
-                        }
-                        if (!(hS < k.eps || hN < k.eps)) {
-                            syE = minmod(eta - etaS, etaN - eta); syH = minmod(h - hS, hN - h);
-                            syQx = minmod(qx - ld(o_m, T::P_QX, lc), ld(o_p, T::P_QX, lc) - qx);
-                            syQy = minmod(qy - ld(o_m, T::P_QY, lc), ld(o_p, T::P_QY, lc) - qy);
-                        }
+                        // a dry neighbour drops the slopes of its direction (:301-320): no branch, the switch rides in the
+                        // limiter's sign test (where this block runs at all, both directions are almost always kept)
+                        const int xoff = (fm_lt_opaque(hW, k.eps) | fm_lt_opaque(hE, k.eps)) ? int(0x80000000u) : 0;
+                        const int yoff = (fm_lt_opaque(hS, k.eps) | fm_lt_opaque(hN, k.eps)) ? int(0x80000000u) : 0;
+                        sxE = minmod_sw(eta - etaW, etaE - eta, xoff); sxH = minmod_sw(h - hW, hE - h, xoff);
+                        sxQx = minmod_sw(qx - ld(o_c, T::P_QX, lw), ld(o_c, T::P_QX, le) - qx, xoff);
+                        sxQy = minmod_sw(qy - ld(o_c, T::P_QY, lw), ld(o_c, T::P_QY, le) - qy, xoff);
+                        syE = minmod_sw(eta - etaS, etaN - eta, yoff); syH = minmod_sw(h - hS, hN - h, yoff);
+                        syQx = minmod_sw(qx - ld(o_m, T::P_QX, lc), ld(o_p, T::P_QX, lc) - qx, yoff);
+                        syQy = minmod_sw(qy - ld(o_m, T::P_QY, lc), ld(o_p, T::P_QY, lc) - qy, yoff);
                         // Face depths h +- s/2 with |s| <= |h - h_neighbour| and both >= 0: never below h/2 >= 5e-6, so the
                         // reference's `face depth < VERY_SMALL => zero velocity` (:333-346) cannot fire here.
                         const R hEf = h + half * sxH, hWf = h - half * sxH, hNf = h + half * syH, hSf = h - half * syH;
@@ -245,7 +257,8 @@ mh_step_march2(const StepArgs a, const __grid_constant__ TmaBlockMap maps) {
                     const R hfR = ch - half * syH;
                     const R rR = hfR <= k.eps ? R(0) : fm_rcp(hfR);                              // :1140-1150
                     face_solve2<R, false>(k, Le, Le - Lh, Lun, Lut, R(0), etaR, etaR - hfR, (cqy - half * syQy) * rR,
-                                          (cqx - half * syQx) * rR, R(0), ld(o_m, T::P_QY, lc), qy, fy);
+                                          (cqx - half * syQx) * rR, R(0), [&] { return ld_again(o_m, T::P_QY, lc); },
+                                          [&] { return ld_again(o_c, T::P_QY, lc); }, fy);
                     if (j >= 3) {
                         // ---- corrector of row y-1 (CLSchemeMUSCLHancock.clc:596-800) -----------------
                         const int gyc = gy - 1;
@@ -301,7 +314,8 @@ mh_step_march2(const StepArgs a, const __grid_constant__ TmaBlockMap maps) {
                     const R rR = hfR <= k.eps ? R(0) : fm_rcp(hfR);
                     FaceOut<R> fx;
                     face_solve2<R, false>(k, etaL, etaL - hfL, uL, vL, R(0), xw_eta, xw_eta - hfR, (cqx - half * sxQx) * rR,
-                                          (cqy - half * sxQy) * rR, R(0), ld(o_c, T::P_QX, lw), qx, fx);
+                                          (cqy - half * sxQy) * rR, R(0), [&] { return ld_again(o_c, T::P_QX, lw); },
+                                          [&] { return ld_again(o_c, T::P_QX, lc); }, fx);
                     // the east face comes back from lane+1
                     const R eM = shfl_dn1(fx.m), eN = shfl_dn1(fx.n), eT = shfl_dn1(fx.t), eZ = shfl_dn1(fx.zmax), eH = shfl_dn1(fx.hR);
                     const int eStop = __shfl_down_sync(FULL, fx.stopL, 1);

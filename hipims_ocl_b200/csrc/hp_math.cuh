@@ -116,14 +116,21 @@ __device__ __forceinline__ float fm_sqrt(float a) {
     g = fmaf(d, h, g);
     return a > 0.0f ? g : 0.0f;
 }
-// a^(-1/3) for a > 0: single-precision seed (MUFU lg2/ex2) + two Newton steps y <- y (4 - a y^3) / 3
+// a^(-1/3) for a > 0: single-precision seed (MUFU lg2/ex2) refined in double precision
 __device__ __forceinline__ double fm_rcbrt(double a) {
     double y = static_cast<double>(exp2f(-0.333333343f * __log2f(static_cast<float>(a))));
+#if HP_FM_HALLEY
+    // the seed is good to ~2e-7 (MUFU lg2 / ex2); with e = 1 - a y^3, a^(-1/3) = y (1 - e)^(-1/3) =
+    // y (1 + e/3 + 2/9 e^2 + O(e^3)): one third-order step, six operations instead of nine
+    const double e = fma(-(a * y), y * y, 1.0);
+    return fma(y * e, fma(e, 0.22222222222222222, 0.33333333333333333), y);
+#else
     double t = y * y * y;
     y = y * fma(-0.33333333333333333 * a, t, 1.3333333333333333);
     t = y * y * y;
     y = y * fma(-0.33333333333333333 * a, t, 1.3333333333333333);
     return y;
+#endif
 }
 __device__ __forceinline__ float fm_rcbrt(float a) { return rcbrtf(a); }
 

@@ -170,7 +170,9 @@ int enqueue_iteration(hp_scheme* s, bool alt, int* launched) {
     // the NCCL send/recv kernels of the halo exchange can run beside it instead of after it
     auto step = [&](const hp::StepArgs& args, int spare_sms = 0) {
         const int sms = s->ex->prop.multiProcessorCount - spare_sms > 0 ? s->ex->prop.multiProcessorCount - spare_sms : 1;
-        if (s->use_march) return s->K->step_march(static_cast<int>(s->cfg.scheme), rb, args, &s->march_map, alt ? 1 : 0, sms, st);
+        if (s->use_march)
+            return s->K->step_march(static_cast<int>(s->cfg.scheme), rb, args, &s->march_map,
+                                    (alt ? 1 : 0) | ((s->cfg.options & HP_OPT_NARROW_MARCH) ? 2 : 0), sms, st);
         if (s->use_tma) return s->K->step_tma(static_cast<int>(s->cfg.scheme), rb, args, alt ? &s->maps_b : &s->maps_a, sms, st);
         return s->K->step(static_cast<int>(s->cfg.scheme), rb, args, st);
     };
@@ -300,7 +302,8 @@ int build_tma_maps(hp_scheme* s) {
     const int rbi = static_cast<int>(s->rb);
     if (s->use_march) {
         // marching kernels: one 3-D descriptor over the ten-plane block; a box is one row of six planes
-        return encode_plane_map(s->march_map.bytes[0], s->block, s->grid, s->rb, hp::march_box_w(rbi, 1), 1, 10, s->plane_bytes, 6);
+        const int box_w = s->K->march_box_w(static_cast<int>(s->cfg.scheme), rbi, (s->cfg.options & HP_OPT_NARROW_MARCH) ? 1 : 0);
+        return encode_plane_map(s->march_map.bytes[0], s->block, s->grid, s->rb, box_w, 1, 10, s->plane_bytes, 6);
     }
     const int w = hp::tma_box_w(rbi, halo), h = hp::tma_box_h(halo);
     for (int b = 0; b < 2; ++b) {

@@ -447,6 +447,7 @@ template <class R> __global__ void __launch_bounds__(256) derive_raster_kernel(P
 #include "hp_fast_kernels.cuh"
 #include "hp_march_kernels.cuh"
 #include "hp_march_mh.cuh"
+#include "hp_march_pair.cuh"
 #endif
 
 namespace HP_NS {
@@ -465,8 +466,17 @@ static int launch_step_tma(int scheme, int real_bytes, const StepArgs& a, const 
     return -1;
 }
 static_assert(sizeof(TmaBlockMap) == sizeof(hp::TmaMaps6POD), "descriptor block layout");
-static int launch_step_march(int scheme, int real_bytes, const StepArgs& a, const hp::TmaMaps6POD* maps, int alt, int sm_count, cudaStream_t st) {
+// which (scheme, precision) pairs have a two-columns-per-lane kernel
+static bool has_wide(int scheme, int real_bytes) { (void)real_bytes; return scheme == 2; }
+static int march_box_w(int scheme, int real_bytes, int narrow) {
+    return (!narrow && has_wide(scheme, real_bytes)) ? hp::wide_box_w(real_bytes) : hp::march_box_w(real_bytes, 1);
+}
+static int launch_step_march(int scheme, int real_bytes, const StepArgs& a, const hp::TmaMaps6POD* maps, int alt_bits, int sm_count, cudaStream_t st) {
     const TmaBlockMap& m = *reinterpret_cast<const TmaBlockMap*>(maps);
+    const int alt = alt_bits & 1;
+    if (!(alt_bits & 2) && has_wide(scheme, real_bytes)) {
+        if (scheme == 2) return real_bytes == 8 ? launch_inertial_wide<double>(a, m, alt, sm_count, st) : launch_inertial_wide<float>(a, m, alt, sm_count, st);
+    }
     if (scheme == 0) return real_bytes == 8 ? launch_godunov_march<double>(a, m, alt, sm_count, st) : launch_godunov_march<float>(a, m, alt, sm_count, st);
     if (scheme == 1) return real_bytes == 8 ? launch_mh_march2<double>(a, m, alt, sm_count, st) : launch_mh_march2<float>(a, m, alt, sm_count, st);
     if (scheme == 2) return real_bytes == 8 ? launch_inertial_march<double>(a, m, alt, sm_count, st) : launch_inertial_march<float>(a, m, alt, sm_count, st);
@@ -570,9 +580,9 @@ static int launch_derive_raster(int real_bytes, Planes src, const void* bed, dou
 
 static const hp::KernelTable g_table = {
 #ifndef HP_FLAVOUR_STRICT
-    launch_step_tma, launch_step_march,
+    launch_step_tma, launch_step_march, march_box_w,
 #else
-    nullptr, nullptr,
+    nullptr, nullptr, nullptr,
 #endif
     launch_step, launch_reduce_only, launch_advance, launch_update_timestep, launch_bdy_uniform, launch_bdy_gridded,
     launch_bdy_cell, launch_aos_to_soa, launch_soa_to_aos, launch_copy_plane_rows, launch_derive_raster,

@@ -91,13 +91,20 @@ constexpr int march_box_w(int real_bytes, int halo) {
     const int a16 = 16 / real_bytes, padl = ((-halo) % a16 + a16) % a16;
     return (32 + padl + a16 - 1) / a16 * a16;
 }
+// "Wide" marching kernels (hp_march_pair.cuh): two adjacent columns per lane, one warp per 64-column strip of which
+// 60 are updated; box = {wide_box_w, 1, 6} of the same descriptor layout.
+constexpr int kWideUse = 60;
+constexpr int wide_box_w(int real_bytes) { return real_bytes == 8 ? 64 : 68; }
 
 // The launch interface of one compiled flavour (strict / fast).
 struct KernelTable {
     // TMA-staged step (fast flavour only, NULL otherwise); returns -1 if the scheme has no such kernel
     int (*step_tma)(int scheme, int real_bytes, const StepArgs& a, const TmaMapsPOD* maps, int sm_count, cudaStream_t st);
     // marching step (fast flavour only, NULL otherwise); returns -1 if the scheme has no such kernel
+    // alt: bit 0 = the step reads buffer B, bit 1 = one column per lane even where a wide kernel exists
     int (*step_march)(int scheme, int real_bytes, const StepArgs& a, const TmaMaps6POD* maps, int alt, int sm_count, cudaStream_t st);
+    // columns of the TMA box the marching kernel of (scheme, precision) expects
+    int (*march_box_w)(int scheme, int real_bytes, int narrow);
     // returns the number of kernels launched
     int (*step)(int scheme, int real_bytes, const StepArgs& a, cudaStream_t st);
     int (*reduce_only)(int real_bytes, const StepArgs& a, cudaStream_t st);       // tst_Reduce

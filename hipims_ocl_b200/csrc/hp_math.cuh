@@ -117,8 +117,16 @@ __device__ __forceinline__ float fm_sqrt(float a) {
     return a > 0.0f ? g : 0.0f;
 }
 // a^(-1/3) for a > 0: single-precision seed (MUFU lg2/ex2) refined in double precision
+// 2^(-lg2(a) / 3) straight from the MUFU units: the callers' arguments are depths above the dry threshold (1e-10) and
+// far below 2^126, so neither lg2's denormal scaling nor ex2's range reduction (what exp2f adds) can be needed
+__device__ __forceinline__ float fm_rcbrt_seed(float a) {
+    float l, y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(a));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(-0.333333343f * l));
+    return y;
+}
 __device__ __forceinline__ double fm_rcbrt(double a) {
-    double y = static_cast<double>(exp2f(-0.333333343f * __log2f(static_cast<float>(a))));
+    double y = static_cast<double>(fm_rcbrt_seed(static_cast<float>(a)));
 #if HP_FM_HALLEY
     // the seed is good to ~2e-7 (MUFU lg2 / ex2); with e = 1 - a y^3, a^(-1/3) = y (1 - e)^(-1/3) =
     // y (1 + e/3 + 2/9 e^2 + O(e^3)): one third-order step, six operations instead of nine

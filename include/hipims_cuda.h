@@ -77,8 +77,11 @@ enum {
                                       the default marching kernel (one warp per column strip)      */
     HP_OPT_MARCH_GODUNOV = 1u << 4, /* Godunov: use the marching kernel instead of the default TMA tile
                                       kernel (equal on wet domains, slower on mostly dry ones)     */
-    HP_OPT_SPLIT_STRIPS = 1u << 5  /* row strips: always split a step into edge rows + interior rows with
+    HP_OPT_SPLIT_STRIPS = 1u << 5, /* row strips: always split a step into edge rows + interior rows with
                                       the halo exchange overlapped (default only for large strips) */
+    HP_OPT_NARROW_MARCH = 1u << 6  /* marching kernels: one column per lane even where a two-column
+                                      ("wide") kernel exists -- the kernels the wide ones are checked
+                                      against                                                      */
 };
 
 /*

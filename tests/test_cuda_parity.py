@@ -127,9 +127,10 @@ TOLERANCE_CASES = [
 ]
 
 
-# "fast" runs the default kernels (Godunov: TMA tiles, MUSCL-Hancock: marching warps), "fast-other" the other
+# "fast" runs the default kernels (Godunov: TMA tiles, MUSCL-Hancock: marching warps, inertial: wide marching warps
+# with two columns per lane), "fast-other" the other
 # kernel of each scheme (Godunov marching, MUSCL-Hancock tiles)
-OTHER_KERNELS = hx.OPT_TILE_KERNELS | hx.OPT_MARCH_GODUNOV
+OTHER_KERNELS = hx.OPT_TILE_KERNELS | hx.OPT_MARCH_GODUNOV | hx.OPT_NARROW_MARCH
 
 
 @pytest.mark.parametrize("options", [hx.OPT_STRICT_FP, 0, hx.OPT_NO_GRAPH, OTHER_KERNELS], ids=["strict", "fast", "fast-nograph", "fast-other"])

@@ -79,6 +79,7 @@ def check(cfg, orc, gpu, bed, st, iters):
 
 
 MARCH = hx.OPT_MARCH_GODUNOV
+NARROW = hx.OPT_NARROW_MARCH                 # one column per lane where the default is the two-column ("wide") kernel
 
 # (workload, rows, cols, options, start time): rows x cols chosen so that march_runs >= 2 for that kernel's grid
 WRAP_CASES = [
@@ -87,6 +88,8 @@ WRAP_CASES = [
     pytest.param("river32768", 4096, 4096, 0, 700.0, id="mh-f64-river-cells"),                # configs[4] cropped
     pytest.param("dambreak4096-inertial", 4096, 4096, 0, None, id="inertial-f64-dambreak"),
     pytest.param("dambreak4096-inertial-f32", 4096, 4096, 0, None, id="inertial-f32-dambreak"),
+    pytest.param("dambreak4096-inertial", 4096, 4096, NARROW, None, id="inertial-narrow-f64-dambreak"),
+    pytest.param("dambreak4096-inertial-f32", 4096, 4096, NARROW, None, id="inertial-narrow-f32-dambreak"),
     pytest.param("dambreak4096", 3072, 4096, MARCH, None, id="godunov-march-f64-dambreak"),
     pytest.param("dambreak4096-f32", 3072, 4096, MARCH, None, id="godunov-march-f32-dambreak"),
     # the tile kernel: 1024 x 1536 = 32 x 192 = 6144 tiles > 888 (fp64) / 1332 (fp32) resident CTAs
@@ -105,8 +108,8 @@ def test_wrapping_kernels_match_the_oracle(ex, workload, rows, cols, options, t0
     orc.close()
 
 
-@pytest.mark.parametrize("scheme,options", [("godunov", 0), ("godunov", MARCH), ("muscl-hancock", 0), ("inertial", 0)],
-                         ids=["godunov-tiles", "godunov-march", "mh-march", "inertial-march"])
+@pytest.mark.parametrize("scheme,options", [("godunov", 0), ("godunov", MARCH), ("muscl-hancock", 0), ("inertial", 0), ("inertial", NARROW)],
+                         ids=["godunov-tiles", "godunov-march", "mh-march", "inertial-wide", "inertial-narrow"])
 def test_wrapping_kernels_on_wet_dry_terrain(ex, scheme, options):
     """Random rough terrain with wet and dry patches, fronts everywhere (the adversarial generator of the small parity
     cases) at a size where the persistent loops wrap: every dry-side / stop-flag / stale-destination branch next to a
@@ -223,3 +226,35 @@ def test_configs3_combination(ex):
     assert (out[..., 0].astype(np.float64) - bed).sum() > (st[..., 0].astype(np.float64) - bed).sum()
     gpu.close()
     orc.close()
+
+
+@pytest.mark.parametrize("workload", ["dambreak4096-inertial", "dambreak4096-inertial-f32", "radar16384"])
+def test_wide_and_narrow_marching_kernels_agree(ex, workload):
+    """The two-columns-per-lane ("wide") kernels evaluate, component by component, the expression tree of the
+    one-column kernels they replace; only where the compiler contracts a product and a sum differently can the last
+    bit differ.  Ragged sizes (columns not a multiple of 60, 30 or 28), boundaries attached, 25 iterations."""
+    rows, cols, iters = 1500, 1999, 25
+    w = crop(workload, rows, cols)
+    cfg = bench.cfg_for(w, rows, cols)
+    dtype = np.float64 if cfg.precision == "double" else np.float32
+    bed, st, man = bench.make_inputs(w, rows, cols, dtype)
+    out = []
+    for options in (0, NARROW):
+        sim = hx.CudaScheme(ex, cfg, options=options)
+        sim.upload(st, bed, man)
+        bench.attach_boundaries(sim, w, cols, rows)
+        sim.set_target(1.0e7)
+        if w.get("boundaries"):
+            sim.set_clock(100.0, cfg.initial_dt, 0.97)
+        sim.iterate(iters)
+        out.append((sim.download_both(), sim.stats()))
+        sim.close()
+    (wa, wb), sw = out[0]
+    (na, nb), sn = out[1]
+    assert sw["batch_successful"] == sn["batch_successful"] == iters
+    tol = 1e-12 if cfg.precision == "double" else 1e-5
+    assert abs(sw["time"] - sn["time"]) <= tol * max(1.0, sn["time"])
+    for got, want in ((wa, na), (wb, nb)):
+        assert np.isfinite(got).all()
+        assert np.abs(got[..., :2] - want[..., :2]).max() <= tol
+        assert np.abs(got[..., 2:] - want[..., 2:]).max() <= 100 * tol

@@ -467,7 +467,16 @@ static int launch_step_tma(int scheme, int real_bytes, const StepArgs& a, const 
 }
 static_assert(sizeof(TmaBlockMap) == sizeof(hp::TmaMaps6POD), "descriptor block layout");
 // which (scheme, precision) pairs have a two-columns-per-lane kernel
-static bool has_wide(int scheme, int real_bytes) { (void)real_bytes; return scheme == 2; }
+#ifndef HP_WIDE_MH64
+#define HP_WIDE_MH64 1
+#endif
+#ifndef HP_WIDE_MH32
+#define HP_WIDE_MH32 1
+#endif
+static bool has_wide(int scheme, int real_bytes) {
+    if (scheme == 1) return real_bytes == 8 ? HP_WIDE_MH64 != 0 : HP_WIDE_MH32 != 0;
+    return scheme == 2;
+}
 static int march_box_w(int scheme, int real_bytes, int narrow) {
     return (!narrow && has_wide(scheme, real_bytes)) ? hp::wide_box_w(real_bytes) : hp::march_box_w(real_bytes, 1);
 }
@@ -475,6 +484,7 @@ static int launch_step_march(int scheme, int real_bytes, const StepArgs& a, cons
     const TmaBlockMap& m = *reinterpret_cast<const TmaBlockMap*>(maps);
     const int alt = alt_bits & 1;
     if (!(alt_bits & 2) && has_wide(scheme, real_bytes)) {
+        if (scheme == 1) return real_bytes == 8 ? launch_mh_wide<double>(a, m, alt, sm_count, st) : launch_mh_wide<float>(a, m, alt, sm_count, st);
         if (scheme == 2) return real_bytes == 8 ? launch_inertial_wide<double>(a, m, alt, sm_count, st) : launch_inertial_wide<float>(a, m, alt, sm_count, st);
     }
     if (scheme == 0) return real_bytes == 8 ? launch_godunov_march<double>(a, m, alt, sm_count, st) : launch_godunov_march<float>(a, m, alt, sm_count, st);

@@ -154,6 +154,11 @@ int apply_boundaries(hp_scheme* s, const hp::Planes& state) {
     return n;
 }
 
+// width mode of the marching kernels (KernelTable::step_march): 0 default, 1 one column per lane, 2 two columns
+static int march_width_mode(const hp_scheme* s) {
+    return (s->cfg.options & HP_OPT_NARROW_MARCH) ? 1 : ((s->cfg.options & HP_OPT_WIDE_MARCH) ? 2 : 0);
+}
+
 // One iteration = CSchemeGodunov::scheduleIteration / CSchemeMUSCLHancock::scheduleIteration.
 int enqueue_iteration(hp_scheme* s, bool alt, int* launched) {
     const int rb = static_cast<int>(s->rb);
@@ -172,7 +177,7 @@ int enqueue_iteration(hp_scheme* s, bool alt, int* launched) {
         const int sms = s->ex->prop.multiProcessorCount - spare_sms > 0 ? s->ex->prop.multiProcessorCount - spare_sms : 1;
         if (s->use_march)
             return s->K->step_march(static_cast<int>(s->cfg.scheme), rb, args, &s->march_map,
-                                    (alt ? 1 : 0) | ((s->cfg.options & HP_OPT_NARROW_MARCH) ? 2 : 0), sms, st);
+                                    (alt ? 1 : 0) | (march_width_mode(s) << 1), sms, st);
         if (s->use_tma) return s->K->step_tma(static_cast<int>(s->cfg.scheme), rb, args, alt ? &s->maps_b : &s->maps_a, sms, st);
         return s->K->step(static_cast<int>(s->cfg.scheme), rb, args, st);
     };
@@ -302,7 +307,7 @@ int build_tma_maps(hp_scheme* s) {
     const int rbi = static_cast<int>(s->rb);
     if (s->use_march) {
         // marching kernels: one 3-D descriptor over the ten-plane block; a box is one row of six planes
-        const int box_w = s->K->march_box_w(static_cast<int>(s->cfg.scheme), rbi, (s->cfg.options & HP_OPT_NARROW_MARCH) ? 1 : 0);
+        const int box_w = s->K->march_box_w(static_cast<int>(s->cfg.scheme), rbi, march_width_mode(s));
         return encode_plane_map(s->march_map.bytes[0], s->block, s->grid, s->rb, box_w, 1, 10, s->plane_bytes, 6);
     }
     const int w = hp::tma_box_w(rbi, halo), h = hp::tma_box_h(halo);

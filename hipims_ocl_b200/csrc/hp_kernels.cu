@@ -467,23 +467,29 @@ static int launch_step_tma(int scheme, int real_bytes, const StepArgs& a, const 
 }
 static_assert(sizeof(TmaBlockMap) == sizeof(hp::TmaMaps6POD), "descriptor block layout");
 // which (scheme, precision) pairs have a two-columns-per-lane kernel
+// MUSCL-Hancock in fp64 stays on the one-column kernel: two columns need 228 registers, i.e. 8 warps per SM, and the
+// fixed-latency stalls of so few warps cost more than the 15 % fewer instructions save (23.0 against 25.2 G
+// cell-updates/s on the wet dam break; 22.4 G with 168 registers, 12 warps and spills) -- profiles/r02_wide_mh_f64.txt
 #ifndef HP_WIDE_MH64
-#define HP_WIDE_MH64 1
+#define HP_WIDE_MH64 0
 #endif
 #ifndef HP_WIDE_MH32
 #define HP_WIDE_MH32 1
 #endif
-static bool has_wide(int scheme, int real_bytes) {
-    if (scheme == 1) return real_bytes == 8 ? HP_WIDE_MH64 != 0 : HP_WIDE_MH32 != 0;
-    return scheme == 2;
+// mode: 0 = the default kernel of (scheme, precision), 1 = one column per lane, 2 = two columns per lane wherever such a
+// kernel exists
+static bool use_wide(int scheme, int real_bytes, int mode) {
+    if (mode == 1 || (scheme != 1 && scheme != 2)) return false;
+    if (mode == 2 || scheme == 2) return true;
+    return real_bytes == 8 ? HP_WIDE_MH64 != 0 : HP_WIDE_MH32 != 0;
 }
-static int march_box_w(int scheme, int real_bytes, int narrow) {
-    return (!narrow && has_wide(scheme, real_bytes)) ? hp::wide_box_w(real_bytes) : hp::march_box_w(real_bytes, 1);
+static int march_box_w(int scheme, int real_bytes, int mode) {
+    return use_wide(scheme, real_bytes, mode) ? hp::wide_box_w(real_bytes) : hp::march_box_w(real_bytes, 1);
 }
 static int launch_step_march(int scheme, int real_bytes, const StepArgs& a, const hp::TmaMaps6POD* maps, int alt_bits, int sm_count, cudaStream_t st) {
     const TmaBlockMap& m = *reinterpret_cast<const TmaBlockMap*>(maps);
     const int alt = alt_bits & 1;
-    if (!(alt_bits & 2) && has_wide(scheme, real_bytes)) {
+    if (use_wide(scheme, real_bytes, (alt_bits >> 1) & 3)) {
         if (scheme == 1) return real_bytes == 8 ? launch_mh_wide<double>(a, m, alt, sm_count, st) : launch_mh_wide<float>(a, m, alt, sm_count, st);
         if (scheme == 2) return real_bytes == 8 ? launch_inertial_wide<double>(a, m, alt, sm_count, st) : launch_inertial_wide<float>(a, m, alt, sm_count, st);
     }

@@ -101,10 +101,10 @@ struct KernelTable {
     // TMA-staged step (fast flavour only, NULL otherwise); returns -1 if the scheme has no such kernel
     int (*step_tma)(int scheme, int real_bytes, const StepArgs& a, const TmaMapsPOD* maps, int sm_count, cudaStream_t st);
     // marching step (fast flavour only, NULL otherwise); returns -1 if the scheme has no such kernel
-    // alt: bit 0 = the step reads buffer B, bit 1 = one column per lane even where a wide kernel exists
+    // alt: bit 0 = the step reads buffer B, bits 1-2 = kernel width mode (0 default, 1 one column per lane, 2 two columns)
     int (*step_march)(int scheme, int real_bytes, const StepArgs& a, const TmaMaps6POD* maps, int alt, int sm_count, cudaStream_t st);
-    // columns of the TMA box the marching kernel of (scheme, precision) expects
-    int (*march_box_w)(int scheme, int real_bytes, int narrow);
+    // columns of the TMA box the marching kernel of (scheme, precision, width mode) expects
+    int (*march_box_w)(int scheme, int real_bytes, int mode);
     // returns the number of kernels launched
     int (*step)(int scheme, int real_bytes, const StepArgs& a, cudaStream_t st);
     int (*reduce_only)(int real_bytes, const StepArgs& a, cudaStream_t st);       // tst_Reduce

@@ -385,7 +385,7 @@ template <class R> __device__ __forceinline__ void friction_pair(const Params<R>
 #define HP_WIDE_MH_CTAS64 2
 #endif
 #ifndef HP_WIDE_MH_CTAS32
-#define HP_WIDE_MH_CTAS32 3
+#define HP_WIDE_MH_CTAS32 4
 #endif
 #ifndef HP_WIDE_MH_WARPS
 #define HP_WIDE_MH_WARPS 4

@@ -24,6 +24,7 @@ OPT_TILE_KERNELS = 8
 OPT_MARCH_GODUNOV = 16
 OPT_SPLIT_STRIPS = 32
 OPT_NARROW_MARCH = 64
+OPT_WIDE_MARCH = 128
 
 _SCHEME_ID = {hc.SCHEME_GODUNOV: 0, hc.SCHEME_MUSCL_HANCOCK: 1, hc.SCHEME_INERTIAL: 2}
 

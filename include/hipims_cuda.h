@@ -79,9 +79,11 @@ enum {
                                       kernel (equal on wet domains, slower on mostly dry ones)     */
     HP_OPT_SPLIT_STRIPS = 1u << 5, /* row strips: always split a step into edge rows + interior rows with
                                       the halo exchange overlapped (default only for large strips) */
-    HP_OPT_NARROW_MARCH = 1u << 6  /* marching kernels: one column per lane even where a two-column
-                                      ("wide") kernel exists -- the kernels the wide ones are checked
-                                      against                                                      */
+    HP_OPT_NARROW_MARCH = 1u << 6, /* marching kernels: one column per lane even where the two-column
+                                      ("wide") kernel is the default (inertial, fp32 MUSCL-Hancock)  */
+    HP_OPT_WIDE_MARCH  = 1u << 7   /* marching kernels: two columns per lane even where the one-column
+                                      kernel is the default (fp64 MUSCL-Hancock: fewer instructions
+                                      but too few resident warps)                   */
 };
 
 /*

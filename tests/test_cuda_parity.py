@@ -129,11 +129,14 @@ TOLERANCE_CASES = [
 
 # "fast" runs the default kernels (Godunov: TMA tiles, MUSCL-Hancock: marching warps, inertial: wide marching warps
 # with two columns per lane), "fast-other" the other
-# kernel of each scheme (Godunov marching, MUSCL-Hancock tiles)
+# kernel of each scheme (Godunov marching, MUSCL-Hancock tiles, inertial one column per lane); "fast-narrow" /
+# "fast-wide" pin the marching kernels to one / two columns per lane whatever the default of the precision is
 OTHER_KERNELS = hx.OPT_TILE_KERNELS | hx.OPT_MARCH_GODUNOV | hx.OPT_NARROW_MARCH
+WIDTHS = [hx.OPT_NARROW_MARCH, hx.OPT_WIDE_MARCH]
 
 
-@pytest.mark.parametrize("options", [hx.OPT_STRICT_FP, 0, hx.OPT_NO_GRAPH, OTHER_KERNELS], ids=["strict", "fast", "fast-nograph", "fast-other"])
+@pytest.mark.parametrize("options", [hx.OPT_STRICT_FP, 0, hx.OPT_NO_GRAPH, OTHER_KERNELS] + WIDTHS,
+                         ids=["strict", "fast", "fast-nograph", "fast-other", "fast-narrow", "fast-wide"])
 @pytest.mark.parametrize("scheme,precision,scen,bdy,n,iters,extra", TOLERANCE_CASES)
 def test_parity_within_tolerance(ex, options, scheme, precision, scen, bdy, n, iters, extra):
     cfg = make_cfg(scheme, precision, n, n, **extra)
@@ -144,7 +147,7 @@ def test_parity_within_tolerance(ex, options, scheme, precision, scen, bdy, n, i
 SINGLE_STEP = [(s, p) for s in ("godunov", "muscl-hancock", "inertial") for p in ("double", "single")]
 
 
-@pytest.mark.parametrize("options", [hx.OPT_STRICT_FP, 0, OTHER_KERNELS], ids=["strict", "fast", "fast-other"])
+@pytest.mark.parametrize("options", [hx.OPT_STRICT_FP, 0, OTHER_KERNELS] + WIDTHS, ids=["strict", "fast", "fast-other", "fast-narrow", "fast-wide"])
 @pytest.mark.parametrize("scheme,precision", SINGLE_STEP)
 def test_single_iteration_on_adversarial_input(ex, options, scheme, precision):
     """One iteration from identical adversarial states (rough bed, wet/dry patches, disabled cells,
@@ -207,12 +210,12 @@ def test_ragged_sizes_and_ring(ex):
         np.testing.assert_array_equal(out[:, 0], st[:, 0])
 
 
-@pytest.mark.parametrize("options", [0, OTHER_KERNELS], ids=["fast", "fast-other"])
+@pytest.mark.parametrize("options", [0, OTHER_KERNELS] + WIDTHS, ids=["fast", "fast-other", "fast-narrow", "fast-wide"])
 @pytest.mark.parametrize("scheme", ["godunov", "muscl-hancock", "inertial"])
 def test_ragged_sizes_fast_kernels(ex, scheme, options):
-    """Sizes around the tile (32 x 8) and strip (28 / 30 columns, 4 warps per CTA) boundaries of the fast kernels, a few
-    iterations from adversarial states: every flavour must agree with the oracle to rounding, ring frozen."""
-    for rows, cols in ((3, 3), (4, 31), (5, 67), (37, 4), (33, 65), (9, 30), (12, 61), (7, 121), (66, 29)):
+    """Sizes around the tile (32 x 8) and strip (28 / 30 / 60 columns, 4 warps per CTA) boundaries of the fast kernels, a
+    few iterations from adversarial states: every flavour must agree with the oracle to rounding, ring frozen."""
+    for rows, cols in ((3, 3), (4, 31), (5, 67), (37, 4), (33, 65), (9, 30), (12, 61), (7, 121), (66, 29), (6, 60), (11, 241), (5, 59)):
         cfg = make_cfg(scheme, "double", rows, cols)
         bed, st, man = scenario("wetdry", rows, cols, np.float64, seed=rows * 100 + cols)
         orc = cpu_sim.CpuSim("oracle", cfg)

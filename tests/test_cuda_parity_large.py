@@ -80,12 +80,15 @@ def check(cfg, orc, gpu, bed, st, iters):
 
 MARCH = hx.OPT_MARCH_GODUNOV
 NARROW = hx.OPT_NARROW_MARCH                 # one column per lane where the default is the two-column ("wide") kernel
+WIDE = hx.OPT_WIDE_MARCH                     # two columns per lane where the default is the one-column kernel
 
 # (workload, rows, cols, options, start time): rows x cols chosen so that march_runs >= 2 for that kernel's grid
 WRAP_CASES = [
     pytest.param("dambreak4096-mh", 3072, 4096, 0, None, id="mh-f64-dambreak"),
     pytest.param("dambreak4096-mh-f32", 3072, 4096, 0, None, id="mh-f32-dambreak"),
     pytest.param("river32768", 4096, 4096, 0, 700.0, id="mh-f64-river-cells"),                # configs[4] cropped
+    pytest.param("dambreak4096-mh", 3072, 4096, WIDE, None, id="mh-wide-f64-dambreak"),
+    pytest.param("river32768", 4096, 4096, WIDE, 700.0, id="mh-wide-f64-river-cells"),
     pytest.param("dambreak4096-mh", 3072, 4096, NARROW, None, id="mh-narrow-f64-dambreak"),
     pytest.param("dambreak4096-mh-f32", 3072, 4096, NARROW, None, id="mh-narrow-f32-dambreak"),
     pytest.param("river32768", 4096, 4096, NARROW, 700.0, id="mh-narrow-f64-river-cells"),
@@ -111,7 +114,7 @@ def test_wrapping_kernels_match_the_oracle(ex, workload, rows, cols, options, t0
     orc.close()
 
 
-@pytest.mark.parametrize("scheme,options", [("godunov", 0), ("godunov", MARCH), ("muscl-hancock", 0), ("muscl-hancock", NARROW),
+@pytest.mark.parametrize("scheme,options", [("godunov", 0), ("godunov", MARCH), ("muscl-hancock", WIDE), ("muscl-hancock", NARROW),
                                             ("inertial", 0), ("inertial", NARROW)],
                          ids=["godunov-tiles", "godunov-march", "mh-wide", "mh-narrow", "inertial-wide", "inertial-narrow"])
 def test_wrapping_kernels_on_wet_dry_terrain(ex, scheme, options):
@@ -244,7 +247,7 @@ def test_wide_and_narrow_marching_kernels_agree(ex, workload):
     dtype = np.float64 if cfg.precision == "double" else np.float32
     bed, st, man = bench.make_inputs(w, rows, cols, dtype)
     out = []
-    for options in (0, NARROW):
+    for options in (WIDE, NARROW):
         sim = hx.CudaScheme(ex, cfg, options=options)
         sim.upload(st, bed, man)
         bench.attach_boundaries(sim, w, cols, rows)

@@ -40,6 +40,10 @@ template <> __device__ __forceinline__ float fm_posdiff<float>(float a, float b)
 // |v| < eps => 0: the reference's "round delta values to zero if small" (CLSchemeGodunov.clc:340-348)
 template <class R> __device__ __forceinline__ R fm_chop(R v, R eps) { return hp_abs(v) < eps ? R(0) : v; }
 
+// a * b + c in one rounding, written out where the compiler's contraction would share the product instead
+__device__ __forceinline__ double hp_fma(double a, double b, double c) { return fma(a, b, c); }
+__device__ __forceinline__ float hp_fma(float a, float b, float c) { return fmaf(a, b, c); }
+
 // ---- forms the compiler cannot turn into max.f64 / min.f64 ---------------------------------------------------------
 // NVVM rewrites `v > 0 ? v : 0` into max.f64 and `a < c || b < c` into `min.f64(a, b) < c`; on this part either one
 // becomes DSETP.MAX/MIN + five register moves + SEL + FSEL + LOP3 (NaN quieting) -- ten issue slots for what a compare

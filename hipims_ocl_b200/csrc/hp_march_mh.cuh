@@ -234,9 +234,11 @@ mh_step_march2(const StepArgs a, const __grid_constant__ TmaBlockMap maps) {
                         syQy = minmod_sw(qy - ld(o_m, T::P_QY, lc), ld(o_p, T::P_QY, lc) - qy, yoff);
                         // Face depths h +- s/2 with |s| <= |h - h_neighbour| and both >= 0: never below h/2 >= 5e-6, so the
                         // reference's `face depth < VERY_SMALL => zero velocity` (:333-346) cannot fire here.
-                        const R hEf = h + half * sxH, hWf = h - half * sxH, hNf = h + half * syH, hSf = h - half * syH;
-                        const R qxE = qx + half * sxQx, qxW = qx - half * sxQx, qyE = qy + half * sxQy, qyW = qy - half * sxQy;
-                        const R qxN = qx + half * syQx, qxS = qx - half * syQx, qyN = qy + half * syQy, qyS = qy - half * syQy;
+                        // v +- s/2 as two multiply-adds: s/2 is exact, so each is the correctly rounded v +- s/2 of the
+                        // product-then-sum form, in two fp64 operations per pair instead of three
+                        const R hEf = hp_fma(half, sxH, h), hWf = hp_fma(-half, sxH, h), hNf = hp_fma(half, syH, h), hSf = hp_fma(-half, syH, h);
+                        const R qxE = hp_fma(half, sxQx, qx), qxW = hp_fma(-half, sxQx, qx), qyE = hp_fma(half, sxQy, qy), qyW = hp_fma(-half, sxQy, qy);
+                        const R qxN = hp_fma(half, syQx, qx), qxS = hp_fma(-half, syQx, qx), qyN = hp_fma(half, syQy, qy), qyS = hp_fma(-half, syQy, qy);
                         const R uE = qxE * fm_rcp(hEf), uW = qxW * fm_rcp(hWf);
                         const R vN = qyN * fm_rcp(hNf), vS = qyS * fm_rcp(hSf);
                         const R dEta = ((qxE - qxW) + (qyN - qyS)) * inv_delta;
@@ -251,13 +253,13 @@ mh_step_march2(const StepArgs a, const __grid_constant__ TmaBlockMap maps) {
 
                 FaceOut<R> fy;
                 fy.m = R(0); fy.n = R(0); fy.t = R(0); fy.zmax = R(0); fy.hL = R(0); fy.hR = R(0); fy.stopL = 0; fy.stopR = 0;
-                const R etaR = ce - half * syE;                  // southern face estimate of row y
+                const R etaR = hp_fma(-half, syE, ce);           // southern face estimate of row y
                 if (j >= 2) {
                     // ---- face between rows y-1 (left, carried) and y (right); normal = y ----------------------
-                    const R hfR = ch - half * syH;
+                    const R hfR = hp_fma(-half, syH, ch);
                     const R rR = hfR <= k.eps ? R(0) : fm_rcp(hfR);                              // :1140-1150
-                    face_solve2<R, false>(k, Le, Le - Lh, Lun, Lut, R(0), etaR, etaR - hfR, (cqy - half * syQy) * rR,
-                                          (cqx - half * syQx) * rR, R(0), [&] { return ld_again(o_m, T::P_QY, lc); },
+                    face_solve2<R, false>(k, Le, Le - Lh, Lun, Lut, R(0), etaR, etaR - hfR, hp_fma(-half, syQy, cqy) * rR,
+                                          hp_fma(-half, syQx, cqx) * rR, R(0), [&] { return ld_again(o_m, T::P_QY, lc); },
                                           [&] { return ld_again(o_c, T::P_QY, lc); }, fy);
                     if (j >= 3) {
                         // ---- corrector of row y-1 (CLSchemeMUSCLHancock.clc:596-800) -----------------
@@ -306,15 +308,15 @@ mh_step_march2(const StepArgs a, const __grid_constant__ TmaBlockMap maps) {
                 int xStop = 0;
                 if (j >= 2 && j < J) {
                     // the east-side estimate goes one lane up and meets that lane's west side
-                    const R xe_eta = ce + half * sxE, xe_h = ch + half * sxH;
+                    const R xe_eta = hp_fma(half, sxE, ce), xe_h = hp_fma(half, sxH, ch);
                     const R xe_r = xe_h <= k.eps ? R(0) : fm_rcp(xe_h);
-                    const R xe_u = (cqx + half * sxQx) * xe_r, xe_v = (cqy + half * sxQy) * xe_r;
+                    const R xe_u = hp_fma(half, sxQx, cqx) * xe_r, xe_v = hp_fma(half, sxQy, cqy) * xe_r;
                     const R etaL = shfl_up1(xe_eta), hfL = shfl_up1(xe_h), uL = shfl_up1(xe_u), vL = shfl_up1(xe_v);
-                    const R xw_eta = ce - half * sxE, hfR = ch - half * sxH;
+                    const R xw_eta = hp_fma(-half, sxE, ce), hfR = hp_fma(-half, sxH, ch);
                     const R rR = hfR <= k.eps ? R(0) : fm_rcp(hfR);
                     FaceOut<R> fx;
-                    face_solve2<R, false>(k, etaL, etaL - hfL, uL, vL, R(0), xw_eta, xw_eta - hfR, (cqx - half * sxQx) * rR,
-                                          (cqy - half * sxQy) * rR, R(0), [&] { return ld_again(o_c, T::P_QX, lw); },
+                    face_solve2<R, false>(k, etaL, etaL - hfL, uL, vL, R(0), xw_eta, xw_eta - hfR, hp_fma(-half, sxQx, cqx) * rR,
+                                          hp_fma(-half, sxQy, cqy) * rR, R(0), [&] { return ld_again(o_c, T::P_QX, lw); },
                                           [&] { return ld_again(o_c, T::P_QX, lc); }, fx);
                     // the east face comes back from lane+1
                     const R eM = shfl_dn1(fx.m), eN = shfl_dn1(fx.n), eT = shfl_dn1(fx.t), eZ = shfl_dn1(fx.zmax), eH = shfl_dn1(fx.hR);
@@ -329,9 +331,9 @@ mh_step_march2(const StepArgs a, const __grid_constant__ TmaBlockMap maps) {
                 // ---- hand over to the next row (everything carried is dead by now) -----------------------------
                 Aeta = Xeta - fy.m; Aqx = Xqx - fy.t; Aqy = Xqy - fy.n;
                 bS = fm_min(fy.zmax, etaR); sH = fy.hL; cStop = xStop + fy.stopR;
-                Le = ce + half * syE; Lh = ch + half * syH;
+                Le = hp_fma(half, syE, ce); Lh = hp_fma(half, syH, ch);
                 const R rL = Lh <= k.eps ? R(0) : fm_rcp(Lh);
-                Lun = (cqy + half * syQy) * rL; Lut = (cqx + half * syQx) * rL;
+                Lun = hp_fma(half, syQy, cqy) * rL; Lut = hp_fma(half, syQx, cqx) * rL;
                 f_ew_prev = (f_w >> 1) | ((f_e >> 1) << 2);
                 f_m2 = f_m1; f_m1 = f_c; f_c = f_p;
             }

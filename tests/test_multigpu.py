@@ -42,6 +42,9 @@ CASES = [
     ("muscl-hancock", "single", 250, 200, 40, "cells", 0),            # rows not divisible by the rank count
     ("godunov", "double", 256, 192, 41, "rain", 2),                   # direct launches (HP_OPT_NO_GRAPH), odd count
     ("muscl-hancock", "double", 256, 192, 40, "cells", 32),           # split path forced on a small strip
+    ("muscl-hancock", "double", 256, 192, 40, "cells", 128),          # two columns per lane (HP_OPT_WIDE_MARCH)
+    ("inertial", "single", 250, 200, 40, "cells", 32),                # wide kernel, split path, rows not divisible
+    ("inertial", "double", 256, 192, 40, "cells", 64),                # one column per lane (HP_OPT_NARROW_MARCH)
 ]
 
 

@@ -25,6 +25,7 @@ __device__ __forceinline__ bool any(B2 m) { return m.a | m.b; }
 __device__ __forceinline__ B2 operator!(B2 m) { return B2{!m.a, !m.b}; }
 __device__ __forceinline__ B2 operator&(B2 x, B2 y) { return B2{x.a && y.a, x.b && y.b}; }
 __device__ __forceinline__ B2 operator|(B2 x, B2 y) { return B2{x.a || y.a, x.b || y.b}; }
+__device__ __forceinline__ B2 operator&(B2 x, bool y) { return B2{x.a && y, x.b && y}; }
 
 // ---- fp64: two doubles (contraction is written out, so both precisions evaluate the same expression tree) ---------
 __device__ __forceinline__ P2<double> operator+(P2<double> x, P2<double> y) { return {x.a + y.a, x.b + y.b}; }

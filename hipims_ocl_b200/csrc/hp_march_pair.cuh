@@ -347,7 +347,7 @@ __device__ __forceinline__ void face_solve_pair(const Params<R>& k, P2<R> etaL, 
         const I2 both{((lowR.a && unL.a < R(0)) ? 1 : 0) + ((lowL.a && unR.a > R(0)) ? 1 : 0),
                       ((lowR.b && unL.b < R(0)) ? 1 : 0) + ((lowL.b && unR.b > R(0)) ? 1 : 0)};
         o.stopL = both; o.stopR = both;
-        if (any(lowL | lowR)) {                          // the owners' raw discharge is read here only
+        if (__any_sync(FULL, any(lowL | lowR))) {        // the owners' raw discharge is read here only
             const P2<R> qL = qOwnL(), qR = qOwnR();
             o.stopL = I2{both.a + ((lowL.a && qL.a > R(0)) ? 1 : 0), both.b + ((lowL.b && qL.b > R(0)) ? 1 : 0)};
             o.stopR = I2{both.a + ((lowR.a && qR.a < R(0)) ? 1 : 0), both.b + ((lowR.b && qR.b < R(0)) ? 1 : 0)};
@@ -384,7 +384,6 @@ template <class R> __device__ __forceinline__ void friction_pair(const Params<R>
     const P2<R> q2 = sx + sy;
     const P2<R> q = pcelerity(R(1), q2);                 // sqrt(q2), a zero discharge giving a harmless tiny root
     go = go & !(h < k.eps) & !(q < k.eps);
-    if (!any(go)) return;
     const P2<R> A = (dt * k.g) * n * n * rh * rh * prcbrt(h);             // dt * Cf / h^2
     const P2<R> aq2 = A * q2;
     const P2<R> nx = fma2(-(qx * aq2), prcp(fma2(A, q2 + sx, q)), qx);
@@ -591,7 +590,7 @@ mh_step_wide(const StepArgs a, const __grid_constant__ TmaBlockMap maps) {
                     const P2<R> h = eta - zb;
                     const B2 pred{valid_y && x_valid.a && !(h.a < R(1E-5)) && !((f_p.a | f_e.a | f_m1.a | f_w.a) & 1),
                                   valid_y && x_valid.b && !(h.b < R(1E-5)) && !((f_p.b | f_e.b | f_m1.b | f_w.b) & 1)};
-                    if (any(pred)) {
+                    if (__any_sync(FULL, any(pred))) {             // a warp vote, not a per-lane branch (see inertial_face2)
                         const P2<R> etaE{eta.b, lde(o_c, T::P_ETA)}, etaW{ldw(o_c, T::P_ETA), eta.a};
                         const P2<R> etaN = ld2(o_p, T::P_ETA), etaS = ld2(o_m, T::P_ETA);
                         const P2<R> hE = etaE - P2<R>{zb.b, lde(o_c, T::P_ZB)}, hW = etaW - P2<R>{ldw(o_c, T::P_ZB), zb.a};
@@ -644,14 +643,12 @@ mh_step_wide(const StepArgs a, const __grid_constant__ TmaBlockMap maps) {
                     const int gyc = gy - 1;
                     P2<R> c_eta = ld2(o_m, T::P_ETA), c_emax = ld2(o_m, T::P_EMAX), c_qx = ld2(o_m, T::P_QX), c_qy = ld2(o_m, T::P_QY);
                     const P2<R> pzb = ld2(o_m, T::P_ZB);
-                    P2<R> rh_new = zero;
-                    B2 have_rh{false, false};
                     const bool rows_ok = gyc >= 2 && gyc <= g.grows - 3;
                     const B2 live = x_interior & !((c_emax <= R(-9999.0)) | (c_eta == splat(R(-9999.0))));
                     const I2 dry{((c_eta.a - pzb.a < k.eps) ? 1 : 0) + (f_c.a >> 1) + (f_m2.a >> 1) + (f_ew_prev.a & 1) + (f_ew_prev.a >> 2),
                                  ((c_eta.b - pzb.b < k.eps) ? 1 : 0) + (f_c.b >> 1) + (f_m2.b >> 1) + (f_ew_prev.b & 1) + (f_ew_prev.b >> 2)};
                     const B2 upd{rows_ok && live.a && dry.a < 5, rows_ok && live.b && dry.b < 5};
-                    if (any(upd)) {
+                    if (__any_sync(FULL, any(upd))) {
                         const P2<R> bN = pmin(fy.zmax, Le);
                         const P2<R> dEta = (Aeta + fy.m) * splat(inv_delta);
                         const P2<R> dQx = (Aqx + fy.t) * splat(inv_delta);
@@ -664,7 +661,7 @@ mh_step_wide(const StepArgs a, const __grid_constant__ TmaBlockMap maps) {
                         const P2<R> h_new = n_eta - pzb;
                         const B2 wet_new = !(h_new < k.eps);
                         const P2<R> hs = sel(wet_new, h_new, splat(R(1)));
-                        rh_new = prcp(hs); have_rh = upd & wet_new;
+                        const P2<R> rh_new = prcp(hs);
                         if (k.friction) friction_pair(k, hs, rh_new, n_qx, n_qy, ld2(o_m, T::P_N), dt, wet_new);
                         n_eta = sel(wet_new, n_eta, pzb);
                         const P2<R> n_emax = sel((n_eta > c_emax) & (c_emax > R(-9990.0)), n_eta, c_emax);
@@ -673,11 +670,7 @@ mh_step_wide(const StepArgs a, const __grid_constant__ TmaBlockMap maps) {
                     }
                     if (x_store.a) {
                         store_row(y - 1, c_eta, c_emax, c_qx, c_qy);
-                        if (a.reduce_mode != hp::kReduceNone) {
-                            const P2<R> h = c_eta - pzb;
-                            if (h.a > k.eps10 && c_emax.a > R(-9999.0)) ws = fm_max(speed_of(h.a, c_qx.a, c_qy.a, have_rh.a, rh_new.a), ws);
-                            if (x_store.b && h.b > k.eps10 && c_emax.b > R(-9999.0)) ws = fm_max(speed_of(h.b, c_qx.b, c_qy.b, have_rh.b, rh_new.b), ws);
-                        }
+                        if (a.reduce_mode != hp::kReduceNone) ws = wide_speed2(k, c_eta, c_emax, c_qx, c_qy, pzb, x_store, ws);
                     }
                 }
 

@@ -478,9 +478,20 @@ static_assert(sizeof(TmaBlockMap) == sizeof(hp::TmaMaps6POD), "descriptor block 
 #endif
 // mode: 0 = the default kernel of (scheme, precision), 1 = one column per lane, 2 = two columns per lane wherever such a
 // kernel exists
+// Godunov (only with HP_OPT_MARCH_GODUNOV; the default kernel of the scheme is the tile kernel): in fp64 two columns need
+// 218 registers -- 168 with spills at 12 warps per SM run at 32.2 G cell-updates/s on the 4096^2 dam break where the
+// one-column kernel reaches 35.7 G; in fp32 (121 registers, 16 warps) the two-column kernel is the faster one, 51.6 against
+// 46.5 G (tiles: 48.1 G)
+#ifndef HP_WIDE_GOD64
+#define HP_WIDE_GOD64 0
+#endif
+#ifndef HP_WIDE_GOD32
+#define HP_WIDE_GOD32 1
+#endif
 static bool use_wide(int scheme, int real_bytes, int mode) {
-    if (mode == 1 || (scheme != 1 && scheme != 2)) return false;
+    if (mode == 1 || scheme < 0 || scheme > 2) return false;
     if (mode == 2 || scheme == 2) return true;
+    if (scheme == 0) return real_bytes == 8 ? HP_WIDE_GOD64 != 0 : HP_WIDE_GOD32 != 0;
     return real_bytes == 8 ? HP_WIDE_MH64 != 0 : HP_WIDE_MH32 != 0;
 }
 static int march_box_w(int scheme, int real_bytes, int mode) {
@@ -490,6 +501,7 @@ static int launch_step_march(int scheme, int real_bytes, const StepArgs& a, cons
     const TmaBlockMap& m = *reinterpret_cast<const TmaBlockMap*>(maps);
     const int alt = alt_bits & 1;
     if (use_wide(scheme, real_bytes, (alt_bits >> 1) & 3)) {
+        if (scheme == 0) return real_bytes == 8 ? launch_godunov_wide<double>(a, m, alt, sm_count, st) : launch_godunov_wide<float>(a, m, alt, sm_count, st);
         if (scheme == 1) return real_bytes == 8 ? launch_mh_wide<double>(a, m, alt, sm_count, st) : launch_mh_wide<float>(a, m, alt, sm_count, st);
         if (scheme == 2) return real_bytes == 8 ? launch_inertial_wide<double>(a, m, alt, sm_count, st) : launch_inertial_wide<float>(a, m, alt, sm_count, st);
     }

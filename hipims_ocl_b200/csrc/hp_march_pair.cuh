@@ -306,19 +306,24 @@ template <class R> __device__ __forceinline__ P2<R> pshfl_dn_a(P2<R> v) { return
 // Two faces in the normal frame, solved once each for the cells on either side (face_solve2 of hp_march_kernels.cuh,
 // component by component).  The wet fast path is taken when every face of the warp's row is wet on both sides; the
 // supercritical exits and the dry cases are selects behind one warp vote each.  Must be called by all 32 lanes.
-template <class R, class QOwnL, class QOwnR>
-__device__ __forceinline__ void face_solve_pair(const Params<R>& k, P2<R> etaL, P2<R> zL, P2<R> unL, P2<R> utL, P2<R> etaR, P2<R> zR,
-                                                P2<R> unR, P2<R> utR, QOwnL qOwnL, QOwnR qOwnR, FaceOut2<R>& o) {
+// CACHED (first-order callers, whose face values are cell values): cL / cR are the celerities of the two cells on their own
+// beds, sqrt(g (eta - z)); a side whose bed IS the face's bed in all 64 columns -- flat or uniformly sloping ground, one
+// warp vote per side -- takes them instead of a new root.
+template <class R, bool CACHED, class QOwnL, class QOwnR>
+__device__ __forceinline__ void face_solve_pair_c(const Params<R>& k, P2<R> etaL, P2<R> zL, P2<R> unL, P2<R> utL, P2<R> cL, P2<R> etaR,
+                                                  P2<R> zR, P2<R> unR, P2<R> utR, P2<R> cR, QOwnL qOwnL, QOwnR qOwnR, FaceOut2<R>& o) {
     constexpr unsigned FULL = 0xffffffffu;
     const R hg = R(0.5) * k.g;
     const P2<R> zero = splat(R(0));
     const P2<R> zmax = pmax(zL, zR);
     const P2<R> dL = etaL - zmax, dR = etaR - zmax;
     o.zmax = zmax;
+    const bool ownL = CACHED && __all_sync(FULL, zmax.a == zL.a && zmax.b == zL.b);
+    const bool ownR = CACHED && __all_sync(FULL, zmax.a == zR.a && zmax.b == zR.b);
     const B2 wet = (dL > k.eps) & (dR > k.eps);
     if (__all_sync(FULL, wet.a && wet.b)) {
         o.hL = dL; o.hR = dR; o.stopL = I2{0, 0}; o.stopR = I2{0, 0};
-        const P2<R> aL = psqrt_pos(k.g * dL), aR = psqrt_pos(k.g * dR);
+        const P2<R> aL = ownL ? cL : psqrt_pos(k.g * dL), aR = ownR ? cR : psqrt_pos(k.g * dR);
         const P2<R> qnL = dL * unL, qnR = dR * unR;
         const P2<R> as = pabs(fma2(splat(R(0.25)), unL - unR, R(0.5) * (aL + aR)));
         const P2<R> us = fma2(splat(R(0.5)), unL + unR, aL) - aR;
@@ -360,7 +365,7 @@ __device__ __forceinline__ void face_solve_pair(const Params<R>& k, P2<R> etaL, 
     if (__all_sync(FULL, dd.a && dd.b)) { o.m = zero; o.n = ddn; o.t = zero; return; }
     unL = sel(dryL, zero, unL); utL = sel(dryL, zero, utL);
     unR = sel(dryR, zero, unR); utR = sel(dryR, zero, utR);
-    const P2<R> aL = pcelerity(k.g, hL), aR = pcelerity(k.g, hR);
+    const P2<R> aL = ownL ? cL : pcelerity(k.g, hL), aR = ownR ? cR : pcelerity(k.g, hR);
     const P2<R> qnL = hL * unL, qnR = hR * unR;
     const P2<R> as = pabs(fma2(splat(R(0.25)), unL - unR, R(0.5) * (aL + aR)));
     const P2<R> us = fma2(splat(R(0.5)), unL + unR, aL) - aR;
@@ -376,6 +381,12 @@ __device__ __forceinline__ void face_solve_pair(const Params<R>& k, P2<R> etaL, 
     o.m = sel(dd, zero, m);
     o.n = sel(dd, ddn, sel(supL, FLn, sel(supR, FRn, f2)));
     o.t = sel(dd, zero, m * sel(supL, utL, sel(supR, utR, sel(!(f1 < R(0)), utL, utR))));
+}
+
+template <class R, class QOwnL, class QOwnR>
+__device__ __forceinline__ void face_solve_pair(const Params<R>& k, P2<R> etaL, P2<R> zL, P2<R> unL, P2<R> utL, P2<R> etaR, P2<R> zR,
+                                                P2<R> unR, P2<R> utR, QOwnL qOwnL, QOwnR qOwnR, FaceOut2<R>& o) {
+    face_solve_pair_c<R, false>(k, etaL, zL, unL, utL, etaL, etaR, zR, unR, utR, etaR, qOwnL, qOwnR, o);
 }
 
 // Point-implicit friction on a pair (friction_fast component by component); `go` masks the components it applies to.
@@ -735,6 +746,243 @@ template <class R> static int launch_mh_wide(const StepArgs& a_in, const TmaBloc
     a.total_ctas = grid; a.march_runs = march_runs(a, T::USE, T::NW, grid);
     if (alt) mh_step_wide<R, true><<<grid, T::NW * 32, T::SMEM_BYTES, st>>>(a, maps);
     else mh_step_wide<R, false><<<grid, T::NW * 32, T::SMEM_BYTES, st>>>(a, maps);
+    return 1;
+}
+
+// =============================================================================================
+// First-order Godunov, two columns per lane.  Same row structure as godunov_step_march (hp_march_kernels.cuh): the
+// cells of the row below (level, bed, velocities, celerity) and their southern faces are carried as pairs; of a lane's
+// two west faces only the first needs the neighbouring lane.  Cells whose stencil is dry stay unwritten (SURVEY.md
+// Q2), exactly like godunov_step_tma.
+// =============================================================================================
+template <class R> struct GodPair { P2<R> eta, zb, u, v, c; };
+
+#ifndef HP_WIDE_GOD_CTAS64
+#define HP_WIDE_GOD_CTAS64 3
+#endif
+#ifndef HP_WIDE_GOD_CTAS32
+#define HP_WIDE_GOD_CTAS32 4
+#endif
+template <class R, bool ALT>
+__global__ void __launch_bounds__(hp::kMarchWarps * 32, sizeof(R) == 8 ? HP_WIDE_GOD_CTAS64 : HP_WIDE_GOD_CTAS32)
+godunov_step_wide(const StepArgs a, const __grid_constant__ TmaBlockMap maps) {
+    using T = Wide<R, ALT>;
+    constexpr unsigned FULL = 0xffffffffu;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* const ring = smem_raw + warp * T::WARP_BYTES;
+    const uint32_t ring_u = smem_u32(ring);
+    const uint32_t bar_u = smem_u32(smem_raw + T::NW * T::WARP_BYTES) + warp * T::RR * 8;
+    if (lane == 0) {
+#pragma unroll
+        for (int r = 0; r < T::RR; ++r) mbar_init(bar_u + 8 * r, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+
+    const Params<R> k = make_params<R>(a.params);
+    const Grid g = a.grid;
+    const R dt = read_timestep<R>(a.clock);
+    const R inv_delta = fm_rcp(k.delta);
+    const R hg = R(0.5) * k.g;
+    const P2<R> zero = splat(R(0));
+    const MutView<R> d(a.dst);
+    const bool stepping = dt > R(0);
+
+    const int nrows = a.y1 - a.y0;
+    const int nstrips = (g.cols + T::USE - 1) / T::USE;
+    const int ngroups = (nstrips + T::NW - 1) / T::NW;
+    const long long units = static_cast<long long>(ngroups) * nrows;
+    const long long total_runs = static_cast<long long>(gridDim.x) * a.march_runs;
+    int run = 0;
+    long long u = units * blockIdx.x / total_runs, u1 = units * (blockIdx.x + 1) / total_runs;
+
+    constexpr int SZ = int(sizeof(R));
+    const int lc = (2 * lane + T::PADL) * SZ;
+    const int lw = lane > 0 ? lc - SZ : lc;
+    auto ld2 = [&](int row_off, int plane) -> P2<R> { return ld_pair<R>(ring + row_off + plane * T::PLANE + lc); };
+    auto ldw = [&](int row_off, int plane) -> R { return *reinterpret_cast<const R*>(ring + row_off + plane * T::PLANE + lw); };
+    // re-read of the raw discharge (only wet/dry fronts ask for it)
+    auto ld2_again = [&](int row_off, int plane) -> P2<R> {
+        const volatile R* p = reinterpret_cast<const volatile R*>(ring + row_off + plane * T::PLANE + lc);
+        return P2<R>{p[0], p[1]};
+    };
+    auto ldw_again = [&](int row_off, int plane) -> R { return *reinterpret_cast<const volatile R*>(ring + row_off + plane * T::PLANE + lw); };
+    const bool lane_owns = lane >= 1 && lane <= 30;
+
+    R ws = R(0);
+    uint32_t ph = 0;
+
+    for (;;) {
+        if (u >= u1) {
+            if (++run >= a.march_runs) break;
+            const long long r = static_cast<long long>(run) * gridDim.x + blockIdx.x;
+            u = units * r / total_runs; u1 = units * (r + 1) / total_runs;
+            continue;
+        }
+        const int grp = static_cast<int>(u / nrows);
+        const int ya = a.y0 + static_cast<int>(u - static_cast<long long>(grp) * nrows);
+        const long long gend = static_cast<long long>(grp + 1) * nrows;
+        const int yb = ya + static_cast<int>((u1 < gend ? u1 : gend) - u);
+        u += yb - ya;
+        const int strip = grp * T::NW + warp;
+        if (strip >= nstrips) continue;
+
+        const int X0 = strip * T::USE - 2;               // first column of lane 0
+        const int xa = X0 + 2 * lane;                     // the lane's columns: xa, xa + 1
+        const int rs = ya - 1;                            // first raw row of this run
+        const int NR = yb - ya + 2;                       // raw rows 0 .. NR-1; rows 1 .. NR-2 are updated
+        const B2 x_interior{xa >= 1 && xa <= g.cols - 2, xa + 1 >= 1 && xa + 1 <= g.cols - 2};
+        const B2 x_store{lane_owns && xa < g.cols, lane_owns && xa + 1 < g.cols};
+        auto issue_row = [&](int j) {
+            const uint32_t bar = bar_u + 8 * (j & (T::RR - 1));
+            mbar_expect_tx(bar, uint32_t(T::ROW_TX));
+            tma_load_3d(ring_u + (j & (T::RR - 1)) * T::SLOT, &maps.block, X0 - T::PADL, rs + j, T::P0, bar);
+        };
+        auto wait_row = [&](int j) {
+            const int s = j & (T::RR - 1);
+            mbar_wait(bar_u + 8 * s, (ph >> s) & 1u);
+            ph ^= 1u << s;
+        };
+        auto derive = [&](int row_off, GodPair<R>& o, B2& dry) {          // phase B of the tile kernel
+            o.eta = ld2(row_off, T::P_ETA); o.zb = ld2(row_off, T::P_ZB);
+            const P2<R> qx = ld2(row_off, T::P_QX), qy = ld2(row_off, T::P_QY);
+            const P2<R> h = o.eta - o.zb;
+            dry = h < k.eps;
+            const P2<R> rh = sel(dry, zero, prcp(sel(dry, splat(R(1)), h)));
+            o.u = qx * rh; o.v = qy * rh;
+            o.c = pcelerity(k.g, ppos(h));
+        };
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < T::RR; ++j) if (j < NR) issue_row(j);
+        }
+        wait_row(0);
+
+        GodPair<R> P;
+        B2 dry_p;
+        derive(0, P, dry_p);
+        P2<R> sM = zero, sN = zero, sT = zero, sZ = zero, sH = zero;       // southern faces of row j-1
+        I2 sStop{0, 0};
+        B2 dry_s{true, true};                                               // dryness of the cells below row j-1
+
+        for (int j = 1; j < NR; ++j) {
+            const int y = rs + j;
+            const int o_m = ((j - 1) & (T::RR - 1)) * T::SLOT, o_c = (j & (T::RR - 1)) * T::SLOT;
+            wait_row(j);
+            GodPair<R> C;
+            B2 dry_c;
+            derive(o_c, C, dry_c);
+            if (a.reduce_mode == hp::kReduceDst && any(x_store) && j + 1 < NR) {      // row y is updated in the next trip
+                const int gy = y + g.gy0;
+                if (!(x_interior.a && x_interior.b) || gy < 1 || gy > g.grows - 2 || any(dry_c & dry_p))
+                    prefetch_dst(d, static_cast<size_t>(y) * g.pitch + xa);          // the pair shares its 32-byte sectors
+            }
+
+            // faces between rows y-1 (left) and y (right); normal = y
+            FaceOut2<R> fy;
+            face_solve_pair_c<R, true>(k, P.eta, P.zb, P.v, P.u, P.c, C.eta, C.zb, C.v, C.u, C.c,
+                                       [&] { return ld2_again(o_m, T::P_QY); }, [&] { return ld2_again(o_c, T::P_QY); }, fy);
+
+            if (j >= 2) {
+                const int yc = y - 1, gyc = yc + g.gy0;
+                P2<R> eta = P.eta, emax = ld2(o_m, T::P_EMAX), qx = ld2(o_m, T::P_QX), qy = ld2(o_m, T::P_QY);
+                const P2<R> zb = P.zb;
+                const B2 disabled = (emax <= R(-9999.0)) | (eta == splat(R(-9999.0)));
+                // rows y-2, y-1, y dry in every column: the stencil of every cell of row y-1 is dry, the reference returns
+                // without writing (CLSchemeGodunov.clc:248-255) -- no face of that row is needed
+                const bool skip = stepping && __all_sync(FULL, dry_s.a && dry_s.b && dry_p.a && dry_p.b && dry_c.a && dry_c.b &&
+                                                                   !(disabled.a || disabled.b));
+                if (a.reduce_mode == hp::kReduceSrc && any(x_store)) {
+                    const B2 ok = x_store & ((eta - zb) > k.eps10) & (emax > R(-9999.0));
+                    const P2<R> sp = sel(ok, k.simplified_speed ? P.c : pmax(pabs(P.u), pabs(P.v)) + P.c, zero);
+                    ws = fm_max(fm_max(sp.a, sp.b), ws);
+                }
+                B2 wrote{false, false};
+                if (!skip) {
+                    // west faces of row y-1: lane-1's second column against the own first, the own first against the own second
+                    const P2<R> w_eta{ldw(o_m, T::P_ETA), P.eta.a}, w_zb{ldw(o_m, T::P_ZB), P.zb.a};
+                    const P2<R> w_u = pshfl_up_b(P.u), w_v = pshfl_up_b(P.v), w_c = pshfl_up_b(P.c);
+                    FaceOut2<R> fx;
+                    face_solve_pair_c<R, true>(k, w_eta, w_zb, w_u, w_v, w_c, P.eta, P.zb, P.u, P.v, P.c,
+                                               [&] { const P2<R> q = ld2_again(o_m, T::P_QX); return P2<R>{ldw_again(o_m, T::P_QX), q.a}; },
+                                               [&] { return ld2_again(o_m, T::P_QX); }, fx);
+                    // east faces: the second column's western face for the first column, lane+1's first for the second
+                    const P2<R> eM = pshfl_dn_a(fx.m), eN = pshfl_dn_a(fx.n), eT = pshfl_dn_a(fx.t), eZ = pshfl_dn_a(fx.zmax), eH = pshfl_dn_a(fx.hR);
+                    const I2 eStop{fx.stopL.b, __shfl_down_sync(FULL, fx.stopL.a, 1)};
+                    const unsigned drym_a = __ballot_sync(FULL, dry_p.a), drym_b = __ballot_sync(FULL, dry_p.b);
+                    const B2 dry_w{((drym_b >> ((lane + 31) & 31)) & 1u) != 0, dry_p.a};
+                    const B2 dry_e{dry_p.b, ((drym_a >> ((lane + 1) & 31)) & 1u) != 0};
+                    const bool rows_ok = gyc >= 1 && gyc <= g.grows - 2;                    // frozen outer ring
+                    const B2 all_dry = dry_p & dry_c & dry_s & dry_e & dry_w;               // CLSchemeGodunov.clc:248-255
+                    const B2 upd = (x_interior & !disabled & !all_dry) & (rows_ok && stepping);
+                    // dt <= 0 copies the state through (:201-206), and so does a disabled cell
+                    wrote = stepping ? (x_interior & (disabled | !all_dry)) & rows_ok : x_interior & rows_ok;
+                    if (__any_sync(FULL, any(upd))) {
+                        const P2<R> bN = pmin(fy.zmax, eta), bS = pmin(sZ, eta), bE = pmin(eZ, eta), bW = pmin(fx.zmax, eta);
+                        const B2 stop{fy.stopL.a + sStop.a + fx.stopR.a + eStop.a > 0, fy.stopL.b + sStop.b + fx.stopR.b + eStop.b > 0};
+                        const P2<R> dEta = ((eM - fx.m) + (fy.m - sM)) * splat(inv_delta);
+                        const P2<R> dQx = fma2(hg * (bE - bW), eH + fx.hL, (eN - fx.n) + (fy.t - sT)) * splat(inv_delta);
+                        const P2<R> dQy = fma2(hg * (bN - bS), fy.hR + sH, (eT - fx.t) + (fy.n - sN)) * splat(inv_delta);
+                        P2<R> n_qx = sel(stop, zero, qx), n_qy = sel(stop, zero, qy);
+                        P2<R> n_eta = sel(!(pabs(dEta) < k.eps), fma2(splat(-dt), dEta, eta), eta);   // |D| < eps => 0 (:340-348)
+                        n_qx = sel(!(pabs(dQx) < k.eps), fma2(splat(-dt), dQx, n_qx), n_qx);
+                        n_qy = sel(!(pabs(dQy) < k.eps), fma2(splat(-dt), dQy, n_qy), n_qy);
+                        const P2<R> h_new = n_eta - zb;
+                        const B2 wet_new = !(h_new < k.eps);
+                        const P2<R> hs = sel(wet_new, h_new, splat(R(1)));
+                        if (k.friction) friction_pair(k, hs, prcp(hs), n_qx, n_qy, ld2(o_m, T::P_N), dt, wet_new);
+                        const P2<R> n_emax = sel((n_eta > emax) & (emax > R(-9990.0)), n_eta, emax);
+                        n_eta = sel(wet_new, n_eta, zb);
+                        eta = sel(upd, n_eta, eta); emax = sel(upd, n_emax, emax);
+                        qx = sel(upd, n_qx, qx); qy = sel(upd, n_qy, qy);
+                    }
+                }
+                if (any(x_store)) {
+                    const size_t id = static_cast<size_t>(yc) * g.pitch + xa;
+                    if (wrote.a && wrote.b && x_store.b) {
+                        st_pair(d.eta + id, eta); st_pair(d.emax + id, emax); st_pair(d.qx + id, qx); st_pair(d.qy + id, qy);
+                    } else {
+                        if (wrote.a && x_store.a) { d.eta[id] = eta.a; d.emax[id] = emax.a; d.qx[id] = qx.a; d.qy[id] = qy.a; }
+                        if (wrote.b && x_store.b) { d.eta[id + 1] = eta.b; d.emax[id + 1] = emax.b; d.qx[id + 1] = qx.b; d.qy[id + 1] = qy.b; }
+                    }
+                    if (a.reduce_mode == hp::kReduceDst) {
+                        // cells left unwritten enter the reduction with what the destination holds
+                        if (!wrote.a && x_store.a) { eta.a = d.eta[id]; emax.a = d.emax[id]; qx.a = d.qx[id]; qy.a = d.qy[id]; }
+                        if (!wrote.b && x_store.b) { eta.b = d.eta[id + 1]; emax.b = d.emax[id + 1]; qx.b = d.qx[id + 1]; qy.b = d.qy[id + 1]; }
+                        ws = wide_speed2(k, eta, emax, qx, qy, zb, x_store, ws);
+                    }
+                }
+            }
+            sM = fy.m; sN = fy.n; sT = fy.t; sZ = fy.zmax; sH = fy.hL; sStop = fy.stopR;
+            dry_s = dry_p; dry_p = dry_c;
+            P = C;
+
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0 && j - 1 + T::RR < NR) issue_row(j - 1 + T::RR);
+        }
+    }
+    block_reduce_finalize<R>(ws, a, k);
+}
+
+template <class R> static int launch_godunov_wide(const StepArgs& a_in, const TmaBlockMap& maps, int alt, int sm_count, cudaStream_t st) {
+    using T = Wide<R, false>;
+    StepArgs a = a_in;
+    if (a.y1 <= a.y0) return 0;
+    static bool configured[kMaxDevices] = {};          // the attribute is per device
+    const int dev = current_device();
+    if (!configured[dev]) {
+        cudaFuncSetAttribute(godunov_step_wide<R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES);
+        cudaFuncSetAttribute(godunov_step_wide<R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES);
+        configured[dev] = true;
+    }
+    const int grid = march_grid(a, T::USE, T::NW, sizeof(R) == 8 ? HP_WIDE_GOD_CTAS64 : HP_WIDE_GOD_CTAS32, sm_count);
+    a.total_ctas = grid; a.march_runs = march_runs(a, T::USE, T::NW, grid);
+    if (alt) godunov_step_wide<R, true><<<grid, T::NW * 32, T::SMEM_BYTES, st>>>(a, maps);
+    else godunov_step_wide<R, false><<<grid, T::NW * 32, T::SMEM_BYTES, st>>>(a, maps);
     return 1;
 }
 

@@ -75,15 +75,18 @@ enum {
     HP_OPT_NO_TMA      = 1u << 2, /* use the plain-load kernels instead of the TMA-staged ones     */
     HP_OPT_TILE_KERNELS = 1u << 3, /* MUSCL-Hancock: use the TMA tile kernel (CTA-wide 2-D tiles) instead of
                                       the default marching kernel (one warp per column strip)      */
-    HP_OPT_MARCH_GODUNOV = 1u << 4, /* Godunov: use the marching kernel instead of the default TMA tile
-                                      kernel (equal on wet domains, slower on mostly dry ones)     */
+    HP_OPT_MARCH_GODUNOV = 1u << 4, /* Godunov: use a marching kernel instead of the default TMA tile kernel
+                                      (3-7 % faster on fully wet domains, slower on mostly dry ones; one
+                                      column per lane in fp64, two in fp32 unless pinned below)    */
     HP_OPT_SPLIT_STRIPS = 1u << 5, /* row strips: always split a step into edge rows + interior rows with
                                       the halo exchange overlapped (default only for large strips) */
     HP_OPT_NARROW_MARCH = 1u << 6, /* marching kernels: one column per lane even where the two-column
-                                      ("wide") kernel is the default (inertial, fp32 MUSCL-Hancock)  */
+                                      ("wide") kernel is the default (inertial, fp32 MUSCL-Hancock,
+                                      fp32 marching Godunov)                                       */
     HP_OPT_WIDE_MARCH  = 1u << 7   /* marching kernels: two columns per lane even where the one-column
-                                      kernel is the default (fp64 MUSCL-Hancock: fewer instructions
-                                      but too few resident warps)                   */
+                                      kernel is the default (fp64 MUSCL-Hancock and fp64 marching
+                                      Godunov: fewer instructions but too few resident warps,
+                                      DESIGN.md 4.4)                                               */
 };
 
 /*

@@ -132,7 +132,7 @@ TOLERANCE_CASES = [
 # kernel of each scheme (Godunov marching, MUSCL-Hancock tiles, inertial one column per lane); "fast-narrow" /
 # "fast-wide" pin the marching kernels to one / two columns per lane whatever the default of the precision is
 OTHER_KERNELS = hx.OPT_TILE_KERNELS | hx.OPT_MARCH_GODUNOV | hx.OPT_NARROW_MARCH
-WIDTHS = [hx.OPT_NARROW_MARCH, hx.OPT_WIDE_MARCH]
+WIDTHS = [hx.OPT_NARROW_MARCH, hx.OPT_WIDE_MARCH | hx.OPT_MARCH_GODUNOV]
 
 
 @pytest.mark.parametrize("options", [hx.OPT_STRICT_FP, 0, hx.OPT_NO_GRAPH, OTHER_KERNELS] + WIDTHS,

@@ -96,8 +96,10 @@ WRAP_CASES = [
     pytest.param("dambreak4096-inertial-f32", 4096, 4096, 0, None, id="inertial-f32-dambreak"),
     pytest.param("dambreak4096-inertial", 4096, 4096, NARROW, None, id="inertial-narrow-f64-dambreak"),
     pytest.param("dambreak4096-inertial-f32", 4096, 4096, NARROW, None, id="inertial-narrow-f32-dambreak"),
-    pytest.param("dambreak4096", 3072, 4096, MARCH, None, id="godunov-march-f64-dambreak"),
-    pytest.param("dambreak4096-f32", 3072, 4096, MARCH, None, id="godunov-march-f32-dambreak"),
+    pytest.param("dambreak4096", 3072, 4096, MARCH | NARROW, None, id="godunov-march-f64-dambreak"),
+    pytest.param("dambreak4096-f32", 3072, 4096, MARCH | NARROW, None, id="godunov-march-f32-dambreak"),
+    pytest.param("dambreak4096", 4096, 4096, MARCH | WIDE, None, id="godunov-wide-f64-dambreak"),
+    pytest.param("dambreak4096-f32", 4096, 4096, MARCH | WIDE, None, id="godunov-wide-f32-dambreak"),
     # the tile kernel: 1024 x 1536 = 32 x 192 = 6144 tiles > 888 (fp64) / 1332 (fp32) resident CTAs
     pytest.param("dambreak4096", 1024, 1536, 0, None, id="godunov-tiles-f64-dambreak"),
     pytest.param("dambreak4096-f32", 1024, 1536, 0, None, id="godunov-tiles-f32-dambreak"),
@@ -114,9 +116,9 @@ def test_wrapping_kernels_match_the_oracle(ex, workload, rows, cols, options, t0
     orc.close()
 
 
-@pytest.mark.parametrize("scheme,options", [("godunov", 0), ("godunov", MARCH), ("muscl-hancock", WIDE), ("muscl-hancock", NARROW),
-                                            ("inertial", 0), ("inertial", NARROW)],
-                         ids=["godunov-tiles", "godunov-march", "mh-wide", "mh-narrow", "inertial-wide", "inertial-narrow"])
+@pytest.mark.parametrize("scheme,options", [("godunov", 0), ("godunov", MARCH | NARROW), ("godunov", MARCH | WIDE), ("muscl-hancock", WIDE),
+                                            ("muscl-hancock", NARROW), ("inertial", 0), ("inertial", NARROW)],
+                         ids=["godunov-tiles", "godunov-march", "godunov-wide", "mh-wide", "mh-narrow", "inertial-wide", "inertial-narrow"])
 def test_wrapping_kernels_on_wet_dry_terrain(ex, scheme, options):
     """Random rough terrain with wet and dry patches, fronts everywhere (the adversarial generator of the small parity
     cases) at a size where the persistent loops wrap: every dry-side / stop-flag / stale-destination branch next to a

@@ -14,6 +14,7 @@ SCHEME_INERTIAL = "inertial"
 QUIRK_REDUCE_BUFFER_A = 1    # Q1: the CFL reduction always reads buffer "Cell states"
 QUIRK_BDY_COVERAGE = 2       # Q6: bdy_Uniform/bdy_Gridded cover floor(n/8)*8 cells per axis
 QUIRK_MH_NO_BOUNDARIES = 4   # Q4: MUSCL-Hancock never applies boundary kernels
+QUIRK_GODUNOV_DT0_KEEP = 8   # gts_cacheEnabled's rule: a Godunov step with timestep <= 0 writes nothing (default: copies through)
 QUIRKS_REFERENCE = QUIRK_REDUCE_BUFFER_A | QUIRK_BDY_COVERAGE
 
 # src/Boundaries/CLBoundaries.clh:31-52

@@ -513,7 +513,8 @@ int hp_scheme_create(hp_executor* ex, const hp_scheme_config* cfg, hp_scheme** o
     g.own_y0 = static_cast<int>(cfg->halo_south); g.own_y1 = g.rows - static_cast<int>(cfg->halo_north);
     s->params = hp::ParamsD{cfg->dry_threshold, cfg->dry_threshold * 10, cfg->delta, cfg->courant, cfg->end_time,
                             cfg->fixed_timestep, static_cast<int>(cfg->dynamic_timestep), static_cast<int>(cfg->friction),
-                            cfg->scheme == HP_SCHEME_INERTIAL ? 1 : 0};
+                            cfg->scheme == HP_SCHEME_INERTIAL ? 1 : 0,
+                            (cfg->scheme == HP_SCHEME_GODUNOV && (cfg->quirks & HP_QUIRK_GODUNOV_DT0_KEEP)) ? 1 : 0};
     s->plane_bytes = static_cast<size_t>(g.rows) * g.pitch * s->rb;
     int rc = HP_OK;
     do {

@@ -393,7 +393,7 @@ godunov_step_tma(const StepArgs a, const __grid_constant__ TmaMaps maps) {
             bool have_new = false;
             if (interior) {
                 if (dt <= R(0)) {
-                    wrote = true;
+                    wrote = !k.dt0_keep;                                 // CLSchemeGodunov.clc:201-206 (:477-478 with the quirk)
                 } else if (c.emax <= R(-9999.0) || c.eta == R(-9999.0)) {
                     wrote = true;
                 } else {

@@ -38,7 +38,7 @@ template <class R> __device__ __forceinline__ Params<R> make_params(const Params
     k.eps = static_cast<R>(p.eps); k.eps10 = static_cast<R>(p.eps10); k.delta = static_cast<R>(p.delta);
     k.courant = static_cast<R>(p.courant); k.end_time = static_cast<R>(p.end_time);
     k.fixed_dt = static_cast<R>(p.fixed_dt);
-    k.dynamic = p.dynamic; k.friction = p.friction; k.simplified_speed = p.simplified_speed;
+    k.dynamic = p.dynamic; k.friction = p.friction; k.simplified_speed = p.simplified_speed; k.dt0_keep = p.dt0_keep;
     return k;
 }
 
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(kTileX* kTileY) step_pingpong_v1(const StepArg
         const bool interior = x >= 1 && x <= g.cols - 2 && gy >= 1 && gy <= g.grows - 2;  // frozen outer ring
         if (interior) {
             if (SCHEME == 0 && dt <= R(0)) {
-                wrote = true;                                        // CLSchemeGodunov.clc:201-206
+                wrote = !k.dt0_keep;                                 // CLSchemeGodunov.clc:201-206 (:477-478 with the quirk)
             } else if (dt <= R(0)) {
                 wrote = false;                                       // CLSchemeInertial.clc:60-61
             } else if (c.emax <= R(-9999.0) || c.eta == R(-9999.0)) {

@@ -35,6 +35,7 @@ struct Grid {
 struct ParamsD {
     double eps, eps10, delta, courant, end_time, fixed_dt;
     int dynamic, friction, simplified_speed;
+    int dt0_keep;             // Godunov, dt <= 0: nothing is written (HP_QUIRK_GODUNOV_DT0_KEEP)
 };
 
 enum ReduceMode { kReduceNone = 0, kReduceSrc = 1, kReduceDst = 2 };

@@ -310,7 +310,7 @@ godunov_step_march(const StepArgs a, const __grid_constant__ TmaBlockMap maps) {
                 const int eStop = __shfl_down_sync(FULL, fx.stopL, 1);
                 if (x_interior && gyc >= 1 && gyc <= g.grows - 2) {                  // frozen outer ring
                     if (!stepping) {
-                        wrote = true;                                                   // CLSchemeGodunov.clc:201-206
+                        wrote = !k.dt0_keep;                                            // CLSchemeGodunov.clc:201-206 (:477-478)
                     } else if (c.emax <= R(-9999.0) || c.eta == R(-9999.0)) {
                         wrote = true;                                                   // disabled cell: copied through
                     } else {

@@ -918,8 +918,9 @@ godunov_step_wide(const StepArgs a, const __grid_constant__ TmaBlockMap maps) {
                     const bool rows_ok = gyc >= 1 && gyc <= g.grows - 2;                    // frozen outer ring
                     const B2 all_dry = dry_p & dry_c & dry_s & dry_e & dry_w;               // CLSchemeGodunov.clc:248-255
                     const B2 upd = (x_interior & !disabled & !all_dry) & (rows_ok && stepping);
-                    // dt <= 0 copies the state through (:201-206), and so does a disabled cell
-                    wrote = stepping ? (x_interior & (disabled | !all_dry)) & rows_ok : x_interior & rows_ok;
+                    // dt <= 0 copies the state through (:201-206; not with gts_cacheEnabled's rule, :477-478), and so does a
+                    // disabled cell
+                    wrote = stepping ? (x_interior & (disabled | !all_dry)) & rows_ok : x_interior & (rows_ok && !k.dt0_keep);
                     if (__any_sync(FULL, any(upd))) {
                         const P2<R> bN = pmin(fy.zmax, eta), bS = pmin(sZ, eta), bE = pmin(eZ, eta), bW = pmin(fx.zmax, eta);
                         const B2 stop{fy.stopL.a + sStop.a + fx.stopR.a + eStop.a > 0, fy.stopL.b + sStop.b + fx.stopR.b + eStop.b > 0};

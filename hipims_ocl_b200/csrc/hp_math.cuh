@@ -33,6 +33,7 @@ template <class R> struct Params {
     int dynamic;  // TIMESTEP_DYNAMIC
     int friction; // FRICTION_ENABLED
     int simplified_speed;  // TIMESTEP_SIMPLIFIED (inertial program, CLSchemeInertial.clh:25)
+    int dt0_keep;          // gts_cacheEnabled's rule for dt <= 0: return before any write (CLSchemeGodunov.clc:477-478)
 };
 
 using hp::Clock;  // device-resident clock record, see hp_kernels.cuh

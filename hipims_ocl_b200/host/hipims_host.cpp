@@ -1073,6 +1073,7 @@ void CScheme::prepareSimulationState() {   // CSchemeGodunov.cpp:1053-1071
 
 void CScheme::runSimulation(double dTarget, double dRealTime) {      // CSchemeGodunov.cpp:1374-1453 + one Threaded_runBatch pass
     if (!pScheme) return;
+    if (dTarget <= 0.0) { dTargetTime = dTarget; return; }     // "No target time? Can't run anything yet then" (:1384-1386)
     if (dCurrentTime > dTarget + 1E-5) { model::doError("Simulation has exceeded target time", model::errorCodes::kLevelWarning); return; }   // :1389-1405
     // batch size: aim for a second of wall clock per batch (:1419-1450; single domain, so no rollback budget to respect).
     // Decided once, here, for all strips: they must enqueue the same number of iterations.
@@ -1086,13 +1087,18 @@ void CScheme::runSimulation(double dTarget, double dRealTime) {      // CSchemeG
     }
     dBatchStartedTime = dRealTime;
     const bool bNewTarget = dTarget != dTargetTime;
-    const bool bUpdate = bNewTarget && dCurrentTimestep <= 0.0;        // forecast sync, :1191-1196
+    const bool bUpdate = bNewTarget && dCurrentTimestep <= 0.0 && ucSyncMethod == model::syncMethod::kSyncForecast;   // :1191-1196
+    // a target that moved in front of the step already decided: the timestep is overridden at the start of the batch (:1198-1232)
+    const bool bOverride = bNewTarget && dCurrentTime + dCurrentTimestep > dTarget + 1E-5 && dCurrentTime < dTarget;
+    const double dOverride = dTarget - dCurrentTime;
     dTargetTime = dTarget;
-    const unsigned int uiBatch = uiQueueAdditionSize;
+    // "Do we need to run any work?" (:1284-1285)
+    const unsigned int uiBatch = (dCurrentTime < dTargetTime) ? uiQueueAdditionSize : 0;
     forStrips([&](SStrip& st, size_t) {
         if (bNewTarget) HP_CHECK(hp_scheme_set_target_time(st.pHandle, dTarget), "target time");
         if (bUpdate) HP_CHECK(hp_scheme_update_timestep(st.pHandle), "timestep update");
-        HP_CHECK(hp_scheme_iterate(st.pHandle, uiBatch), "iterate");
+        if (bOverride) HP_CHECK(hp_scheme_force_timestep(st.pHandle, dOverride), "timestep override");
+        if (uiBatch) HP_CHECK(hp_scheme_iterate(st.pHandle, uiBatch), "iterate");
         HP_CHECK(hp_scheme_sync(st.pHandle), "sync");
     });
     ulCurrentCellsCalculated += static_cast<unsigned long long>(uiBatch) * pDomain->getCellCount();
@@ -1140,6 +1146,9 @@ bool CScheme::deriveRaster(unsigned char ucValue, std::vector<double>& northFirs
 }
 bool CScheme::isSimulationSyncReady(double dExpected) const { return !(dExpected - dCurrentTime > 1E-5); }       // CSchemeGodunov.cpp:1568-1612
 bool CScheme::isSimulationFailure(double dExpected) const {                                                      // :1523-1555
+    // can't exceed the number of buffer cells in forecast mode; in timestep mode this "shouldn't happen"
+    if (ucSyncMethod == model::syncMethod::kSyncForecast && uiBatchSuccessful >= uiRollbackLimit && dExpected - dCurrentTime > 1E-5) return true;
+    if (ucSyncMethod == model::syncMethod::kSyncTimestep && uiBatchSuccessful > uiRollbackLimit) return true;
     if (dCurrentTime > dExpected + 1E-5) { model::doError("Scheme has exceeded target sync time. Rolling back...", model::errorCodes::kLevelWarning); return true; }
     return false;
 }
@@ -1211,6 +1220,12 @@ bool CModel::loadConfiguration(const std::string& sPath, bool bDeviceless) {
         else model::doError("Unrecognised parameter: " + key, model::errorCodes::kLevelWarning);
     }
     const XMLElement* set = sim->FirstChildElement("domainSet");
+    if (set) {                                                     // src/Domain/CDomainManager.cpp:56-76
+        const std::string sSync = Util::toLowercase(set->Attribute("syncMethod"));
+        if (sSync == "timestep") ucSyncMethod = model::syncMethod::kSyncTimestep;
+        else if (sSync == "forecast" || sSync.empty()) ucSyncMethod = model::syncMethod::kSyncForecast;
+        else model::doError("Unrecognised synchronisation method: " + sSync, model::errorCodes::kLevelWarning);
+    }
     const XMLElement* dom = set ? set->FirstChildElement("domain") : nullptr;
     if (!dom) { model::doError("No <domain> defined.", model::errorCodes::kLevelModelStop); return false; }
     const XMLElement* pXScheme = dom->FirstChildElement("scheme");
@@ -1264,28 +1279,126 @@ bool CModel::loadConfiguration(const std::string& sPath, bool bDeviceless) {
     return pScheme->prepareAll(pExecutor.get(), pDomain.get(), ucFloatPrecision, dSimulationTime, ordinals);
 }
 
-bool CModel::runModel() {
+// ---- the management loop (src/CModel.cpp) ---------------------------------------------------------------------------------
+bool CModel::runModel() {                                                      // :217-262
     if (!pScheme || !pScheme->isReady()) return false;
-    pScheme->prepareSimulation();
-    const auto tStart = std::chrono::steady_clock::now();
-    double nextOutput = dOutputFrequency > 0.0 ? dOutputFrequency : dSimulationTime;
-    while (!model::forceAbort && pScheme->getCurrentTime() < dSimulationTime - 1E-5) {
-        const double target = std::min(nextOutput, dSimulationTime);
-        while (!model::forceAbort && !pScheme->isSimulationSyncReady(target)) {
-            const double dRealTime = bRealTimeQueue ? std::chrono::duration<double>(std::chrono::steady_clock::now() - tStart).count() + 1E-4 : 0.0;
-            pScheme->runSimulation(target, dRealTime);
-            if (pScheme->isSimulationFailure(target)) { model::forceAbort = true; break; }     // cannot happen: the device clock stops at the target
-        }
-        if (parts.empty()) {
-            pDomain->writeOutputs(pScheme->getCurrentTime(), pScheme.get());  // derived on the device; no full-state read-back
-        } else {                                                              // every original domain gets its own rasters
-            std::map<unsigned char, std::vector<double>> bands;
-            for (size_t i = 0; i < parts.size(); ++i) parts[i]->writeCroppedOutputs(pScheme->getCurrentTime(), *pDomain, partRowOffsets[i], pScheme.get(), bands);
-        }
-        nextOutput += dOutputFrequency > 0.0 ? dOutputFrequency : dSimulationTime;
-    }
-    pScheme->readDomainAll();                                              // final state back in the CDomain arrays
+    runModelPrepare();
+    runModelMain();
+    runModelCleanup();
     return !model::forceAbort;
+}
+
+void CModel::runModelPrepare() {                                               // :497-547
+    model::forceAbort = false;
+    // "Can't have timestep sync if we've only got one domain" (:503-505) -- and a decomposed model IS one domain here
+    if (ucSyncMethod == model::syncMethod::kSyncTimestep) ucSyncMethod = model::syncMethod::kSyncForecast;
+    pScheme->setSyncMethod(ucSyncMethod);
+    pScheme->prepareSimulation();
+    pScheme->setRollbackLimit();                                               // no links: not constrained by overlapping
+    bSynchronised = true; bAllIdle = true; bRollbackRequired = false; bWaitOnLinks = false;
+    dTargetTime = 0.0; dLastSyncTime = -1.0; dLastOutputTime = 0.0; dCurrentTime = 0.0; dEarliestTime = 0.0; dGlobalTimestep = 0.0;
+    uiSyncCount = 0; uiOutputCount = 0;
+}
+
+void CModel::runModelDomainAssess(bool* bSyncReady, bool* bIdle) {             // :552-692
+    bRollbackRequired = false; dEarliestTime = 0.0; bWaitOnLinks = false;
+    dEarliestTime = pScheme->getCurrentTime();                                 // the minimum over the local domains
+    // either we're not ready to sync, or we were still synced from the last run
+    if (!pScheme->isSimulationSyncReady(dTargetTime) || bSynchronised || dLastSyncTime == dEarliestTime) {
+        bSyncReady[0] = false;
+        if (pScheme->isSimulationFailure(dTargetTime)) bRollbackRequired = true;
+    } else {
+        bSyncReady[0] = true;
+    }
+    bIdle[0] = true;                          // CScheme::runSimulation returns once its batch has left the device
+    bSynchronised = bSyncReady[0]; bAllIdle = bIdle[0];
+    if (bAllIdle && !bWaitOnLinks) {
+        dGlobalTimestep = pScheme->getCurrentTimestep() > 0.0 ? pScheme->getCurrentTimestep() : 0.0;
+        dCurrentTime = dEarliestTime;
+    }
+}
+
+void CModel::runModelDomainExchange() {}      // :697-713 importLinkZoneData: the strips exchanged their halo rows on the device
+
+void CModel::runModelUpdateTarget(double dTimeBase) {                          // :718-770
+    double dEarliestSyncProposal = dSimulationTime;
+    // several domains in forecast mode would take the smallest proposeSyncPoint here (:730-738); one domain runs free
+    // until outputs are needed.  Don't exceed an output interval:
+    const double dFrequency = dOutputFrequency > 0.0 ? dOutputFrequency : dSimulationTime;
+    if (std::floor(dEarliestSyncProposal / dFrequency) > std::floor(dLastSyncTime / dFrequency))
+        dEarliestSyncProposal = (std::floor(dLastSyncTime / dFrequency) + 1.0) * dFrequency;
+    (void)dTimeBase;
+    dTargetTime = dEarliestSyncProposal;
+}
+
+void CModel::writeOutputs() {
+    if (parts.empty()) {
+        pDomain->writeOutputs(dCurrentTime, pScheme.get());                    // derived on the device; no full-state read-back
+    } else {                                                                   // every original domain gets its own rasters
+        std::map<unsigned char, std::vector<double>> bands;
+        for (size_t i = 0; i < parts.size(); ++i) parts[i]->writeCroppedOutputs(dCurrentTime, *pDomain, partRowOffsets[i], pScheme.get(), bands);
+    }
+    ++uiOutputCount;
+}
+
+void CModel::runModelOutputs() {                                               // :859-882
+    const double dFrequency = dOutputFrequency > 0.0 ? dOutputFrequency : dSimulationTime;
+    if (bRollbackRequired || !bSynchronised || !bAllIdle ||
+        !(std::fabs(dCurrentTime - dLastOutputTime - dFrequency) < 1E-5 && dCurrentTime > dLastOutputTime))
+        return;
+    writeOutputs();
+    dLastOutputTime = dCurrentTime;
+    pScheme->forceTimeAdvance();
+}
+
+void CModel::runModelSync() {                                                  // :775-835
+    if (bRollbackRequired || !bSynchronised || !bAllIdle) return;
+    // no rollback required, thus the simulation time can now be increased to match the target
+    dCurrentTime = dEarliestTime;
+    dLastSyncTime = dCurrentTime;
+    ++uiSyncCount;
+    runModelOutputs();
+    runModelUpdateTarget(dCurrentTime);
+    // the state goes back to host memory only where a rollback could need it (several domains in forecast mode) or
+    // outputs are about to be written from it (:808-817); the rasters here are derived on the device
+    const double dFrequency = dOutputFrequency > 0.0 ? dOutputFrequency : dSimulationTime;
+    if (std::fabs(dCurrentTime - dLastOutputTime - dFrequency) < 1E-5 && dCurrentTime > dLastOutputTime) pScheme->saveCurrentState();
+    runModelDomainExchange();
+}
+
+void CModel::runModelSchedule(double dSeconds, bool* bIdle) {                  // :897-943
+    // keep running each domain until we're ready for synchronisation
+    if (!bSynchronised && bIdle[0]) {
+        if (ucSyncMethod == model::syncMethod::kSyncTimestep && dGlobalTimestep > 0.0) pScheme->forceTimestep(dGlobalTimestep);
+        pScheme->runSimulation(dTargetTime, dSeconds);
+    }
+}
+
+void CModel::runModelRollback() {                                              // :964-1021
+    if (!bRollbackRequired || model::forceAbort || !bAllIdle) return;
+    model::doError("Rollback invoked - code not yet ready", model::errorCodes::kLevelModelStop);     // the reference stops here too (:971-974)
+    bRollbackRequired = false; bSynchronised = false;
+    runModelUpdateTarget(dLastSyncTime);
+    dEarliestTime = dLastSyncTime; dCurrentTime = dLastSyncTime;
+    pScheme->rollbackSimulation(dLastSyncTime, dTargetTime);
+}
+
+void CModel::runModelCleanup() {                                               // :1027-1035
+    pScheme->readDomainAll();                 // final state back in the CDomain arrays (the strips stay until the model goes)
+}
+
+void CModel::runModelMain() {                                                  // :1041-1139
+    bool bSyncReady[1] = {false}, bIdle[1] = {true};
+    const auto tStart = std::chrono::steady_clock::now();
+    // even if the user has forced an abort, still wait until the all-idle state is reached
+    while ((dCurrentTime < dSimulationTime - 1E-5 && !model::forceAbort) || !bAllIdle) {
+        runModelDomainAssess(bSyncReady, bIdle);
+        runModelRollback();
+        runModelSync();
+        if (bRollbackRequired) continue;
+        const double dSeconds = bRealTimeQueue ? std::chrono::duration<double>(std::chrono::steady_clock::now() - tStart).count() + 1E-4 : 0.0;
+        runModelSchedule(dSeconds, bIdle);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1320,6 +1433,12 @@ void* hph_model_load_on(const char* path, const int* devices, int count) {
     m->setStripDevices(std::vector<int>(devices, devices + count));
     if (!m->loadConfiguration(path, false)) { delete m; return nullptr; }
     return m;
+}
+// the management loop's bookkeeping after (or before) a run: synchronisations, output sets written, target, last sync time
+void hph_model_loop_state(void* h, unsigned int* syncs, unsigned int* outputs, double* target, double* last_sync, double* current, int* sync_method) {
+    CModel* m = static_cast<CModel*>(h);
+    *syncs = m->getSyncCount(); *outputs = m->getOutputCount(); *target = m->getTargetTime(); *last_sync = m->getLastSyncTime();
+    *current = m->getCurrentTime(); *sync_method = m->getSyncMethod();
 }
 void hph_model_set_realtime_queue(void* h, int on) { static_cast<CModel*>(h)->setRealTimeQueue(on != 0); }
 // rollback: put the host arrays and clock back on the device, then report the recomputed timestep

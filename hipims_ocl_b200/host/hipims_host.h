@@ -27,6 +27,7 @@ namespace model {
 namespace errorCodes { enum errorCodes { kLevelFatal = 1, kLevelModelStop = 2, kLevelModelContinue = 4, kLevelWarning = 8, kLevelInformation = 16 }; }
 namespace floatPrecision { enum floatPrecision { kSingle = 0, kDouble = 1 }; }
 namespace schemeTypes { enum schemeTypes { kGodunov = 0, kMUSCLHancock = 1, kInertialSimplification = 2 }; }
+namespace syncMethod { enum syncMethod { kSyncTimestep = 0, kSyncForecast = 1 }; }     // src/Schemes/CScheme.h:57-62
 extern bool forceAbort;
 extern std::vector<std::string> errorLog;       // every doError message, newest last
 void doError(const std::string& message, unsigned char level);
@@ -247,7 +248,13 @@ class CScheme {
     // synchronisation surface of CScheme (src/Schemes/CScheme.h:85-129, CSchemeGodunov.cpp:1474-1616, 1741-1816).  With one
     // merged domain per device there are no link zones, so the rollback limit never binds; the calls keep their meaning.
     bool isSimulationSyncReady(double dExpectedTargetTime) const;       // the target has been reached (to 1e-5 s)
-    bool isSimulationFailure(double dExpectedTargetTime) const;         // the scheme has run past the target
+    bool isSimulationFailure(double dExpectedTargetTime) const;         // past the target, or out of rollback budget before it
+    // iterations a domain may run between two exchanges of its link zones (src/Domain/CDomainBase.cpp:163-174: the
+    // smallest overlap - 1).  The strips of this engine exchange their halo rows in every iteration, so a domain is "not
+    // constrained by overlapping" (src/CModel.cpp:543) and keeps the unconstrained value.
+    unsigned int getRollbackLimit() const { return uiRollbackLimit; }
+    void setRollbackLimit(unsigned int v = 999999999u) { uiRollbackLimit = v; }
+    void setSyncMethod(unsigned char m) { ucSyncMethod = m; }
     void rollbackSimulation(double dCurrentTime, double dTargetTime);   // host cell arrays + clock back onto the device
     double proposeSyncPoint(double dCurrentTime) const;
     void forceTimeAdvance() {}                                          // the device clock always advances (no suspended state to leave)
@@ -296,14 +303,19 @@ class CScheme {
     double dCurrentTime = 0, dCurrentTimestep = 0, dBatchTimesteps = 0, dTargetTime = 0;
     unsigned int uiBatchSuccessful = 0, uiBatchSkipped = 0;
     unsigned long long ulCurrentCellsCalculated = 0;
+    unsigned int uiRollbackLimit = 999999999u;
+    unsigned char ucSyncMethod = model::syncMethod::kSyncForecast;
 };
 class CSchemeGodunov : public CScheme { public: CSchemeGodunov() : CScheme(model::schemeTypes::kGodunov) {} };
 class CSchemeMUSCLHancock : public CScheme { public: CSchemeMUSCLHancock() : CScheme(model::schemeTypes::kMUSCLHancock) {} };
 class CSchemeInertial : public CScheme { public: CSchemeInertial() : CScheme(model::schemeTypes::kInertialSimplification) {} };
 
 // ---------------------------------------------------------------------------------------------
-// Minimal model driver: configuration file -> run to `duration`, writing outputs every
-// `outputFrequency` seconds (src/CModel.cpp:217, 1041-1139 without the polling UI).
+// Model driver: configuration file -> run to `duration`, writing outputs every `outputFrequency` seconds.  runModel is
+// the reference's management loop (src/CModel.cpp:497-527, 552-1139: assess -> rollback -> sync [outputs, new target]
+// -> schedule) over ONE local domain, without the polling UI and the MPI hooks; the row strips of a decomposed model
+// live inside the domain's scheme and exchange on the device, so "all domains idle / synchronised" is decided from one
+// clock.
 // ---------------------------------------------------------------------------------------------
 class CModel {
   public:
@@ -311,6 +323,24 @@ class CModel {
     // src/main.cpp:376 + src/Datasets/CXMLDataset.cpp:115-260; bDeviceless parses only (no executor, CPU tests)
     bool loadConfiguration(const std::string& sPath, bool bDeviceless = false);
     bool runModel();
+    // the phases of src/CModel.cpp:497-1139, same names and the same state between them
+    void runModelPrepare();
+    void runModelMain();
+    void runModelDomainAssess(bool* bSyncReady, bool* bIdle);
+    void runModelDomainExchange();
+    void runModelUpdateTarget(double dTimeBase);
+    void runModelSync();
+    void runModelOutputs();
+    void runModelSchedule(double dSeconds, bool* bIdle);
+    void runModelRollback();
+    void runModelCleanup();
+    void writeOutputs();
+    unsigned char getSyncMethod() const { return ucSyncMethod; }
+    double getCurrentTime() const { return dCurrentTime; }
+    double getTargetTime() const { return dTargetTime; }
+    double getLastSyncTime() const { return dLastSyncTime; }
+    unsigned int getSyncCount() const { return uiSyncCount; }
+    unsigned int getOutputCount() const { return uiOutputCount; }
     // pass wall-clock time to CScheme::runSimulation so that queueMode="auto" sizes batches for about a second of work
     // (src/CModel.cpp:1041-1139); off by default so that iteration counts are reproducible
     void setRealTimeQueue(bool b) { bRealTimeQueue = b; }
@@ -327,6 +357,11 @@ class CModel {
   private:
     bool bRealTimeQueue = false;
     double dSimulationTime = 0, dOutputFrequency = 0;
+    // src/CModel.h:105-119
+    double dCurrentTime = 0, dLastSyncTime = -1.0, dLastOutputTime = 0, dTargetTime = 0, dEarliestTime = 0, dGlobalTimestep = 0;
+    bool bRollbackRequired = false, bAllIdle = true, bWaitOnLinks = false, bSynchronised = true;
+    unsigned char ucSyncMethod = model::syncMethod::kSyncForecast;     // <domainSet syncMethod=..>, CDomainManager.cpp:56-76
+    unsigned int uiSyncCount = 0, uiOutputCount = 0;
     unsigned char ucFloatPrecision = model::floatPrecision::kDouble;
     std::unique_ptr<CExecutorControlCUDA> pExecutor;
     std::unique_ptr<CDomainCartesian> pDomain;

@@ -63,8 +63,12 @@ enum {
                                             (src/Schemes/CSchemeGodunov.cpp:1629,1634)              */
     HP_QUIRK_BDY_COVERAGE     = 1u << 1, /* bdy_Uniform / bdy_Gridded cover floor(n/8)*8 cells per
                                             axis (src/Boundaries/CBoundaryUniform.cpp:294-295)      */
-    HP_QUIRK_MH_NO_BOUNDARIES = 1u << 2  /* MUSCL-Hancock iteration applies no boundaries
+    HP_QUIRK_MH_NO_BOUNDARIES = 1u << 2, /* MUSCL-Hancock iteration applies no boundaries
                                             (src/Schemes/CSchemeMUSCLHancock.cpp:646-680)           */
+    HP_QUIRK_GODUNOV_DT0_KEEP = 1u << 3  /* Godunov, timestep <= 0: leave the destination untouched like
+                                            gts_cacheEnabled (src/Schemes/CLSchemeGodunov.clc:477-478)
+                                            instead of copying the source through like the default
+                                            gts_cacheDisabled (:201-206); not in the reference default  */
 };
 
 /* Execution options (not part of the numerical contract). */

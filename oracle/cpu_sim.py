@@ -22,6 +22,7 @@ _REF_SCHEME = {"godunov": "godunov", "muscl-hancock": "mh", "inertial": "inertia
 QUIRK_REDUCE_BUFFER_A = 1
 QUIRK_BDY_COVERAGE = 2
 QUIRK_MH_NO_BOUNDARIES = 4
+QUIRK_GODUNOV_DT0_KEEP = 8
 
 
 class HpoConfig(C.Structure):

@@ -41,11 +41,13 @@ enum Dir { N = 0, E = 1, S = 2, W = 3 };  // src/Domain/Cartesian/CLDomainCartes
 template <class R> struct Consts {
     R g, eps, eps10, delta, courant, end_time, fixed_dt;
     int64_t cols, rows;
+    bool dt0_keep;  // gts_cacheEnabled returns before any write when dt <= 0 (src/Schemes/CLSchemeGodunov.clc:477-478)
     explicit Consts(const hpo_config& c)
         : g(R(9.81)),  // src/OpenCL/Executors/CLUniversalHeader.clh:33
           eps(static_cast<R>(c.very_small)), eps10(static_cast<R>(c.quite_small)), delta(static_cast<R>(c.delta)),
           courant(static_cast<R>(c.courant)), end_time(static_cast<R>(c.end_time)),
-          fixed_dt(static_cast<R>(c.fixed_dt)), cols(c.cols), rows(c.rows) {}
+          fixed_dt(static_cast<R>(c.fixed_dt)), cols(c.cols), rows(c.rows),
+          dt0_keep((c.quirks & HPO_QUIRK_GODUNOV_DT0_KEEP) != 0) {}
 };
 
 /* One side of a Riemann problem: the reference's 8-vector {eta,h,qx,qy,u,v,zb,-}. */
@@ -201,7 +203,7 @@ template <class R>
 void godunov_cell(const Consts<R>& k, bool friction, int64_t x, int64_t y, R dt, const R* bed, const Vec4<R>* src,
                   Vec4<R>* dst, const R* manning) {
     const int64_t id = y * k.cols + x;
-    if (dt <= R(0)) { dst[id] = src[id]; return; }                                               // :201-206
+    if (dt <= R(0)) { if (!k.dt0_keep) dst[id] = src[id]; return; }                              // :201-206 (:477-478)
     Vec4<R> c = src[id];
     const R zb = bed[id];
     if (c.y <= R(-9999.0) || c.x == R(-9999.0)) { dst[id] = c; return; }                         // :214-218

@@ -32,7 +32,8 @@ enum { HPO_SCHEME_GODUNOV = 0, HPO_SCHEME_MUSCL_HANCOCK = 1, HPO_SCHEME_INERTIAL
 enum {
     HPO_QUIRK_REDUCE_BUFFER_A   = 1u << 0, /* Q1: tst_Reduce always reads "Cell states"      */
     HPO_QUIRK_BDY_COVERAGE      = 1u << 1, /* Q6: bdy_Uniform/Gridded global = floor(n/8)*8   */
-    HPO_QUIRK_MH_NO_BOUNDARIES  = 1u << 2  /* Q4: MUSCL-Hancock never applies boundaries      */
+    HPO_QUIRK_MH_NO_BOUNDARIES  = 1u << 2, /* Q4: MUSCL-Hancock never applies boundaries      */
+    HPO_QUIRK_GODUNOV_DT0_KEEP  = 1u << 3  /* gts_cacheEnabled's rule for dt <= 0: no write   */
 };
 
 typedef struct hpo_config {

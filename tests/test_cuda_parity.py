@@ -258,6 +258,42 @@ def test_sync_point_suspension_and_update(ex):
     np.testing.assert_array_equal(gpu.download(), orc.download())
 
 
+@pytest.mark.parametrize("options", [hx.OPT_STRICT_FP, 0, hx.OPT_MARCH_GODUNOV | hx.OPT_NARROW_MARCH, hx.OPT_MARCH_GODUNOV | hx.OPT_WIDE_MARCH],
+                         ids=["strict", "tiles", "march", "wide"])
+def test_godunov_dt0_keep_rule(ex, options):
+    """HP_QUIRK_GODUNOV_DT0_KEEP: once the clock sits at its target (timestep <= 0) a Godunov step leaves the destination
+    untouched -- gts_cacheEnabled's rule (CLSchemeGodunov.clc:477-478) -- instead of copying the source through like the
+    default gts_cacheDisabled (:201-206); both ping-pong buffers then stay what they were, the older one stale."""
+    n = 96
+    cfg = make_cfg("godunov", "double", n, n, friction=False)
+    cfg.quirks |= hc.QUIRK_GODUNOV_DT0_KEEP
+    bed, st, man = scenario("dambreak", n, n, np.float64)
+    orc = cpu_sim.CpuSim("oracle", cfg)
+    gpu = hx.CudaScheme(ex, cfg, options=options)
+    for sim in (orc, gpu):
+        sim.upload(st, bed, man)
+        sim.set_target(0.25)
+        sim.iterate(33)                     # reaches the target after ~20 iterations; an odd count on purpose
+    so, sg = orc.stats(), gpu.stats()
+    assert sg["timestep"] < 0 and sg["batch_skipped"] == so["batch_skipped"] > 2
+    (ao, bo), (ag, bg) = orc.download_both(), gpu.download_both()
+    assert not np.array_equal(ao, bo)                                   # the older buffer was left alone
+    if options & hx.OPT_STRICT_FP:
+        np.testing.assert_array_equal(ag, ao)
+        np.testing.assert_array_equal(bg, bo)
+    else:
+        assert np.abs(ag - ao).max() <= 1e-9 and np.abs(bg - bo).max() <= 1e-9
+    for sim in (orc, gpu):                                              # moving the target on resumes from the right buffer
+        sim.set_target(0.5)
+        sim.update_timestep()
+        sim.reset_counters()
+        sim.iterate(10)
+    so, sg = orc.stats(), gpu.stats()
+    assert (sg["batch_successful"], sg["batch_skipped"]) == (so["batch_successful"], so["batch_skipped"]) and so["batch_successful"] >= 5
+    assert np.abs(gpu.download() - orc.download()).max() <= (0 if options & hx.OPT_STRICT_FP else 1e-9)
+    gpu.close(); orc.close()
+
+
 def test_link_rows_roundtrip(ex):
     """hp_scheme_read_rows / write_rows (CDomainLink pull/push)."""
     cfg = make_cfg("godunov", "double", 20, 31)

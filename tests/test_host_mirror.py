@@ -599,6 +599,70 @@ def test_automatic_queue_and_rollback(host, model_dir):
     assert runs[0][1] == runs[1][1] == 30.0 and runs[0][2] == runs[1][2]
 
 
+def loop_state(host, h):
+    syncs, outputs, method = C.c_uint(), C.c_uint(), C.c_int()
+    target, last, cur = C.c_double(), C.c_double(), C.c_double()
+    host.hph_model_loop_state(C.c_void_p(h), C.byref(syncs), C.byref(outputs), C.byref(target), C.byref(last), C.byref(cur), C.byref(method))
+    return dict(syncs=syncs.value, outputs=outputs.value, target=target.value, last_sync=last.value, current=cur.value, sync_method=method.value)
+
+
+def test_sync_method_is_parsed(host, model_dir):
+    """<domainSet syncMethod=..> (src/Domain/CDomainManager.cpp:56-76); forecast is the default."""
+    cfg, _ = model_dir()
+    h = host.hph_model_load(cfg.encode(), 1)
+    assert loop_state(host, h)["sync_method"] == 1
+    host.hph_model_destroy(C.c_void_p(h))
+    text = open(cfg).read().replace("<domainSet>", '<domainSet syncMethod="Timestep">')
+    open(cfg, "w").write(text)
+    h = host.hph_model_load(cfg.encode(), 1)
+    assert loop_state(host, h)["sync_method"] == 0
+    host.hph_model_destroy(C.c_void_p(h))
+
+
+@pytest.mark.gpu
+def test_management_loop_follows_the_reference(host, model_dir):
+    """CModel::runModelMain (src/CModel.cpp:1041-1139): the first pass synchronises at t = 0 and sets the first target, every
+    target is the next multiple of the output frequency or the end of the simulation (:741-744), output sets are written
+    only when a synchronisation lands on such a multiple (:859-866) -- a run of 25 s with outputs every 10 s syncs at 0, 10,
+    20 and 25 s and writes the sets of 10 and 20 s -- and timestep synchronisation falls back to forecast for one domain
+    (:503-505)."""
+    from oracle import cpu_sim
+    from tests.helpers import make_cfg
+    cfg, _ = model_dir(scheme="Godunov", duration=25, outfreq=10)
+    text = open(cfg).read().replace("<domainSet>", '<domainSet syncMethod="timestep">')
+    open(cfg, "w").write(text)
+    h = host.hph_model_load(cfg.encode(), 0)
+    assert h, [host.hph_error(i) for i in range(host.hph_error_count())]
+    st0, bed, man = arrays(host, h, 30, 40)
+    assert host.hph_model_run(C.c_void_p(h)) == 0
+    ls = loop_state(host, h)
+    assert ls == dict(syncs=4, outputs=2, target=25.0, last_sync=25.0, current=25.0, sync_method=1)
+    out = os.path.join(os.path.dirname(cfg), "output")
+    assert sorted(f for f in os.listdir(out) if f.startswith("depth_")) == ["depth_10.tif", "depth_20.tif"]
+    # the same sequence of targets on the oracle: identical iteration counts and state
+    t, dt, ok, skipped = C.c_double(), C.c_double(), C.c_uint(), C.c_uint()
+    host.hph_model_clock(C.c_void_p(h), C.byref(t), C.byref(dt), C.byref(ok), C.byref(skipped))
+    st1, _, _ = arrays(host, h, 30, 40)
+    ocfg = make_cfg("godunov", "double", 30, 40, delta=2.0, end_time=25.0)
+    orc = cpu_sim.CpuSim("oracle", ocfg)
+    orc.upload(st0, bed, man)
+    orc.add_uniform(hc.UNIFORM_LOSS_RATE, [0.0, 1.0e8], [12.0, 12.0])
+    orc.add_uniform(hc.UNIFORM_RAIN_INTENSITY, [0.0, 3600.0, 7200.0, 10800.0], [70.0, 70.0, 0.0, 0.0])
+    orc.add_cell(hc.DEPTH_IGNORE, hc.DISCHARGE_IS_DISCHARGE, [10 * 40 + 1, 11 * 40 + 1, 12 * 40 + 1],
+                 [[0, 0, 0, 0], [10, 0, 1.0, 0], [100000, 0, 1.0, 0]])
+    for target in (10.0, 20.0, 25.0):
+        orc.set_target(target)
+        if orc.stats()["timestep"] <= 0.0:
+            orc.update_timestep()
+        while orc.stats()["time"] < target - 1e-5:
+            orc.iterate(16)
+    so = orc.stats()
+    assert t.value == 25.0 and (ok.value, skipped.value) == (so["batch_successful"], so["batch_skipped"])
+    assert np.abs(st1[..., 0] - orc.download()[..., 0]).max() <= 1e-9
+    orc.close()
+    host.hph_model_destroy(C.c_void_p(h))
+
+
 # ---- decomposed models from the configuration (SURVEY.md 8f-4): <domain deviceNumber=..> stacks -> the strip engine --------
 def _gpu_count():
     import torch

@@ -138,3 +138,32 @@ def test_sync_point_suspension_and_update():
     assert orc.stats() == ref.stats()
     _same(orc.download(), ref.download())
     assert orc.stats()["time"] > 0.25
+
+
+def test_godunov_dt0_keep_rule():
+    """The two Godunov kernels of the reference differ in one observable rule: with a timestep <= 0 gts_cacheDisabled
+    copies the source cell into the destination (CLSchemeGodunov.clc:201-206), gts_cacheEnabled returns before any write
+    (:477-478).  The oracle restates both (HPO_QUIRK_GODUNOV_DT0_KEEP selects the second); only the first is pinned to the
+    compiled reference -- gts_cacheEnabled needs work-group local memory, which the CPU shim does not emulate."""
+    n = 40
+    bed, st, man = scenario("dambreak", n, n, np.float64)
+    out = {}
+    for quirk in (0, hc.QUIRK_GODUNOV_DT0_KEEP):
+        cfg = make_cfg("godunov", "double", n, n)
+        cfg.quirks |= quirk
+        orc = cpu_sim.CpuSim("oracle", cfg)
+        orc.upload(st, bed, man)
+        orc.set_target(0.25)
+        orc.iterate(30)
+        assert orc.stats()["timestep"] < 0.0 and orc.stats()["batch_skipped"] > 2
+        before = orc.download_both()
+        orc.iterate(1)
+        out[quirk] = (before, orc.download_both(), orc.stats())
+        orc.close()
+    (a0, b0), (a1, b1), s_copy = out[0]
+    np.testing.assert_array_equal(a1, b1)                      # copied through: both buffers hold the state at the target
+    (a0, b0), (a1, b1), s_keep = out[hc.QUIRK_GODUNOV_DT0_KEEP]
+    np.testing.assert_array_equal(a1, a0)                      # nothing written ...
+    np.testing.assert_array_equal(b1, b0)
+    assert not np.array_equal(a1, b1)                          # ... so the older buffer stays one step behind
+    assert s_keep["time"] == s_copy["time"] == 0.25

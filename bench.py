@@ -335,7 +335,7 @@ def issue_roofline(name, value_per_gpu, sm_mhz):
             "source": "committed ncu capture (profiles/%s)" % rec.get("profile", "kernels.json")}
 
 
-def strip_parity_check(hx, ex, dist, w, rank, world, options):
+def strip_parity_check(hx, ex, dist, w, rank, world, options, exchange="nccl"):
     """Strips against ONE GPU, bit for bit: a 4096-column slab of the same workload with 256 rows per rank, 10 iterations
     through the same library calls as the timed run (NCCL halo exchange + dt all-reduce); rank 0 also runs the whole slab
     on its own GPU and compares states and clocks (what CDomainLink's exchange must guarantee,
@@ -351,10 +351,16 @@ def strip_parity_check(hx, ex, dist, w, rank, world, options):
     bed, st, man = make_inputs(ws, strip.rows, cols, dtype, row_offset=strip.row_offset - strip.halo_south, total_rows=total)
     sim = hx.CudaScheme(ex, cfg, options=options, global_rows=total, row_offset=strip.row_offset,
                         halo_south=strip.halo_south, halo_north=strip.halo_north)
-    ids = [hx.comm_unique_id() if rank == 0 else None]
-    dist.broadcast_object_list(ids, src=0)
-    sim.attach_comm(ids[0], rank, world)
-    sim.upload(st, bed, man)
+    if exchange == "peer":
+        sim.upload(st, bed, man)
+        blobs = [None] * world
+        dist.all_gather_object(blobs, sim.peer_export())
+        sim.attach_peers(rank, world, blobs)
+    else:
+        ids = [hx.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        sim.attach_comm(ids[0], rank, world)
+        sim.upload(st, bed, man)
     attach_boundaries(sim, ws, cols, total)
     sim.set_target(1.0e7)
     sim.iterate(iters)
@@ -396,6 +402,8 @@ def main():
     ap.add_argument("--no-variants", action="store_true")
     ap.add_argument("--no-strip-parity", action="store_true")
     ap.add_argument("--options", type=int, default=0, help="HP_OPT_* bit mask")
+    ap.add_argument("--exchange", choices=["nccl", "peer"], default=os.environ.get("HIPIMS_BENCH_EXCHANGE", "nccl"),
+                    help="row strips at N > 1: NCCL send/recv + all-reduce (default) or the peer-memory kernel (hp_scheme_attach_peers)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -438,7 +446,8 @@ def main():
     ex = hx.Executor(local_rank)
     sim = hx.CudaScheme(ex, cfg, options=args.options, global_rows=total_rows, row_offset=rank * rows_own, halo_south=hs,
                         halo_north=hn)
-    if world > 1:
+    peer = world > 1 and args.exchange == "peer"
+    if world > 1 and not peer:
         ids = [hx.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         sim.attach_comm(ids[0], rank, world)
@@ -465,6 +474,11 @@ def main():
     # CUDA graphs (with the NCCL exchange captured inside for small strips) are built and uploaded here, and 36
     # untimed iterations replay each of them twice and let NCCL set up its peer connections.
     reset()
+    if peer:
+        # row strips over peer memory instead of NCCL (hp_scheme_attach_peers; a rendezvous, after the upload)
+        blobs = [None] * world
+        dist.all_gather_object(blobs, sim.peer_export())
+        sim.attach_peers(rank, world, blobs)
     sim.prepare_graphs()
     sim.iterate(36, sync=True)
     # Spin-up: the timed steps must see the workload, not its dry initial state.  Rain is applied about once per
@@ -519,7 +533,11 @@ def main():
 
     # ---- multi-GPU: where the strip iteration spends its time, and strips against one GPU ------------
     phases, parity, single = None, None, None
-    if world > 1:
+    if world > 1 and peer:
+        if not args.no_strip_parity:
+            parity = strip_parity_check(hx, ex, dist, w, rank, world, args.options, "peer")
+        dist.barrier()
+    elif world > 1:
         sim.strip_timing(True)
         sim.iterate(4, sync=True)
         sim.strip_timing(True)                   # clears the accumulators: the first timed-mode iterations settle
@@ -596,6 +614,10 @@ def main():
             line["strip_parity_detail"] = parity
         if single:
             line["single_gpu_same_workload"] = single
+        if world > 1:
+            line["exchange"] = ("peer memory: one kernel stores the edge rows into the neighbours' halo rows over NVLink, exchanges the "
+                                "wave-speed maximum through mailboxes and runs the time controller (hp_scheme_attach_peers)") if peer else \
+                               "NCCL: ncclSend/ncclRecv of the halo rows + ncclAllReduce(max) of the wave speed (hp_scheme_attach_comm)"
         if not args.no_variants and world == 1 and args.workload is None:
             sim.close()
             del t_st, t_bed, t_man

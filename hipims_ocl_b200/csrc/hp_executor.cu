@@ -6,13 +6,17 @@
 // prepareSimulation / readDomainAll / CDomainLink.  One CUDA stream per executor; batches of
 // iterations are replayed as CUDA graphs so that small domains are not launch-bound (the
 // reference blocks the host once per batch, CSchemeGodunov.cpp:1337-1341 -- so do we).
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
+
+#include <unistd.h>
 
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -101,6 +105,13 @@ struct hp_scheme {
     bool small_strip = true;             // decided from rank-independent quantities in hp_scheme_attach_comm
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t ev_edges = nullptr, ev_halo = nullptr;
+    // row strips over peer memory (hp_scheme_attach_peers): my mailbox, the peers' mapped buffers, and the exchange
+    // kernel's arguments for the two ping-pong directions
+    hp::PeerBox* peer_box = nullptr;
+    bool peers = false;
+    int peer_rank = 0;
+    hp::PeerArgs peer_args[2]{};          // [alt]
+    std::vector<void*> peer_mapped;       // cudaIpcOpenMemHandle results to close
     // hp_scheme_strip_timing: per-phase device times of the strip iteration (direct launches while enabled)
     bool strip_timing = false;
     cudaEvent_t ev_t[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -190,7 +201,14 @@ int enqueue_iteration(hp_scheme* s, bool alt, int* launched) {
         for (int i = 0; i < 5; ++i) { float ms = 0; cudaEventElapsedTime(&ms, s->ev_t[i], s->ev_t[i + 1]); s->t_phase[i] += ms; }
         ++s->t_count;
     };
-    if (s->comm == nullptr) {
+    if (s->peers) {
+        // Row strips over peer memory: the cell update of all owned rows, then ONE kernel that stores the edge rows into
+        // the neighbours' halo rows, exchanges the wave-speed maximum through the strips' mailboxes and runs the time
+        // controller (hp_kernels.cu: peer_exchange_kernel).
+        a.finalize = 0;
+        n += step(a);
+        n += s->K->peer_exchange(rb, s->peer_args[alt ? 1 : 0], a, 0, st);
+    } else if (s->comm == nullptr) {
         a.finalize = 1;
         n += step(a);
     } else if (s->small_strip && !(s->cfg.options & HP_OPT_SPLIT_STRIPS)) {
@@ -555,6 +573,8 @@ void hp_scheme_destroy(hp_scheme* s) {
         for (auto& e : s->ev_t) if (e) cudaEventDestroy(e);
         if (s->ev_edges) cudaEventDestroy(s->ev_edges);
         if (s->ev_halo) cudaEventDestroy(s->ev_halo);
+        for (void* m : s->peer_mapped) cudaIpcCloseMemHandle(m);
+        cudaFree(s->peer_box);
         cudaFree(s->block); cudaFree(s->clock); cudaFree(s->max_bits); cudaFree(s->ticket); cudaFree(s->staging);
         for (auto& b : s->bdys) { cudaFree(b.series); cudaFree(b.relations); }
     }
@@ -628,7 +648,11 @@ int hp_scheme_upload_cells(hp_scheme* s, const void* states, const void* bed, co
     HP_CUDA(cudaMemcpy2DAsync(s->bed, dp, bed, w, w, g.rows, cudaMemcpyHostToDevice, s->ex->stream));
     HP_CUDA(cudaMemcpy2DAsync(s->manning, dp, manning, w, w, g.rows, cudaMemcpyHostToDevice, s->ex->stream));
     s->use_alt = false;
-    return rows_to_device(s, states, 0, g.rows, true);
+    const int rc = rows_to_device(s, states, 0, g.rows, true);
+    // strips over peer memory: nobody's first cell update (whose edge rows go straight into the neighbours' halo rows)
+    // may start before every strip's upload has landed -- a barrier in stream order, no host synchronisation
+    if (rc == HP_OK && s->peers) s->launches += s->K->peer_barrier(s->peer_args[0], s->ex->stream);
+    return rc;
 }
 
 int hp_scheme_download_cells(hp_scheme* s, void* states) {
@@ -717,6 +741,13 @@ int hp_scheme_update_timestep(hp_scheme* s) {
     if (s->cfg.scheme == HP_SCHEME_MUSCL_HANCOCK || !(s->cfg.quirks & HP_QUIRK_REDUCE_BUFFER_A)) a.src = src_planes(s, s->use_alt);
     else a.src = s->A;
     s->launches += s->K->reduce_only(static_cast<int>(s->rb), a, s->ex->stream);
+    if (s->peers) {
+        hp::PeerArgs p = s->peer_args[0];
+        p.bytes[0] = p.bytes[1] = 0;                // no rows to move: only the maximum and the clock
+        s->launches += s->K->peer_exchange(static_cast<int>(s->rb), p, a, 1, s->ex->stream);
+        HP_CUDA(cudaGetLastError());
+        return HP_OK;
+    }
     if (s->comm) { const char* err = hp::comm_allreduce_max(s->comm, s->max_bits, s->ex->stream); if (err) return fail(HP_ERR_NCCL, "allreduce: %s", err); }
     s->launches += s->K->update_timestep(static_cast<int>(s->rb), a, s->ex->stream);
     HP_CUDA(cudaGetLastError());
@@ -740,7 +771,7 @@ int hp_scheme_reset_counters(hp_scheme* s) {
 // large strips are launched directly -- their launch latency is hidden anyway.  `small_strip` is the same on every
 // rank (hp_scheme_attach_comm), so all ranks issue the same NCCL sequence.
 static bool uses_graphs(const hp_scheme* s) {
-    return !(s->cfg.options & HP_OPT_NO_GRAPH) && !s->strip_timing && (s->comm == nullptr || s->small_strip);
+    return !(s->cfg.options & HP_OPT_NO_GRAPH) && !s->strip_timing && (s->peers || s->comm == nullptr || s->small_strip);
 }
 
 int hp_scheme_prepare_graphs(hp_scheme* s) {
@@ -816,6 +847,11 @@ int hp_scheme_read_stats(hp_scheme* s, hp_scheme_stats* out) {
         out->batch_timesteps = c.batch_timesteps; out->batch_successful = c.batch_successful; out->batch_skipped = c.batch_skipped;
     }
     out->iterations = s->iterations; out->kernel_launches = s->launches; out->use_alternate = s->use_alt ? 1u : 0u; out->reserved0 = 0;
+    if (s->peers) {
+        unsigned int err = 0;
+        HP_CUDA(cudaMemcpy(&err, &s->peer_box->error, sizeof(err), cudaMemcpyDeviceToHost));
+        if (err) return fail(HP_ERR_PEER, "a peer strip did not arrive within the time limit of the exchange kernel");
+    }
     return HP_OK;
 }
 
@@ -857,6 +893,141 @@ int hp_scheme_attach_comm(hp_scheme* s, const void* id, int rank, int world_size
         for (auto& ev : s->ev_t) if (ev) { cudaEventDestroy(ev); ev = nullptr; }
         return fail(HP_ERR_CUDA, "attaching the communicator failed: %s", cudaGetErrorString(e));
     }
+    drop_graphs(s);
+    return HP_OK;
+}
+
+// What a strip tells its peers (HP_PEER_BLOB_BYTES, opaque to the caller)
+struct PeerBlob {
+    uint64_t magic;
+    int64_t pid;
+    int32_t device, rows, own_y0, own_y1, pitch, cols, real_bytes, scheme;
+    uint64_t plane_bytes, global_rows;
+    void* block; void* box;                     // valid inside the exporting process
+    cudaIpcMemHandle_t h_block, h_box;          // ... and for every other process
+};
+static_assert(sizeof(PeerBlob) <= HP_PEER_BLOB_BYTES, "HP_PEER_BLOB_BYTES");
+static_assert(sizeof(hp::PeerBox) <= 1024, "mailbox allocation");
+constexpr uint64_t kPeerMagic = 0x4850504545523031ull;   // "HPPEER01"
+
+static int ensure_peer_box(hp_scheme* s) {
+    if (s->peer_box) return HP_OK;
+    void* p = nullptr;
+    HP_CUDA(cudaMalloc(&p, 1024));
+    HP_CUDA(cudaMemset(p, 0, 1024));
+    s->peer_box = static_cast<hp::PeerBox*>(p);
+    return HP_OK;
+}
+
+int hp_scheme_peer_export(hp_scheme* s, void* blob_out) {
+    if (!s || !blob_out) return fail(HP_ERR_INVALID, "null argument");
+    std::lock_guard<std::recursive_mutex> lock__(s->mu);
+    HP_CUDA(cudaSetDevice(s->ex->device));
+    int rc = ensure_peer_box(s);
+    if (rc) return rc;
+    PeerBlob b{};
+    b.magic = kPeerMagic; b.pid = static_cast<int64_t>(getpid()); b.device = s->ex->device;
+    b.rows = s->grid.rows; b.own_y0 = s->grid.own_y0; b.own_y1 = s->grid.own_y1; b.pitch = s->grid.pitch; b.cols = s->grid.cols;
+    b.real_bytes = static_cast<int32_t>(s->rb); b.scheme = static_cast<int32_t>(s->cfg.scheme);
+    b.plane_bytes = s->plane_bytes; b.global_rows = s->cfg.global_rows;
+    b.block = s->block; b.box = s->peer_box;
+    HP_CUDA(cudaIpcGetMemHandle(&b.h_block, s->block));
+    HP_CUDA(cudaIpcGetMemHandle(&b.h_box, s->peer_box));
+    memset(blob_out, 0, HP_PEER_BLOB_BYTES);
+    memcpy(blob_out, &b, sizeof(b));
+    return HP_OK;
+}
+
+int hp_scheme_attach_peers(hp_scheme* s, int rank, int world_size, const void* blobs) {
+    if (!s || !blobs) return fail(HP_ERR_INVALID, "null argument");
+    std::lock_guard<std::recursive_mutex> lock__(s->mu);
+    if (world_size < 1 || world_size > hp::kMaxPeers || rank < 0 || rank >= world_size) return fail(HP_ERR_INVALID, "bad rank/world size (at most %d strips)", hp::kMaxPeers);
+    if (s->peers) return fail(HP_ERR_INVALID, "peers are already attached");
+    HP_CUDA(cudaSetDevice(s->ex->device));
+    if (world_size == 1) return HP_OK;
+    int rc = ensure_peer_box(s);
+    if (rc) return rc;
+    const int halo = s->cfg.scheme == HP_SCHEME_MUSCL_HANCOCK ? 2 : 1;
+    std::vector<PeerBlob> all(world_size);
+    for (int r = 0; r < world_size; ++r) {
+        memcpy(&all[r], static_cast<const char*>(blobs) + static_cast<size_t>(r) * HP_PEER_BLOB_BYTES, sizeof(PeerBlob));
+        const PeerBlob& b = all[r];
+        if (b.magic != kPeerMagic) return fail(HP_ERR_INVALID, "blob %d is not a peer description", r);
+        if (b.pitch != s->grid.pitch || b.cols != s->grid.cols || b.real_bytes != static_cast<int32_t>(s->rb) ||
+            b.scheme != static_cast<int32_t>(s->cfg.scheme) || b.global_rows != s->cfg.global_rows)
+            return fail(HP_ERR_INVALID, "strip %d was created with a different geometry, precision or scheme", r);
+    }
+    if (all[rank].box != s->peer_box || all[rank].pid != static_cast<int64_t>(getpid())) return fail(HP_ERR_INVALID, "blob %d is not this strip's own", rank);
+    // neighbours must hold the halo rows my edge rows go into
+    if (rank > 0 && all[rank - 1].rows - all[rank - 1].own_y1 != halo) return fail(HP_ERR_INVALID, "the southern neighbour has no northern halo of %d rows", halo);
+    if (rank + 1 < world_size && all[rank + 1].own_y0 != halo) return fail(HP_ERR_INVALID, "the northern neighbour has no southern halo of %d rows", halo);
+    if ((rank > 0 && s->grid.own_y0 != halo) || (rank + 1 < world_size && s->grid.rows - s->grid.own_y1 != halo) || s->grid.own_y1 - s->grid.own_y0 < halo)
+        return fail(HP_ERR_INVALID, "this strip's halo rows do not match its position among %d strips", world_size);
+    // map every peer's mailbox, the neighbours' plane blocks too
+    std::vector<char*> blocks(world_size, nullptr);
+    auto map = [&](const PeerBlob& b, bool block, void** out) -> int {
+        if (b.pid == static_cast<int64_t>(getpid())) {                         // same process: the pointer itself, peer access enabled
+            if (b.device != s->ex->device) {
+                int can = 0;
+                HP_CUDA(cudaDeviceCanAccessPeer(&can, s->ex->device, b.device));
+                if (!can) return fail(HP_ERR_PEER, "device %d cannot access the memory of device %d", s->ex->device, b.device);
+                const cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(HP_ERR_CUDA, "cudaDeviceEnablePeerAccess failed: %s", cudaGetErrorString(e));
+                cudaGetLastError();
+            }
+            *out = block ? b.block : b.box;
+            return HP_OK;
+        }
+        const cudaError_t e = cudaIpcOpenMemHandle(out, block ? b.h_block : b.h_box, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) return fail(HP_ERR_PEER, "cudaIpcOpenMemHandle failed: %s", cudaGetErrorString(e));
+        s->peer_mapped.push_back(*out);
+        return HP_OK;
+    };
+    hp::PeerArgs base{};
+    base.rank = rank; base.world = world_size;
+    for (int r = 0; r < world_size; ++r) {
+        void* p = nullptr;
+        if (r == rank) p = s->peer_box; else if ((rc = map(all[r], false, &p))) return rc;
+        base.box[r] = static_cast<hp::PeerBox*>(p);
+        if (r == rank - 1 || r == rank + 1) { void* b = nullptr; if ((rc = map(all[r], true, &b))) return rc; blocks[r] = static_cast<char*>(b); }
+    }
+    // plane q of buffer A / B inside a ten-plane block (alloc_block): A.eta A.qx A.qy A.emax | zb n | B.eta B.qx B.qy B.emax;
+    // PeerArgs order is eta emax qx qy
+    static const int kPlaneA[4] = {0, 3, 1, 2}, kPlaneB[4] = {6, 9, 7, 8};
+    const size_t row = static_cast<size_t>(s->grid.pitch) * s->rb;
+    for (int alt = 0; alt < 2; ++alt) {
+        hp::PeerArgs a = base;
+        const int* mine_planes = alt ? kPlaneA : kPlaneB;         // the step's DESTINATION: B when it read A (alt == 0)
+        for (int n = 0; n < 2; ++n) {
+            const int r = n == 0 ? rank - 1 : rank + 1;
+            if (r < 0 || r >= world_size) { a.bytes[n] = 0; continue; }
+            a.bytes[n] = row * halo;
+            // my edge rows: the lowest owned rows go south, the highest north; they land in the neighbour's halo rows on
+            // the side facing me
+            const size_t my_row = n == 0 ? static_cast<size_t>(s->grid.own_y0) : static_cast<size_t>(s->grid.own_y1 - halo);
+            const size_t their_row = n == 0 ? static_cast<size_t>(all[r].own_y1) : static_cast<size_t>(all[r].own_y0 - halo);
+            for (int q = 0; q < 4; ++q) {
+                a.src[n][q] = s->block + static_cast<size_t>(mine_planes[q]) * s->plane_bytes + my_row * row;
+                a.dst[n][q] = blocks[r] + static_cast<size_t>(mine_planes[q]) * all[r].plane_bytes + their_row * row;
+            }
+        }
+        s->peer_args[alt] = a;
+    }
+    // rendezvous: tell every peer that its mailbox is mapped here, wait until all of them have told me
+    s->K->peer_hello(base, s->ex->stream);
+    HP_CUDA(cudaStreamSynchronize(s->ex->stream));
+    const auto t0 = std::chrono::steady_clock::now();
+    for (;;) {
+        unsigned long long hello[hp::kMaxPeers] = {};
+        HP_CUDA(cudaMemcpy(hello, s->peer_box->hello, sizeof(hello), cudaMemcpyDeviceToHost));
+        int seen = 0;
+        for (int r = 0; r < world_size; ++r) seen += hello[r] != 0ull;
+        if (seen == world_size) break;
+        if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 60.0)
+            return fail(HP_ERR_PEER, "only %d of %d strips attached within 60 s", seen, world_size);
+        std::this_thread::sleep_for(std::chrono::milliseconds(1));
+    }
+    s->peers = true; s->peer_rank = rank; s->world = world_size;
     drop_graphs(s);
     return HP_OK;
 }

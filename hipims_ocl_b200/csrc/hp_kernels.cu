@@ -256,6 +256,111 @@ template <class R, bool UPDATE_ONLY> __global__ void clock_kernel(const StepArgs
 }
 
 // ---------------------------------------------------------------------------------------------
+// Row strips over peer memory (see PeerBox in hp_kernels.cuh): push my edge rows into the neighbours' halo rows, publish
+// my wave-speed maximum to every strip, wait for theirs, run the time controller.  Replaces the reference's
+// CDomainLink::pullFromBuffer -> sendOverMPI -> pushToBuffer (src/Domain/Links/CDomainLink.cpp:168-270) and the
+// MPI_Allreduce of CMPIManager::reduceTimeData (src/MPI/CMPIManager.cpp:837-889) -- and this library's own NCCL calls
+// (hp_comm.cpp) -- by stores over NVLink from one kernel.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void peer_hello_kernel(const hp::PeerArgs p) {
+    const int r = threadIdx.x;
+    if (r < p.world) { st_sys(&p.box[r]->hello[p.rank], 1ull); __threadfence_system(); }
+}
+
+// Stream-ordered barrier over all strips: what follows on this stream (the first cell update after an upload) starts only
+// when every strip has finished what preceded it on its own stream (its upload) -- a neighbour's edge rows must not land
+// in halo rows an upload is still going to overwrite.
+__global__ void peer_barrier_kernel(const hp::PeerArgs p) {
+    __shared__ unsigned long long s_epoch;
+    hp::PeerBox* const mine = p.box[p.rank];
+    if (threadIdx.x == 0) s_epoch = mine->bar_epoch + 1ull;
+    __syncthreads();
+    const unsigned long long e = s_epoch;
+    const int r = threadIdx.x;
+    if (r < p.world) {
+        __threadfence_system();
+        st_sys(&p.box[r]->bar[p.rank], e);
+        const long long t0 = clock64();
+        while (ld_sys(&mine->bar[r]) < e) {
+            if (clock64() - t0 > hp::kPeerSpinCycles) { mine->error = 1u; break; }
+            __nanosleep(64);
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) mine->bar_epoch = e;
+}
+
+template <class R, bool UPDATE_ONLY> __global__ void __launch_bounds__(256) peer_exchange_kernel(const hp::PeerArgs p, const StepArgs a) {
+    __shared__ unsigned int s_last;
+    __shared__ unsigned long long s_it;
+    hp::PeerBox* const mine = p.box[p.rank];
+    // ---- halo rows: 16-byte stores straight into the neighbours' memory, all CTAs --------------------------------
+    const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x, nthreads = static_cast<size_t>(gridDim.x) * blockDim.x;
+#pragma unroll
+    for (int n = 0; n < 2; ++n) {
+        const size_t vecs = p.bytes[n] / 16;
+        if (vecs == 0) continue;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint4* __restrict__ s = static_cast<const uint4*>(p.src[n][q]);
+            uint4* __restrict__ d = static_cast<uint4*>(p.dst[n][q]);
+            for (size_t i = tid; i < vecs; i += nthreads) d[i] = s[i];
+        }
+    }
+    __threadfence_system();                          // my stores are visible system-wide before this CTA counts as arrived
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int arrived = atomicAdd(&mine->ticket, 1u);
+        s_last = arrived == gridDim.x - 1u ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    // ---- the last CTA: publish, wait for the peers, advance the clock ------------------------------------------------
+    __threadfence();                                 // everything the other CTAs stored before they arrived
+    if (threadIdx.x == 0) {
+        mine->ticket = 0u;
+        s_it = mine->iter + 1ull;
+    }
+    __syncthreads();
+    const unsigned long long it = s_it;
+    const int r = threadIdx.x;
+    if (r < p.world) {
+        // (every lane reads the same local word; the exchange of lane 0 below resets it)
+        const unsigned long long bits = *reinterpret_cast<volatile unsigned long long*>(a.max_bits);
+        st_sys(&p.box[r]->vmax[it & 1ull][p.rank], bits);
+        __threadfence_system();                      // halo rows (fenced above) and vmax before the signal
+        st_sys(&p.box[r]->sig[p.rank], it);
+        const long long t0 = clock64();
+        while (ld_sys(&mine->sig[r]) < it) {
+            if (clock64() - t0 > hp::kPeerSpinCycles) { mine->error = 1u; break; }
+            __nanosleep(64);
+        }
+        __threadfence_system();                      // acquire: strip r's halo rows and vmax
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    unsigned long long best = 0ull;
+    for (int q = 0; q < p.world; ++q) { const unsigned long long v = ld_sys(&mine->vmax[it & 1ull][q]); best = v > best ? v : best; }
+    *a.max_bits = 0ull;
+    const Params<R> k = make_params<R>(a.params);
+    Clock<R>* ck = reinterpret_cast<Clock<R>*>(a.clock);
+    Clock<R> c = *ck;
+    if (UPDATE_ONLY) update_timestep_clock(k, c, bits_speed<R>(best)); else advance_clock(k, c, bits_speed<R>(best));
+    *ck = c;
+    mine->iter = it;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Boundary kernels; reproduce src/Boundaries/CLBoundaries.clc.  Grid-stride with a small fixed
 // grid: most iterations they only read the device clock and leave (the hydrological
 // accumulator gates rain to about once per simulated second).
@@ -563,6 +668,20 @@ static int launch_update_timestep(int real_bytes, const StepArgs& a, cudaStream_
     if (real_bytes == 8) clock_kernel<double, true><<<1, 1, 0, st>>>(a); else clock_kernel<float, true><<<1, 1, 0, st>>>(a);
     return 1;
 }
+static int launch_peer_exchange(int real_bytes, const hp::PeerArgs& p, const StepArgs& a, int update_only, cudaStream_t st) {
+    // enough CTAs to keep the links busy (a few MB at most), never more than the copy has 16-byte pieces for
+    const unsigned long long vecs = (p.bytes[0] + p.bytes[1]) / 16 * 4;
+    int grid = static_cast<int>((vecs + 1023) / 1024);
+    grid = grid < 1 ? 1 : (grid > 64 ? 64 : grid);
+    if (real_bytes == 8) {
+        if (update_only) peer_exchange_kernel<double, true><<<grid, 256, 0, st>>>(p, a); else peer_exchange_kernel<double, false><<<grid, 256, 0, st>>>(p, a);
+    } else {
+        if (update_only) peer_exchange_kernel<float, true><<<grid, 256, 0, st>>>(p, a); else peer_exchange_kernel<float, false><<<grid, 256, 0, st>>>(p, a);
+    }
+    return 1;
+}
+static int launch_peer_hello(const hp::PeerArgs& p, cudaStream_t st) { peer_hello_kernel<<<1, 32, 0, st>>>(p); return 1; }
+static int launch_peer_barrier(const hp::PeerArgs& p, cudaStream_t st) { peer_barrier_kernel<<<1, 32, 0, st>>>(p); return 1; }
 static int launch_bdy_uniform(int real_bytes, const BdyUniformArgs& a, cudaStream_t st) {
     const int grid = stride_grid(static_cast<long long>(a.grid.rows) * a.grid.cols, 256, 8);
     if (real_bytes == 8) bdy_uniform_kernel<double><<<grid, 256, 0, st>>>(a); else bdy_uniform_kernel<float><<<grid, 256, 0, st>>>(a);
@@ -612,7 +731,7 @@ static const hp::KernelTable g_table = {
 #else
     nullptr, nullptr, nullptr,
 #endif
-    launch_step, launch_reduce_only, launch_advance, launch_update_timestep, launch_bdy_uniform, launch_bdy_gridded,
+    launch_step, launch_reduce_only, launch_advance, launch_update_timestep, launch_peer_exchange, launch_peer_hello, launch_peer_barrier, launch_bdy_uniform, launch_bdy_gridded,
     launch_bdy_cell, launch_aos_to_soa, launch_soa_to_aos, launch_copy_plane_rows, launch_derive_raster,
 };
 

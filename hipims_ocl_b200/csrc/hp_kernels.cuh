@@ -56,6 +56,39 @@ struct StepArgs {
     int march_runs;           // marching kernels: runs of (strip group, row) units per CTA, interleaved across the grid
 };
 
+// ---------------------------------------------------------------------------------------------
+// Row strips over PEER MEMORY (NVLink 5 / NVSwitch): what hp_comm.cpp does with ncclSend/ncclRecv and ncclAllReduce --
+// halo rows to the neighbouring strips, the maximum of the wave speed over all strips -- done by ONE kernel with plain
+// stores into the peers' memory, followed in the same kernel by the time controller.
+//
+// Every strip owns a mailbox that its peers write into:
+//   vmax[it & 1][r]  wave-speed bits of strip r for iteration `it` (double-buffered: strip r can be one iteration ahead)
+//   sig[r]           the last iteration strip r has published -- written AFTER its halo rows and its vmax, behind a
+//                    system-scope fence, so "sig[r] >= it" means both have landed
+// and keeps its own iteration count next to it.  A strip never runs more than one iteration ahead of a peer (it waits for
+// every sig of iteration `it` before it advances its clock), which is what makes two vmax slots and the ping-pong halo
+// rows enough.  A peer that does not show up within kPeerSpinCycles sets `error` instead of hanging the GPU.
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxPeers = 16;
+constexpr long long kPeerSpinCycles = 8000000000ll;          // ~4 s of SM clock
+struct PeerBox {
+    unsigned long long sig[kMaxPeers];
+    unsigned long long vmax[2][kMaxPeers];
+    unsigned long long hello[kMaxPeers];   // attach rendezvous: strip r has mapped this mailbox
+    unsigned long long bar[kMaxPeers];     // stream-ordered barrier (after an upload): the last epoch strip r has reached
+    unsigned long long bar_epoch;     // local: barriers this strip has passed
+    unsigned long long iter;          // local: iterations this strip has completed
+    unsigned int ticket;              // local: CTA arrival counter of the exchange kernel
+    unsigned int error;               // local: a peer did not arrive in time
+};
+struct PeerArgs {
+    const void* src[2][4];            // [south, north][eta emax qx qy]: first of my `halo` owned edge rows in this iteration's dst
+    void* dst[2][4];                  // ... and the first halo row they land in, in the neighbour's dst buffer (peer memory)
+    unsigned long long bytes[2];      // bytes per plane and neighbour (halo rows x pitch x sizeof(real)); 0 = no neighbour
+    PeerBox* box[kMaxPeers];          // every strip's mailbox by rank (mine included)
+    int rank, world;
+};
+
 struct BdyUniformArgs {
     Planes state; const void* bed; const void* clock; const void* series;  // series: entries x {t, value}
     Grid grid; unsigned int entries, definition; double interval, length; int cover_x, cover_y;
@@ -111,6 +144,10 @@ struct KernelTable {
     int (*reduce_only)(int real_bytes, const StepArgs& a, cudaStream_t st);       // tst_Reduce
     int (*advance)(int real_bytes, const StepArgs& a, cudaStream_t st);           // tst_Advance_Normal
     int (*update_timestep)(int real_bytes, const StepArgs& a, cudaStream_t st);   // tst_UpdateTimestep
+    // halo rows -> peers, wave-speed maximum over all strips, then tst_Advance_Normal (or tst_UpdateTimestep), one launch
+    int (*peer_exchange)(int real_bytes, const PeerArgs& p, const StepArgs& a, int update_only, cudaStream_t st);
+    int (*peer_hello)(const PeerArgs& p, cudaStream_t st);                        // attach rendezvous
+    int (*peer_barrier)(const PeerArgs& p, cudaStream_t st);                      // all strips have reached this point of their streams
     int (*bdy_uniform)(int real_bytes, const BdyUniformArgs& a, cudaStream_t st);
     int (*bdy_gridded)(int real_bytes, const BdyGriddedArgs& a, cudaStream_t st);
     int (*bdy_cell)(int real_bytes, const BdyCellArgs& a, cudaStream_t st);

@@ -99,10 +99,13 @@ ABI = {
     "hp_scheme_read_stats": (C.c_int, [_VP, C.POINTER(HpSchemeStats)]),
     "hp_comm_unique_id": (C.c_int, [_VP]),
     "hp_scheme_attach_comm": (C.c_int, [_VP, _VP, C.c_int, C.c_int]),
+    "hp_scheme_peer_export": (C.c_int, [_VP, _VP]),
+    "hp_scheme_attach_peers": (C.c_int, [_VP, C.c_int, C.c_int, _VP]),
     "hp_scheme_strip_timing": (C.c_int, [_VP, C.c_int]),
     "hp_scheme_read_strip_phases": (C.c_int, [_VP, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
 }
 
+PEER_BLOB_BYTES = 256
 STRIP_PHASES = ("edge_rows", "interior_rows", "halo_wait", "allreduce", "clock")
 
 _lib = None
@@ -344,6 +347,19 @@ class CudaScheme:
         buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id))
         _check(self.lib.hp_scheme_attach_comm(self.h, C.cast(buf, _VP), int(rank), int(world_size)))
 
+
+    def peer_export(self):
+        """This strip's buffers and mailbox as an opaque blob for its peers (hp_scheme_peer_export)."""
+        buf = (C.c_char * PEER_BLOB_BYTES)()
+        _check(self.lib.hp_scheme_peer_export(self.h, C.cast(buf, _VP)))
+        return bytes(buf)
+
+    def attach_peers(self, rank, world_size, blobs):
+        """Row strips over peer memory instead of NCCL: `blobs` = peer_export() of every strip, by rank.  A rendezvous --
+        every strip must call it, after its upload."""
+        assert len(blobs) == world_size and all(len(b) == PEER_BLOB_BYTES for b in blobs)
+        buf = (C.c_char * (PEER_BLOB_BYTES * world_size)).from_buffer_copy(b"".join(blobs))
+        _check(self.lib.hp_scheme_attach_peers(self.h, int(rank), int(world_size), C.cast(buf, _VP)))
 
     def strip_timing(self, enable=True):
         _check(self.lib.hp_scheme_strip_timing(self.h, int(bool(enable))))

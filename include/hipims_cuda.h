@@ -48,7 +48,8 @@ typedef enum hp_status {
     HP_ERR_INVALID = -2,
     HP_ERR_CUDA = -3,
     HP_ERR_NCCL = -4,
-    HP_ERR_OOM = -5
+    HP_ERR_OOM = -5,
+    HP_ERR_PEER = -6      /* a peer strip did not arrive in time (row strips over peer memory) */
 } hp_status;
 
 typedef struct hp_executor hp_executor; /* one CUDA device + stream: CExecutorControlOpenCL + COCLDevice */
@@ -272,6 +273,25 @@ int  hp_scheme_read_stats(hp_scheme* s, hp_scheme_stats* out);
 #define HP_COMM_ID_BYTES 128
 int  hp_comm_unique_id(void* id_out);
 int  hp_scheme_attach_comm(hp_scheme* s, const void* id, int rank, int world_size);
+/* ---- row strips over peer memory (NVLink 5 / NVSwitch) ------------------------------------------
+ * The same exchange without NCCL: after each cell update ONE kernel stores the strip's edge rows straight into the
+ * neighbouring strips' halo rows, publishes the strip's wave-speed maximum to every strip, waits for theirs and runs
+ * the time controller -- the reference's CDomainLink::pullFromBuffer -> sendOverMPI -> pushToBuffer
+ * (src/Domain/Links/CDomainLink.cpp:168-270) plus CMPIManager::reduceTimeData (src/MPI/CMPIManager.cpp:837-889) as
+ * stores over NVLink.  An iteration is then two launches (cell update, exchange + clock), replayed from CUDA graphs
+ * whatever the strip's size, from one process per GPU (CUDA IPC) or from one process driving several GPUs.
+ *   hp_scheme_peer_export   fills an opaque HP_PEER_BLOB_BYTES description of this strip's buffers and mailbox;
+ *   the caller gathers the blobs of all strips (torch.distributed all_gather, MPI_Allgather, or by hand in one process);
+ *   hp_scheme_attach_peers  maps them and returns once every strip has done the same (a rendezvous: call it after the
+ *                           cells have been uploaded, from every strip, concurrently).
+ * With peers attached hp_scheme_iterate / hp_scheme_update_timestep use this path; a communicator need not be
+ * attached.  Collective like the NCCL path: every strip must enqueue the same iterations, and hp_scheme_upload_cells
+ * becomes collective too (it ends in a stream-ordered barrier over all strips, so that no neighbour's edge rows land in
+ * halo rows an upload is still going to overwrite).  A peer that does not
+ * arrive within a few seconds fails the iteration (HP_ERR_PEER from hp_scheme_read_stats) instead of hanging. */
+#define HP_PEER_BLOB_BYTES 256
+int  hp_scheme_peer_export(hp_scheme* s, void* blob_out /* HP_PEER_BLOB_BYTES */);
+int  hp_scheme_attach_peers(hp_scheme* s, int rank, int world_size, const void* blobs /* world_size x HP_PEER_BLOB_BYTES, by rank */);
 /* Per-phase device times of the strip iteration, the counterpart of the reference's per-domain wall-clock log lines
  * around its exchange (src/CModel.cpp:843-958).  While enabled, iterations are launched directly (no graph replay)
  * with CUDA events between the phases and one host synchronisation per iteration: a diagnostic mode, not a fast one.

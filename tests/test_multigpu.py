@@ -55,6 +55,33 @@ def test_two_strips_equal_one_gpu(scheme, precision, rows, cols, iters, bdy, opt
     run_check(2, scheme, precision, rows, cols, iters, bdy, options)
 
 
+# the same strips exchanging over PEER MEMORY (hp_scheme_attach_peers: one kernel stores the edge rows into the neighbours'
+# halo rows, exchanges the wave-speed maximum through mailboxes and runs the time controller; no NCCL in the loop)
+PEER_CASES = [
+    ("godunov", "double", 256, 192, 60, "cells", 0),
+    ("muscl-hancock", "double", 256, 192, 60, "cells", 0),
+    ("inertial", "single", 250, 200, 41, "cells", 0),                 # rows not divisible, odd count
+    ("muscl-hancock", "double", 256, 192, 41, "rain", 2),             # direct launches (HP_OPT_NO_GRAPH)
+]
+
+
+@pytest.mark.parametrize("scheme,precision,rows,cols,iters,bdy,options", PEER_CASES)
+def test_two_strips_over_peer_memory_equal_one_gpu(scheme, precision, rows, cols, iters, bdy, options):
+    if gpu_count() < 2:
+        pytest.skip("needs two GPUs")
+    run_check(2, scheme, precision, rows, cols, iters, bdy, options, "peer")
+
+
+def test_strips_over_peer_memory_with_two_neighbours():
+    n = gpu_count()
+    if n < 3:
+        pytest.skip("needs three GPUs (a strip with two neighbours)")
+    world = 4 if n >= 4 else 3
+    run_check(world, "muscl-hancock", "double", 64 * world + 1, 192, 40, "cells", 0, "peer")
+    if n >= 8:
+        run_check(8, "godunov", "double", 1021, 512, 40, "rain", 0, "peer")
+
+
 def test_decision_at_the_small_strip_threshold(monkeypatch):
     """A decomposition straddling the small/large-strip threshold: an edge strip holds own + 2 rows (small by its own
     count), an inner strip own + 4 (large).  The iteration shape -- and with it the order of NCCL calls -- must be decided

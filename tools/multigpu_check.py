@@ -24,6 +24,7 @@ def main():
     iters = int(sys.argv[5]) if len(sys.argv) > 5 else 60
     bdy = sys.argv[6] if len(sys.argv) > 6 else "cells"
     options = int(sys.argv[7]) if len(sys.argv) > 7 else 0
+    exchange = sys.argv[8] if len(sys.argv) > 8 else "nccl"       # "nccl" | "peer" (row strips over peer memory, no NCCL in the loop)
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -35,11 +36,18 @@ def main():
     ex = hx.Executor(local)
     sim = hx.CudaScheme(ex, cfg, options=options, global_rows=rows, row_offset=strip.row_offset, halo_south=strip.halo_south,
                         halo_north=strip.halo_north)
-    ids = [hx.comm_unique_id() if rank == 0 else None]
-    dist.broadcast_object_list(ids, src=0)
-    sim.attach_comm(ids[0], rank, world)
     sl = strip.local_slice()
-    sim.upload(st[sl], bed[sl], man[sl])
+    if exchange == "peer":
+        sim.upload(st[sl], bed[sl], man[sl])
+        sim.sync()
+        blobs = [None] * world
+        dist.all_gather_object(blobs, sim.peer_export())
+        sim.attach_peers(rank, world, blobs)
+    else:
+        ids = [hx.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        sim.attach_comm(ids[0], rank, world)
+        sim.upload(st[sl], bed[sl], man[sl])
     add_standard_boundaries(sim, cfg_full, bdy)   # global cell ids; the library keeps the ones it holds
     sim.set_target(1e6)
     sim.iterate(iters)
@@ -59,8 +67,8 @@ def main():
         same_state = np.array_equal(full, want, equal_nan=True)
         same_clock = all(g[2] == ref.stats() for g in gathered)
         err = float(np.nan_to_num(np.abs(full - want)).max())
-        print("multigpu_check %s %s %dx%d x%d ranks, %d iterations, bdy=%s options=%d: state %s (max diff %.3e), clocks %s, t=%.6f" % (
-            scheme, precision, rows, cols, world, iters, bdy, options, "IDENTICAL" if same_state else "DIFFERENT", err,
+        print("multigpu_check %s %s %dx%d x%d ranks, %d iterations, bdy=%s options=%d exchange=%s: state %s (max diff %.3e), clocks %s, t=%.6f" % (
+            scheme, precision, rows, cols, world, iters, bdy, options, exchange, "IDENTICAL" if same_state else "DIFFERENT", err,
             "IDENTICAL" if same_clock else "DIFFERENT", ref.stats()["time"]))
         if not same_state:
             d = np.abs(full - want).max(axis=2)

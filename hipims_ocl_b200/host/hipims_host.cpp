@@ -1003,6 +1003,8 @@ bool CScheme::prepareAll(CExecutorControlCUDA* pExec, CDomainCartesian* pDom, un
     size_t n = devices.size() > 1 ? devices.size() : 1;
     if (n > 1 && ulRows / n < 2 * ulHalo + 1) { model::doError("The domain is too short to be split into that many row strips; running on one device.", model::errorCodes::kLevelWarning); n = 1; }
     strips.assign(n, SStrip());
+    if (const char* e = getenv("HIPIMS_STRIP_EXCHANGE")) bPeerExchange = std::string(e) == "peer";
+    bPeersAttached = false;
     // rows are dealt out as evenly as possible, the first (rows % n) strips get one more (hipims_ocl_b200/strips.py)
     const unsigned long ulBase = ulRows / n, ulExtra = ulRows % n;
     for (size_t i = 0; i < n; ++i) {
@@ -1017,10 +1019,11 @@ bool CScheme::prepareAll(CExecutorControlCUDA* pExec, CDomainCartesian* pDom, un
         } else st.bOwnsExecutor = true;
         hp_scheme_config c{};
         c.struct_size = sizeof(c); c.scheme = ucSchemeType; c.real_bytes = ucPrecision == model::floatPrecision::kSingle ? 4 : 8;
-        // Strips of ONE process launch directly: capturing NCCL operations into CUDA graphs from several threads of the
-        // same process fails inside NCCL (ncclGroupEnd: internal error, NCCL 2.28, measured); with one process per GPU --
-        // bench.py, tools/multigpu_check.py -- the captured path is used.
-        c.quirks = uiQuirks; c.options = uiOptions | (n > 1 ? HP_OPT_NO_GRAPH : 0u);
+        // Strips of ONE process that exchange through NCCL launch directly: capturing NCCL operations into CUDA graphs from
+        // several threads of the same process fails inside NCCL (ncclGroupEnd: internal error, NCCL 2.28, measured); with
+        // one process per GPU -- bench.py, tools/multigpu_check.py -- the captured path is used.  Strips that exchange over
+        // peer memory (HIPIMS_STRIP_EXCHANGE=peer) have no NCCL call in the loop and replay graphs like a single device.
+        c.quirks = uiQuirks; c.options = uiOptions | ((n > 1 && !bPeerExchange) ? HP_OPT_NO_GRAPH : 0u);
         c.dynamic_timestep = bDynamicTimestep ? 1 : 0; c.friction = bFrictionEffects ? 1 : 0;
         c.cols = pDom->getCols(); c.rows = st.ulRows; c.global_rows = ulRows; c.row_offset = st.ulOwnFirst;
         c.halo_south = static_cast<uint32_t>(ulHaloS); c.halo_north = static_cast<uint32_t>(ulHaloN);
@@ -1031,7 +1034,7 @@ bool CScheme::prepareAll(CExecutorControlCUDA* pExec, CDomainCartesian* pDom, un
         }
     }
     pScheme = strips[0].pHandle;
-    if (n > 1) {
+    if (n > 1 && !bPeerExchange) {
         unsigned char id[HP_COMM_ID_BYTES];
         if (hp_comm_unique_id(id) < 0) { model::doError(std::string("NCCL: ") + hp_last_error(), model::errorCodes::kLevelModelStop); cleanupSimulation(); return false; }
         forStrips([&](SStrip& st, size_t i) {
@@ -1056,18 +1059,29 @@ void CScheme::prepareSimulationState() {   // CSchemeGodunov.cpp:1053-1071
         bed32.assign(pDomain->dBedElevations.begin(), pDomain->dBedElevations.end());
         man32.assign(pDomain->dManningValues.begin(), pDomain->dManningValues.end());
     }
-    for (auto& st : strips) {                                    // each strip: the rows it holds, halo rows included
+    // each strip: the rows it holds, halo rows included.  One host thread per strip: with peers attached an upload ends in
+    // a barrier over all strips, so the uploads must be in flight together
+    forStrips([&](SStrip& st, size_t) {
         const size_t off = static_cast<size_t>(st.ulFirstRow) * ulCols;
         if (ucFloatPrecision == model::floatPrecision::kSingle)
             HP_CHECK(hp_scheme_upload_cells(st.pHandle, st32.data() + 4 * off, bed32.data() + off, man32.data() + off), "upload");
         else
             HP_CHECK(hp_scheme_upload_cells(st.pHandle, pDomain->dCellStates.data() + 4 * off, pDomain->dBedElevations.data() + off,
                                             pDomain->dManningValues.data() + off), "upload");
-    }
-    for (auto& st : strips) {
         HP_CHECK(hp_scheme_sync(st.pHandle), "upload");
-        HP_CHECK(hp_scheme_set_clock(st.pHandle, 0.0, dTimestep, 0.0), "clock");
+    });
+    if (strips.size() > 1 && bPeerExchange && !bPeersAttached) {
+        // row strips over peer memory (include/hipims_cuda.h): every strip describes its buffers, then all of them map their
+        // peers' -- a rendezvous, after the first upload
+        std::vector<unsigned char> blobs(strips.size() * HP_PEER_BLOB_BYTES);
+        for (size_t i = 0; i < strips.size(); ++i) HP_CHECK(hp_scheme_peer_export(strips[i].pHandle, blobs.data() + i * HP_PEER_BLOB_BYTES), "peer export");
+        forStrips([&](SStrip& st, size_t i) {
+            if (hp_scheme_attach_peers(st.pHandle, static_cast<int>(i), static_cast<int>(strips.size()), blobs.data()) < 0)
+                model::doError(std::string("Could not connect the row strips over peer memory: ") + hp_last_error(), model::errorCodes::kLevelModelStop);
+        });
+        bPeersAttached = !model::forceAbort;
     }
+    for (auto& st : strips) HP_CHECK(hp_scheme_set_clock(st.pHandle, 0.0, dTimestep, 0.0), "clock");
     ulCurrentCellsCalculated = 0;
 }
 

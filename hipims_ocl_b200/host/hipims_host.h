@@ -303,6 +303,7 @@ class CScheme {
     double dCurrentTime = 0, dCurrentTimestep = 0, dBatchTimesteps = 0, dTargetTime = 0;
     unsigned int uiBatchSuccessful = 0, uiBatchSkipped = 0;
     unsigned long long ulCurrentCellsCalculated = 0;
+    bool bPeerExchange = false, bPeersAttached = false;     // HIPIMS_STRIP_EXCHANGE=peer: hp_scheme_attach_peers instead of NCCL
     unsigned int uiRollbackLimit = 999999999u;
     unsigned char ucSyncMethod = model::syncMethod::kSyncForecast;
 };

@@ -670,14 +670,17 @@ def _gpu_count():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("scheme", ["Godunov", "MUSCL-Hancock", "Inertial"])
-def test_stacked_domains_run_as_row_strips_on_their_devices(host, tmp_path, scheme):
+@pytest.mark.parametrize("scheme,exchange", [("Godunov", "nccl"), ("MUSCL-Hancock", "nccl"), ("Inertial", "nccl"), ("MUSCL-Hancock", "peer"),
+                                             ("Godunov", "peer")])
+def test_stacked_domains_run_as_row_strips_on_their_devices(host, tmp_path, scheme, exchange, monkeypatch):
     """A two-<domain> configuration naming deviceNumber 1 and 2 runs as two row strips, one per GPU (NCCL halo exchange and
-    dt all-reduce inside the library, one host thread per strip), bit-identical to the same terrain configured as one
+    dt all-reduce inside the library -- or, with HIPIMS_STRIP_EXCHANGE=peer, the peer-memory exchange kernel and graph
+    replay -- one host thread per strip), bit-identical to the same terrain configured as one
     domain on one GPU -- states, clock and per-domain rasters (src/Domain/CDomainManager.cpp:56-282,
     Links/CDomainLink.cpp:286-382 re-targeted)."""
     if _gpu_count() < 2:
         pytest.skip("needs two GPUs")
+    monkeypatch.setenv("HIPIMS_STRIP_EXCHANGE", exchange)
     from oracle import raster_oracle as ro
     bed = make_stacked(tmp_path, duration=20)
     (tmp_path / "boundaries" / "map_lower.csv").write_text("x,y\n1,10\n")

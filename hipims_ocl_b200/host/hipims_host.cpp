@@ -977,7 +977,14 @@ void CScheme::setupFromConfig(const XMLElement* pXScheme) {            // CSchem
             else model::doError("Invalid queue mode given.", model::errorCodes::kLevelWarning);
         }
         else if (key == "riemannsolver") { if (val != "hllc") model::doError("Invalid Riemann solver given.", model::errorCodes::kLevelWarning); }
-        else if (key == "groupsize" || key == "cachedgroupsize" || key == "noncachedgroupsize" || key == "localcachelevel" || key == "localcacheconstraints" ||
+        else if (key == "localcachelevel") {
+            // The cache strategy is the executor's business -- except the one observable difference between the two Godunov
+            // kernels: gts_cacheEnabled writes nothing when the timestep is <= 0 (CLSchemeGodunov.clc:477-478; selected by
+            // src/Schemes/CSchemeGodunov.cpp:296-304, 966-968)
+            if (ucSchemeType == model::schemeTypes::kGodunov && (val == "maximum" || val == "max" || val == "enabled")) uiQuirks |= HP_QUIRK_GODUNOV_DT0_KEEP;
+            else if (val == "none" || val == "no") uiQuirks &= ~static_cast<uint32_t>(HP_QUIRK_GODUNOV_DT0_KEEP);
+        }
+        else if (key == "groupsize" || key == "cachedgroupsize" || key == "noncachedgroupsize" || key == "localcacheconstraints" ||
                  key == "timestepreductiondivisions" || key == "contiguousextrapolationdata") { /* launch geometry and cache strategy are the executor's business */ }
         else model::doError("Unrecognised parameter: " + key, model::errorCodes::kLevelWarning);
     }

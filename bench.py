@@ -638,13 +638,16 @@ def run_variants(hx, ex, args):
     """Short device-resident runs of configs[1] (4096^2 circular dam break, Godunov fp64 / fp32) and of the other schemes
     on the same domain."""
     out = {}
-    for name in ("dambreak4096", "dambreak4096-f32", "dambreak4096-mh", "dambreak4096-mh-f32", "dambreak4096-inertial",
-                 "dambreak4096-inertial-f32"):
+    # "+march": the same workload on the Godunov marching kernels (HP_OPT_MARCH_GODUNOV: one column per lane in fp64, two
+    # in fp32) instead of the scheme's default tile kernel
+    for key in ("dambreak4096", "dambreak4096-f32", "dambreak4096-mh", "dambreak4096-mh-f32", "dambreak4096-inertial",
+                "dambreak4096-inertial-f32", "dambreak4096+march", "dambreak4096-f32+march"):
+        name, _, extra = key.partition("+")
         w = WORKLOADS[name]
         cfg = cfg_for(w, w["rows_per_gpu"], w["cols"])
         dtype = np.float64 if cfg.precision == "double" else np.float32
         bed, st, man = make_inputs(w, cfg.rows, cfg.cols, dtype)
-        sim = hx.CudaScheme(ex, cfg, options=args.options)
+        sim = hx.CudaScheme(ex, cfg, options=args.options | (hx.OPT_MARCH_GODUNOV if extra == "march" else 0))
         sim.upload(st, bed, man)
         sim.set_target(1.0e7)
         steps = max(20, args.steps // 2)
@@ -655,7 +658,7 @@ def run_variants(hx, ex, args):
         ms = ex.timer_stop()
         peak, _ = peak_hbm()
         rate = cfg.cells * steps / (ms * 1e-3)
-        out[name] = {"value": rate, "unit": "cell-updates/s", "steps": steps,
+        out[key] = {"value": rate, "unit": "cell-updates/s", "steps": steps,
                      "roofline_frac": rate * algorithmic_bytes_per_cell(cfg) / 1e9 / peak}
         sim.close()
     return out

@@ -643,24 +643,30 @@ def run_variants(hx, ex, args):
     for key in ("dambreak4096", "dambreak4096-f32", "dambreak4096-mh", "dambreak4096-mh-f32", "dambreak4096-inertial",
                 "dambreak4096-inertial-f32", "dambreak4096+march", "dambreak4096-f32+march"):
         name, _, extra = key.partition("+")
-        w = WORKLOADS[name]
-        cfg = cfg_for(w, w["rows_per_gpu"], w["cols"])
-        dtype = np.float64 if cfg.precision == "double" else np.float32
-        bed, st, man = make_inputs(w, cfg.rows, cfg.cols, dtype)
-        sim = hx.CudaScheme(ex, cfg, options=args.options | (hx.OPT_MARCH_GODUNOV if extra == "march" else 0))
-        sim.upload(st, bed, man)
-        sim.set_target(1.0e7)
-        steps = max(20, args.steps // 2)
-        sim.prepare_graphs()
-        sim.iterate(max(args.warmup, 18), sync=True)
-        ex.timer_start()
-        sim.iterate(steps, sync=False)
-        ms = ex.timer_stop()
-        peak, _ = peak_hbm()
-        rate = cfg.cells * steps / (ms * 1e-3)
-        out[key] = {"value": rate, "unit": "cell-updates/s", "steps": steps,
-                     "roofline_frac": rate * algorithmic_bytes_per_cell(cfg) / 1e9 / peak}
-        sim.close()
+        # a side measurement must never take the headline down with it: a failure is recorded in its place
+        try:
+            w = WORKLOADS[name]
+            cfg = cfg_for(w, w["rows_per_gpu"], w["cols"])
+            dtype = np.float64 if cfg.precision == "double" else np.float32
+            bed, st, man = make_inputs(w, cfg.rows, cfg.cols, dtype)
+            sim = hx.CudaScheme(ex, cfg, options=args.options | (hx.OPT_MARCH_GODUNOV if extra == "march" else 0))
+            try:
+                sim.upload(st, bed, man)
+                sim.set_target(1.0e7)
+                steps = max(20, args.steps // 2)
+                sim.prepare_graphs()
+                sim.iterate(max(args.warmup, 18), sync=True)
+                ex.timer_start()
+                sim.iterate(steps, sync=False)
+                ms = ex.timer_stop()
+            finally:
+                sim.close()
+            peak, _ = peak_hbm()
+            rate = cfg.cells * steps / (ms * 1e-3)
+            out[key] = {"value": rate, "unit": "cell-updates/s", "steps": steps,
+                        "roofline_frac": rate * algorithmic_bytes_per_cell(cfg) / 1e9 / peak}
+        except Exception as exc:                                            # noqa: BLE001 -- reported, not swallowed
+            out[key] = {"error": "%s: %s" % (type(exc).__name__, exc)}
     return out
 
 

@@ -236,6 +236,21 @@ class CpuSim:
         d = np.array([dt], dtype=self.dtype)
         self._f(name)(C.byref(self.c), _ptr(d), _ptr(bed), _ptr(src), _ptr(dst), _ptr(manning))
 
+    def k_step_cached(self, dt, bed, src, dst, manning):
+        """The scheme's step kernel in its local-memory form (gts_cacheEnabled / ine_cacheEnabled), run a work-group at a time
+        by the shim; only the libraries built from the reference sources have it."""
+        fn = getattr(self.lib, "hpo_ref_k_step_cached")
+        fn.restype, fn.argtypes = None, [C.POINTER(HpoConfig)] + [C.c_void_p] * 5
+        d = np.array([dt], dtype=self.dtype)
+        fn(C.byref(self.c), _ptr(d), _ptr(bed), _ptr(src), _ptr(dst), _ptr(manning))
+
+    def k_mch_1st_cached(self, dt, bed, state, faces):
+        """mch_1st_cachePrediction, a work-group at a time (reference libraries only)."""
+        fn = getattr(self.lib, "hpo_ref_k_mch_1st_cached")
+        fn.restype, fn.argtypes = None, [C.POINTER(HpoConfig)] + [C.c_void_p] * 7
+        d = np.array([dt], dtype=self.dtype)
+        fn(C.byref(self.c), _ptr(d), _ptr(bed), _ptr(state), *[_ptr(f) for f in faces])
+
     def k_mch_1st(self, dt, bed, state, faces):
         d = np.array([dt], dtype=self.dtype)
         self._f("k_mch_1st")(C.byref(self.c), _ptr(d), _ptr(bed), _ptr(state), *[_ptr(f) for f in faces])

@@ -203,7 +203,13 @@ template <class R>
 void godunov_cell(const Consts<R>& k, bool friction, int64_t x, int64_t y, R dt, const R* bed, const Vec4<R>* src,
                   Vec4<R>* dst, const R* manning) {
     const int64_t id = y * k.cols + x;
-    if (dt <= R(0)) { if (!k.dt0_keep) dst[id] = src[id]; return; }                              // :201-206 (:477-478)
+    if (dt <= R(0)) {
+        if (!k.dt0_keep) { dst[id] = src[id]; return; }                                          // gts_cacheDisabled, :201-206
+        /* gts_cacheEnabled: the disabled-cell copy comes first (:449-454), then the return without a write (:477-478) */
+        const Vec4<R> c0 = src[id];
+        if (c0.y <= R(-9999.0) || c0.x == R(-9999.0)) dst[id] = c0;
+        return;
+    }
     Vec4<R> c = src[id];
     const R zb = bed[id];
     if (c.y <= R(-9999.0) || c.x == R(-9999.0)) { dst[id] = c; return; }                         // :214-218

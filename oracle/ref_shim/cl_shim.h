@@ -88,19 +88,29 @@ typedef shim_v8<SHIM_REAL> cl_double8;
 #define __global
 #define __constant
 #define __private
-#define __local
+/* Work-group local memory: one copy per host thread, alive across the work-items a thread runs one after the other
+ * (every __local in the reference is a function-scope array). */
+#define __local static thread_local
 #define restrict __restrict__
 #define CLK_LOCAL_MEM_FENCE 0
-inline void barrier(int) {}
+/* Barriers.  The kernels normally run with work-groups of ONE item, where a barrier is nothing.  The kernels that stage
+ * a tile in local memory (gts_cacheEnabled, ine_cacheEnabled: one barrier, and everything before it only LOADS into local
+ * memory) are run a work-group at a time in two passes (ref_unit.inc: ndrange2_tiles): pass 1 takes every work-item up
+ * to the barrier, where it leaves the kernel; pass 2 runs every work-item from the top with the barrier a no-op -- the
+ * repeated loads store the same values again. */
+extern thread_local int shim_barrier_leaves;
+struct shim_barrier_hit {};
+inline void barrier(int) { if (shim_barrier_leaves) throw shim_barrier_hit(); }
 
-/* ---- work-item functions: one work-item per call, work-groups of one ------------------- */
-extern thread_local int64_t shim_gid[3];
+/* ---- work-item functions: one work-item per call; work-groups of one unless ndrange2_tiles says otherwise ---------- */
+extern thread_local int64_t shim_gid[3], shim_lid[3], shim_lsize[3], shim_grp[3];
+extern thread_local int shim_tiled;          /* inside ndrange2_tiles: real work-groups */
 extern int64_t shim_gsize[3];
 inline int64_t get_global_id(int d) { return shim_gid[d]; }
 inline int64_t get_global_size(int d) { return shim_gsize[d]; }
-inline int64_t get_local_id(int) { return 0; }
-inline int64_t get_local_size(int) { return 1; }
-inline int64_t get_group_id(int d) { return shim_gid[d]; }
+inline int64_t get_local_id(int d) { return shim_lid[d]; }
+inline int64_t get_local_size(int d) { return shim_lsize[d]; }
+inline int64_t get_group_id(int d) { return shim_tiled ? shim_grp[d] : shim_gid[d]; }
 
 /* ---- maths built-ins -------------------------------------------------------------------- */
 using std::sqrt; using std::pow; using std::fabs; using std::floor; using std::fmod;
@@ -135,7 +145,7 @@ extern cl_double shim_delta, shim_very_small, shim_quite_small, shim_courant, sh
 #define REQD_WG_SIZE_FULL_TS
 #define REQD_WG_SIZE_HALF_TS
 #define REQD_WG_SIZE_LINE
-/* local-tile extents of the cached kernel variants (compiled, never run here) */
+/* local-tile extents of the cached kernel variants (the work-group size ndrange2_tiles runs them with) */
 #define GTS_DIM1 16
 #define GTS_DIM2 16
 #define MCH_STG1_DIM1 16

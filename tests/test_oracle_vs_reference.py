@@ -167,3 +167,87 @@ def test_godunov_dt0_keep_rule():
     np.testing.assert_array_equal(b1, b0)
     assert not np.array_equal(a1, b1)                          # ... so the older buffer stays one step behind
     assert s_keep["time"] == s_copy["time"] == 0.25
+
+
+@pytest.mark.parametrize("precision", ["double", "single"])
+@pytest.mark.parametrize("scheme", ["godunov", "inertial"])
+def test_local_memory_kernels_of_the_reference(scheme, precision):
+    """gts_cacheEnabled / ine_cacheEnabled -- the reference's step kernels with the tile staged in work-group local memory
+    -- run through the shim a work-group at a time (16 x 16 items, groups overlapping by two cells, one barrier;
+    oracle/ref_shim/ref_unit.inc: ndrange2_tiles).  They are alternative implementations of the same maths: with a
+    positive timestep bit-identical to the oracle.  With a timestep <= 0 both copy disabled cells through and leave every
+    other cell untouched (CLSchemeGodunov.clc:449-454, 477-478; CLSchemeInertial.clc:215-241), where gts_cacheDisabled
+    copies the whole interior (:201-206; the oracle restates the other rule under HPO_QUIRK_GODUNOV_DT0_KEEP) and
+    ine_cacheDisabled returns before even the disabled-cell copy (CLSchemeInertial.clc:60-61 -- no switch for that one: a
+    disabled cell holds the same values in both ping-pong buffers anyway).  Sizes that are not a multiple of the 14 cells
+    a group updates; the destination starts as the source with the interior levels moved, so that "left untouched" and
+    "copied through" are both visible."""
+    rows, cols = 61, 83
+    cfg = make_cfg(scheme, precision, rows, cols)
+    cfg_keep = make_cfg(scheme, precision, rows, cols)
+    cfg_keep.quirks |= hc.QUIRK_GODUNOV_DT0_KEEP
+    orc, ref = _pair(cfg)
+    orc_keep = cpu_sim.CpuSim("oracle", cfg_keep)
+    dt = dtype_of(precision)
+    for seed in (1, 2):
+        bed, st, man = scenario("wetdry", rows, cols, dt, seed)
+        off = (st[..., 1] <= -9999.0) | (st[..., 0] == -9999.0)
+        inner = np.zeros(off.shape, bool)
+        inner[1:-1, 1:-1] = True
+        assert (off & inner).any()                                        # disabled cells inside the domain
+        start = st.copy()
+        start[1:-1, 1:-1, 0] += 1.0
+        for step_dt in (0.05, 0.0, -0.01):
+            d_ref, d_orc, d_keep = start.copy(), start.copy(), start.copy()
+            ref.k_step_cached(step_dt, bed, st, d_ref, man)
+            orc.k_step(step_dt, bed, st, d_orc, man)
+            orc_keep.k_step(step_dt, bed, st, d_keep, man)
+            if step_dt > 0:
+                _same(d_orc, d_ref)
+                _same(d_keep, d_ref)
+                assert (d_ref != start).any()
+                continue
+            expected = start.copy()
+            expected[off & inner] = st[off & inner]                       # disabled cells copied, the rest untouched
+            _same(d_ref, expected)
+            if scheme == "godunov":
+                _same(d_keep, d_ref)                                      # the quirk IS the local-memory kernel's rule
+                assert not np.array_equal(d_orc, d_ref)                   # gts_cacheDisabled copied the interior through
+            else:
+                _same(d_orc, start)                                       # ine_cacheDisabled wrote nothing at all
+    orc_keep.close()
+
+
+@pytest.mark.parametrize("precision", ["double", "single"])
+def test_local_memory_predictor_of_the_reference(precision):
+    """mch_1st_cachePrediction (the MUSCL-Hancock predictor with its tile in work-group local memory,
+    CLSchemeMUSCLHancock.clc:158-) through the same work-group emulation: the four face buffers are bit-identical to the
+    oracle's (and so to mch_1st_cacheNone's), for a positive and for a non-positive timestep -- except next to DISABLED
+    cells: the local tile carries the bed elevation in the slot of eta_max (:199-200), so the variant's "is a neighbour
+    disabled" test (:246-251, and the one inside mch_1st) reads a bed where mch_1st_cacheNone reads eta_max, and keeps the
+    second-order predictor where the default kernel falls back to the cell's own state.  One more reason (with SURVEY Q3)
+    why the oracle follows the default pair mch_1st_cacheNone + mch_2nd_cacheNone."""
+    from hipims_ocl_b200 import scenarios as sc
+    rows, cols = 57, 66
+    cfg = make_cfg("muscl-hancock", precision, rows, cols)
+    orc, ref = _pair(cfg)
+    dt = dtype_of(precision)
+    for seed in (4, 5):
+        for disabled in (False, True):
+            bed, st, man = sc.random_wet_dry(rows, cols, seed, dtype=dt, disabled=disabled)
+            off = st[..., 1] <= -9999.0
+            near = np.zeros_like(off)
+            near[1:, :] |= off[:-1, :]; near[:-1, :] |= off[1:, :]; near[:, 1:] |= off[:, :-1]; near[:, :-1] |= off[:, 1:]
+            for step_dt in (0.03, 0.0):
+                f_o = [np.full_like(st, -5.0) for _ in range(4)]
+                f_r = [np.full_like(st, -5.0) for _ in range(4)]
+                orc.k_mch_1st(step_dt, bed, st, f_o)
+                ref.k_mch_1st_cached(step_dt, bed, st, f_r)
+                for a, b in zip(f_o, f_r):
+                    differs = (a != b).any(axis=2)
+                    if disabled:
+                        assert not (differs & ~(near | off)).any()       # only beside (or on) disabled cells
+                    else:
+                        assert not differs.any()
+                if step_dt > 0:
+                    assert (f_o[0] != -5.0).any()

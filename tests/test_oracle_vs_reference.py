@@ -143,8 +143,8 @@ def test_sync_point_suspension_and_update():
 def test_godunov_dt0_keep_rule():
     """The two Godunov kernels of the reference differ in one observable rule: with a timestep <= 0 gts_cacheDisabled
     copies the source cell into the destination (CLSchemeGodunov.clc:201-206), gts_cacheEnabled returns before any write
-    (:477-478).  The oracle restates both (HPO_QUIRK_GODUNOV_DT0_KEEP selects the second); only the first is pinned to the
-    compiled reference -- gts_cacheEnabled needs work-group local memory, which the CPU shim does not emulate."""
+    (:477-478).  The oracle restates both (HPO_QUIRK_GODUNOV_DT0_KEEP selects the second); both are pinned to the compiled
+    reference kernels, the second in test_local_memory_kernels_of_the_reference.  Here: what the rule does to a run."""
     n = 40
     bed, st, man = scenario("dambreak", n, n, np.float64)
     out = {}

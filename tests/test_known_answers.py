@@ -1,6 +1,8 @@
 """Known-answer tests in the spirit of the reference's own test material (SURVEY.md 4 / 8c,
 tools/model-builder/tests/): they bound the PHYSICAL error of the schemes, where the parity tests bound the
-difference to the reference's arithmetic.
+difference to the reference's arithmetic.  Of the reference's four test cases three are here (sloshing bowl, lake at rest,
+dam break over an emerging bed); the fourth compares with laboratory gauges whose positions are not in the reference
+tree (TestDamBreakAgainstObstacle.js, Soares-Frazao and Zech 2007).
 
 Sloshing parabolic bowl (TestSloshingBowl.js, Wang et al. 2011; frictionless Thacker solution): a planar free surface
 circulates in the paraboloid z = h0 (x^2 + y^2) / a^2 with period 2 pi / S, S = sqrt(2 g h0) / a:
@@ -67,6 +69,76 @@ def test_sloshing_bowl_oracle():
         assert coarse < BOUNDS[scheme][0] and fine[scheme] < BOUNDS[scheme][1] and fine[scheme] < 0.7 * coarse     # converges
         assert drift_c < 1e-9 and drift_f < 1e-9          # closed basin, dry rim: volume is conserved
     assert fine["muscl-hancock"] < fine["godunov"]        # "normally requires MUSCL-Hancock" (TestSloshingBowl.js)
+
+
+def test_lake_at_rest_oracle():
+    """TestLakeAtRest.js (adapted from Xing et al. 2010): a smooth island z = max(i - b r^2 / a^2, n - s) in a lake at level
+    n, no friction -- "no change in water level should occur".  The schemes are well balanced over wet and dry cells
+    alike: after 300 iterations the level has not moved by a single bit and no discharge has appeared, for all three
+    schemes.  (Shape and scaling factors, levels and depth as in the script: a = 2000, b = 5000, n = 0, i = 100, s = 50.)"""
+    n, half = 120, 600.0
+    d = 2 * half / n
+    xs = (np.arange(n) + 0.5) * d - half
+    x, y = np.meshgrid(xs, xs)
+    bed = np.maximum(100.0 - 5000.0 * (x ** 2 + y ** 2) / 2000.0 ** 2, 0.0 - 50.0)
+    eta = np.where(0.0 > bed, 0.0, bed)
+    assert 0.1 < (eta > bed).mean() < 0.95                       # an island AND a lake
+    for scheme in ("godunov", "muscl-hancock", "inertial"):
+        st = np.zeros((n, n, 4))
+        st[..., 0] = st[..., 1] = eta
+        sim = cpu_sim.CpuSim("oracle", make_cfg(scheme, "double", n, n, delta=d, friction=False, end_time=1.0e6))
+        sim.upload(st, bed, np.zeros((n, n)))
+        sim.set_target(1.0e6)
+        sim.iterate(300)
+        out, stats = sim.download(), sim.stats()
+        sim.close()
+        assert stats["batch_successful"] == 300 and stats["time"] > 1.0
+        np.testing.assert_array_equal(out[..., 0], eta)
+        assert not out[..., 2:].any()
+
+
+def emerging_bed_front(scheme, dx, t_end=2.0, slope=np.pi / 60.0, wall=2.0, dam=1.0):
+    """TestDamBreakEmergingBed.js: bed z = x tan(a) between walls, water at level `dam` behind x = 0, no friction; returns
+    the x of the wet front along the centre line at t_end."""
+    xmin, xmax, ny = -15.0, 15.0, 12
+    nx = int(round((xmax - xmin) / dx))
+    xs = xmin + (np.arange(nx) + 0.5) * dx
+    x = np.tile(xs, (ny, 1))
+    bed = x * np.tan(slope)
+    edge = np.zeros(bed.shape, bool)
+    edge[:, :2] = edge[:, -2:] = True
+    edge[:2, :] = edge[-2:, :] = True
+    bed = np.where(edge, wall, bed)                              # the script raises everything within 1.1 cells of the extent
+    depth = np.where((x <= 0.0) & (dam > bed), dam - bed, 0.0)
+    st = np.zeros((ny, nx, 4))
+    st[..., 0] = st[..., 1] = bed + depth
+    sim = cpu_sim.CpuSim("oracle", make_cfg(scheme, "double", ny, nx, delta=dx, friction=False, end_time=t_end))
+    sim.upload(st, bed, np.zeros_like(bed))
+    sim.set_target(t_end)
+    while sim.stats()["time"] < t_end - 1e-6:
+        sim.iterate(16)
+    out = sim.download()
+    sim.close()
+    wet = np.nonzero(out[ny // 2, :, 0] - bed[ny // 2] > 1e-6)[0]
+    return xs[wet.max()] + dx / 2
+
+
+def test_dam_break_over_an_emerging_bed_oracle():
+    """TestDamBreakEmergingBed.js (Xing et al. 2010): the TIP of a dam-break wave running up a 3-degree slope is at
+    x = 2 t sqrt(g h0 cos a) - g t^2 tan(a) / 2.  That tip has no depth; a finite-volume front with a positivity-preserving
+    reconstruction trails it (the reference's script only paints the expected front next to the result).  What can be
+    asserted: the front is behind the tip but has covered most of the way, the second-order scheme is ahead of the
+    first-order one, and refining the grid moves both towards the tip.  Measured at t = 2 s (tip at 11.49 m):
+    Godunov 7.8 / 8.2 m and MUSCL-Hancock 8.1 / 8.6 m at 0.1 / 0.05 m cells."""
+    t_end = 2.0
+    tip = 2 * t_end * np.sqrt(G * 1.0 * np.cos(np.pi / 60.0)) - 0.5 * G * t_end ** 2 * np.tan(np.pi / 60.0)
+    front = {(s, dx): emerging_bed_front(s, dx, t_end) for s in ("godunov", "muscl-hancock") for dx in (0.1, 0.05)}
+    for (s, dx), xf in front.items():
+        assert 0.6 * tip < xf < tip, (s, dx, xf, tip)
+    for dx in (0.1, 0.05):
+        assert front[("muscl-hancock", dx)] > front[("godunov", dx)]
+    for s in ("godunov", "muscl-hancock"):
+        assert front[(s, 0.05)] > front[(s, 0.1)]
 
 
 @pytest.mark.gpu

@@ -1,7 +1,7 @@
 /*
  * hipims_cuda.h -- C ABI of the B200 executor for the HiPIMS explicit cell-update path.
  *
- * This library replaces the reference's OpenCL executor layer (src/OpenCL/Executors/*:
+ * This library replaces the reference's OpenCL executor layer (src/OpenCL/Executors/ --
  * CExecutorControlOpenCL, COCLDevice, COCLProgram, COCLKernel, COCLBuffer and the
  * runtime-compiled .clc sources) underneath the scheme / domain / boundary classes.  The entry
  * points are what CSchemeGodunov / CSchemeMUSCLHancock / CSchemeInertial, CBoundaryCell /

@@ -1461,6 +1461,7 @@ void hph_model_loop_state(void* h, unsigned int* syncs, unsigned int* outputs, d
     *syncs = m->getSyncCount(); *outputs = m->getOutputCount(); *target = m->getTargetTime(); *last_sync = m->getLastSyncTime();
     *current = m->getCurrentTime(); *sync_method = m->getSyncMethod();
 }
+double hph_model_next_target(void* h, double last_sync) { return static_cast<CModel*>(h)->proposeTargetAfterSyncAt(last_sync); }
 void hph_model_set_realtime_queue(void* h, int on) { static_cast<CModel*>(h)->setRealTimeQueue(on != 0); }
 // rollback: put the host arrays and clock back on the device, then report the recomputed timestep
 double hph_model_rollback(void* h, double time, double target) {

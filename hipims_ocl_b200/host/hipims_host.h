@@ -340,6 +340,8 @@ class CModel {
     double getCurrentTime() const { return dCurrentTime; }
     double getTargetTime() const { return dTargetTime; }
     double getLastSyncTime() const { return dLastSyncTime; }
+    // the target the loop would set after a synchronisation at `dTime` (runModelUpdateTarget on its own: host arithmetic)
+    double proposeTargetAfterSyncAt(double dTime) { dLastSyncTime = dTime; dCurrentTime = dTime; runModelUpdateTarget(dTime); return dTargetTime; }
     unsigned int getSyncCount() const { return uiSyncCount; }
     unsigned int getOutputCount() const { return uiOutputCount; }
     // pass wall-clock time to CScheme::runSimulation so that queueMode="auto" sizes batches for about a second of work

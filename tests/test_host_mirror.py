@@ -619,6 +619,24 @@ def test_sync_method_is_parsed(host, model_dir):
     host.hph_model_destroy(C.c_void_p(h))
 
 
+@pytest.mark.parametrize("duration,outfreq,syncs,targets", [
+    (30, 10, [0, 10, 20, 30], [10, 20, 30, 30]),            # outputs divide the run
+    (25, 10, [0, 10, 20, 25], [10, 20, 25, 25]),            # ... or not: the last target is the end of the simulation
+    (30, 45, [0, 30], [30, 30]),                            # no output interval inside the run
+    (7200, 600, [0, 599.999999, 600, 6600], [600, 600, 1200, 7200]),
+])
+def test_targets_follow_the_output_interval(host, model_dir, duration, outfreq, syncs, targets):
+    """CModel::runModelUpdateTarget (src/CModel.cpp:718-770) for one domain: the end of the simulation, but never across
+    the next multiple of the output frequency after the last synchronisation (:741-744)."""
+    host.hph_model_next_target.restype = C.c_double
+    host.hph_model_next_target.argtypes = [C.c_void_p, C.c_double]
+    cfg, _ = model_dir(duration=duration, outfreq=outfreq)
+    h = host.hph_model_load(cfg.encode(), 1)
+    assert h
+    assert [host.hph_model_next_target(C.c_void_p(h), float(t)) for t in syncs] == [float(t) for t in targets]
+    host.hph_model_destroy(C.c_void_p(h))
+
+
 @pytest.mark.gpu
 def test_management_loop_follows_the_reference(host, model_dir):
     """CModel::runModelMain (src/CModel.cpp:1041-1139): the first pass synchronises at t = 0 and sets the first target, every
